@@ -1,0 +1,645 @@
+// drc_b200 -- per-robot stages of the control cycle (one robot per thread).
+//
+// Stage "robot_job": updateState (reference robot_data.cpp:91-124) and everything that only needs
+// the robot's own kinematics: frame getters (:378-422), manipulability (:519-573), task-space error
+// (math_type_define.h:633-645), CLIK / OSF (robot_controller.cpp:156-171,208-247), joint PD torque
+// (:115-125) and the QPIK / QPID problem records (QP_IK.cpp:69-131, QP_ID.cpp:92-193).
+// Stage "collision_job": min self-distance + gradients (robot_data.cpp:424-517) -> dense row 1.
+// The template FLAGS select which parts a kernel instantiation contains.
+#pragma once
+#include "drc_geom.h"
+#include "drc_kin.h"
+#include "drc_qp.h"
+#include <type_traits>
+
+namespace drc {
+
+enum JobFlags : unsigned {
+  F_DYN = 1u << 0,        // M, Minv, g, nle -> cache
+  F_STORE = 1u << 1,      // q, qd, oMi -> cache
+  F_FROM_CACHE = 1u << 2, // read q, qd from the cache instead of the inputs
+  F_FRAME_OUT = 1u << 3,  // pose / J / Jdot / velocity outputs
+  F_MANIP_OUT = 1u << 4,  // manipulability outputs
+  F_QPIK = 1u << 5,
+  F_QPID = 1u << 6,
+  F_STEP = 1u << 7,       // desired task signal from (x_target, xdot_target) and the gains
+  F_CLIK = 1u << 8,
+  F_OSF = 1u << 9,
+  F_TORQUE = 1u << 10,    // moveJointTorqueStep(q_target, qdot_target)
+  F_GRADDOT = 1u << 11,   // manipulability gradient time variation
+};
+
+struct JobIO {
+  int B;
+  // inputs (any layout)
+  const double* q; Strided sq;
+  const double* qd; Strided sqd;
+  const double* x_target; Strided sxt;      // 12 per robot: top 3 rows of the homogeneous matrix
+  const double* xdot_target; Strided sxd;   // 6 per robot (target velocity, or the desired xdot / xddot)
+  const double* aux; Strided saux;          // n per robot: null-space vector (CLIK/OSF) or q_target (TORQUE)
+  const double* aux2; Strided saux2;        // n per robot: qdot_target (TORQUE)
+  // state cache (SoA, component stride Bc)
+  double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
+  long long Bc;
+  // outputs (any layout; null = skip)
+  double* pose; Strided spose;
+  double* J; Strided sJ;
+  double* Jdot; Strided sJd;
+  double* vel; Strided svel;
+  double* mani; double* mani_grad; Strided smg; double* mani_graddot; Strided smgd;
+  double* out; Strided sout;                // n per robot (CLIK qdot / OSF torque / PD torque)
+  double* out2;                             // OSF torque when CLIK and OSF run in one launch (same layout)
+  double* qp;                               // QP records (AoS, Cfg::STRIDE doubles per robot)
+};
+
+template <int NV>
+using QpikCfg = QpCfg<NV, 2, 2, 0, true, true>;
+template <int NV>
+using QpidCfg = QpCfg<NV, 4, 2, NV, true, true>;
+
+template <int NV, bool CHAIN, unsigned FLAGS>
+DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame& frame, const JobIO& io, int b) {
+  double q[NV], qd[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (FLAGS & F_FROM_CACHE) { q[i] = io.c_q[i * io.Bc + b]; qd[i] = io.c_qd[i * io.Bc + b]; }
+    else { q[i] = io.q[b * io.sq.sb + i * io.sq.sk]; qd[i] = io.qd[b * io.sqd.sb + i * io.sqd.sk]; }
+  }
+  KinState<NV> k;
+  k.origin = v3(0, 0, 0);
+  forward_kinematics<NV, CHAIN>(m, q, k);
+  Spatial v[NV];
+  joint_velocities<NV, CHAIN>(m, k, qd, v);
+
+  if (FLAGS & F_STORE) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      io.c_q[i * io.Bc + b] = q[i];
+      io.c_qd[i * io.Bc + b] = qd[i];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) io.c_oMi[(12 * i + 4 * r + c) * io.Bc + b] = k.R[i].m[3 * r + c];
+        io.c_oMi[(12 * i + 4 * r + 3) * io.Bc + b] = comp(k.p[i], r);
+      }
+    }
+  }
+
+  double M[NV * NV], g[NV], Minv[NV * NV];
+  constexpr bool need_dyn_vals = (FLAGS & (F_QPID | F_OSF | F_TORQUE)) != 0;
+  if (FLAGS & F_DYN) {
+    double nle[NV];
+    mass_matrix<NV, CHAIN>(m, k, M);
+    rnea_bias<NV, CHAIN>(m, k, v, false, qd, g);
+    rnea_bias<NV, CHAIN>(m, k, v, true, qd, nle);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      io.c_g[i * io.Bc + b] = g[i];
+      io.c_nle[i * io.Bc + b] = nle[i];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) io.c_M[(i * NV + j) * io.Bc + b] = M[i * NV + j];
+    }
+    spd_pinv<NV>(M, Minv, prm.pinv_threshold);
+#pragma unroll
+    for (int i = 0; i < NV * NV; ++i) io.c_Minv[i * io.Bc + b] = Minv[i];
+  } else if (need_dyn_vals) {
+    if (FLAGS & F_OSF) {
+#pragma unroll
+      for (int i = 0; i < NV * NV; ++i) Minv[i] = io.c_Minv[i * io.Bc + b];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      g[i] = io.c_g[i * io.Bc + b];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) M[i * NV + j] = io.c_M[(i * NV + j) * io.Bc + b];
+    }
+  }
+
+  if (FLAGS & F_TORQUE) {  // tau = M (Kp (q_t - q) + Kv (qd_t - qd)) + g
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      acc[i] = prm.Kp_joint[i] * (io.aux[b * io.saux.sb + i * io.saux.sk] - q[i]) +
+               prm.Kv_joint[i] * (io.aux2[b * io.saux2.sb + i * io.saux2.sk] - qd[i]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = g[i];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) s += M[i * NV + j] * acc[j];
+      io.out[b * io.sout.sb + i * io.sout.sk] = s;
+    }
+  }
+
+  constexpr bool need_frame = (FLAGS & (F_FRAME_OUT | F_MANIP_OUT | F_QPIK | F_QPID | F_CLIK | F_OSF)) != 0;
+  if (!need_frame) return;
+
+  Mat3 Rf;
+  Vec3 pf;
+  frame_pose<NV>(k, frame, Rf, pf);
+  double J[6 * NV];
+  point_jacobian<NV, CHAIN>(m, k, frame.parent, pf, J);
+  double Jd[6 * NV];
+  constexpr bool need_jdot = (FLAGS & (F_FRAME_OUT | F_QPID | F_GRADDOT)) != 0;
+  if (need_jdot) point_jacobian_dot<NV, CHAIN>(m, k, v, frame.parent, pf, Jd);
+  double xdot[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += J[r * NV + j] * qd[j];
+    xdot[r] = s;
+  }
+
+  if (FLAGS & F_FRAME_OUT) {
+    if (io.pose) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) io.pose[b * io.spose.sb + (4 * r + c) * io.spose.sk] = Rf.m[3 * r + c];
+        io.pose[b * io.spose.sb + (4 * r + 3) * io.spose.sk] = comp(pf, r);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6 * NV; ++i) {
+      if (io.J) io.J[b * io.sJ.sb + i * io.sJ.sk] = J[i];
+      if (io.Jdot) io.Jdot[b * io.sJd.sb + i * io.sJd.sk] = Jd[i];
+    }
+    if (io.vel) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) io.vel[b * io.svel.sb + r * io.svel.sk] = xdot[r];
+    }
+  }
+
+  // manipulability
+  double mani = 0, mgrad[NV], mgraddot[NV];
+  if (FLAGS & (F_MANIP_OUT | F_QPIK | F_QPID)) {
+    constexpr bool gd = (FLAGS & (F_QPID | F_GRADDOT)) != 0;
+    manipulability<NV, NV, CHAIN>(m, k, frame.parent, pf, J, Jd, 0, gd, prm.pinv_threshold, mani, mgrad, mgraddot);
+    if (FLAGS & F_MANIP_OUT) {
+      io.mani[b] = mani;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (io.mani_grad) io.mani_grad[b * io.smg.sb + i * io.smg.sk] = mgrad[i];
+        if (gd && io.mani_graddot) io.mani_graddot[b * io.smgd.sb + i * io.smgd.sk] = mgraddot[i];
+      }
+    }
+  }
+
+  // desired task-space signal
+  double des[6];
+  if (FLAGS & (F_QPIK | F_QPID | F_CLIK | F_OSF)) {
+    double xd_t[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) xd_t[r] = io.xdot_target[b * io.sxd.sb + r * io.sxd.sk];
+    if (FLAGS & F_STEP) {
+      Mat3 Rt;
+      Vec3 pt;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rt.m[3 * r + c] = io.x_target[b * io.sxt.sb + (4 * r + c) * io.sxt.sk];
+      }
+      pt = v3(io.x_target[b * io.sxt.sb + 3 * io.sxt.sk], io.x_target[b * io.sxt.sb + 7 * io.sxt.sk],
+              io.x_target[b * io.sxt.sb + 11 * io.sxt.sk]);
+      const Vec3 ep = pt - pf, eo = orientation_error(Rt, Rf);
+      const double xe[6] = {ep.x, ep.y, ep.z, eo.x, eo.y, eo.z};
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        // CLIKStep: Kp e + xdot_target (robot_controller.cpp:169); QPIK/QPID/OSF Step: Kp e + Kv edot (:238,:299,:342)
+        des[r] = prm.Kp_task[r] * xe[r] + ((FLAGS & F_CLIK) ? xd_t[r] : prm.Kv_task[r] * (xd_t[r] - xdot[r]));
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) des[r] = xd_t[r];
+    }
+  }
+
+  if (FLAGS & F_CLIK) {
+    // qdot = J+ des + (I - J+ J) null,  J+ = PinvCOD(J)
+    double Jp[NV * 6];
+    pinv_cpqr<6, NV>(J, Jp, prm.pinv_threshold);
+    double y[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = des[r];
+      if (io.aux) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s -= J[r * NV + j] * io.aux[b * io.saux.sb + j * io.saux.sk];
+      }
+      y[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = io.aux ? io.aux[b * io.saux.sb + i * io.saux.sk] : 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s += Jp[i * 6 + r] * y[r];
+      io.out[b * io.sout.sb + i * io.sout.sk] = s;
+    }
+  }
+
+  if (FLAGS & F_OSF) {
+    // Lambda = pinv(J Minv J^T); tau = J^T Lambda xddot + (I - J^T Lambda J Minv) tau_null + g
+    double JMi[6 * NV], Li[36], Lam[36];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        double s = 0;
+#pragma unroll
+        for (int l = 0; l < NV; ++l) s += J[r * NV + l] * Minv[l * NV + j];
+        JMi[r * NV + j] = s;
+      }
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s += JMi[r * NV + j] * J[c * NV + j];
+        Li[r * 6 + c] = s;
+      }
+    pinv_cpqr<6, 6>(Li, Lam, prm.pinv_threshold);
+    // F = Lambda (xddot - J Minv tau_null)
+    double y[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = des[r];
+      if (io.aux) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s -= JMi[r * NV + j] * io.aux[b * io.saux.sb + j * io.saux.sk];
+      }
+      y[r] = s;
+    }
+    double F[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = 0;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s += Lam[r * 6 + c] * y[c];
+      F[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = g[i] + (io.aux ? io.aux[b * io.saux.sb + i * io.saux.sk] : 0.0);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s += J[r * NV + i] * F[r];
+      double* o = (FLAGS & F_CLIK) ? io.out2 : io.out;  // fused CLIK+OSF: second output array
+      o[b * io.sout.sb + i * io.sout.sk] = s;
+    }
+  }
+
+  if (FLAGS & (F_QPIK | F_QPID)) {
+    constexpr bool ID = (FLAGS & F_QPID) != 0;
+    typedef typename std::conditional<ID, QpidCfg<NV>, QpikCfg<NV>>::type Cfg;
+    double* rec = io.qp + (long long)b * Cfg::STRIDE;
+    const double al = prm.alpha;
+    double rhs[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      double s = des[r];
+      if (ID) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s -= Jd[r * NV + j] * qd[j];
+      }
+      rhs[r] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int j = i; j < NV; ++j) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s += J[r * NV + i] * J[r * NV + j];
+        rec[Cfg::OFF_P + symidx<NV>(i, j)] = 2.0 * s + ((!ID && i == j) ? prm.ik_reg : 0.0);
+      }
+      double s = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) s += J[r * NV + i] * rhs[r];
+      rec[Cfg::OFF_Q + i] = -2.0 * s;
+      rec[Cfg::OFF_LO + i] = ID ? -kOsqpInfty : -m.v_lim[i];
+      rec[Cfg::OFF_HI + i] = ID ? kOsqpInfty : m.v_lim[i];
+      if (!ID) {
+        rec[Cfg::OFF_UNIT + 0 * NV + i] = -al * (q[i] - m.q_lo[i]);
+        rec[Cfg::OFF_UNIT + 1 * NV + i] = -al * (m.q_hi[i] - q[i]);
+      } else {
+        rec[Cfg::OFF_UNIT + 0 * NV + i] = -(al + al) * qd[i] - al * al * (q[i] - m.q_lo[i]);
+        rec[Cfg::OFF_UNIT + 1 * NV + i] = +(al + al) * qd[i] - al * al * (m.q_hi[i] - q[i]);
+        rec[Cfg::OFF_UNIT + 2 * NV + i] = -al * (qd[i] + m.v_lim[i]);
+        rec[Cfg::OFF_UNIT + 3 * NV + i] = -al * (m.v_lim[i] - qd[i]);
+      }
+    }
+    // dense row 0: singularity avoidance
+    double* row0 = rec + Cfg::OFF_ROW;
+    double gq = 0, gdq = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { row0[i] = mgrad[i]; gq += mgrad[i] * qd[i]; if (ID) gdq += mgraddot[i] * qd[i]; }
+    row0[NV] = ID ? (-gdq - (al + al) * gq - al * al * (mani - prm.mani_thresh)) : (-al * (mani - prm.mani_thresh));
+    // dense row 1 (self-collision) is written by collision_job
+    if (ID) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        double* row = rec + Cfg::OFF_ROW + (2 + i) * (NV + 1);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) row[j] = M[i * NV + j];
+        row[NV] = -g[i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Self-collision stage
+// ------------------------------------------------------------------------------------------------
+struct CollisionIO {
+  int B;
+  const double *c_q, *c_qd, *c_oMi;  // state cache (SoA, stride Bc)
+  long long Bc;
+  double* qp;                        // QP records; row written: dense row 1
+  int qp_stride, qp_row_off;         // Cfg::STRIDE, offset of dense row 1 inside the record
+  int mode;                          // 0 getter only, 1 QPIK row, 2 QPID row
+  double* dist; double* grad; Strided sgrad; double* grad_dot; Strided sgd;  // getter outputs (null = skip)
+  int* pair_out; double* witness;    // optional: argmin pair (reference order) and pa|pb (6, AoS)
+  // hand-over to the EPA kernel
+  int* epa_flag;                     // per robot: number of overlapping GJK pairs still to resolve
+  unsigned long long* cand_mask;     // per robot: bit i = GJK-type pair i must be resolved by EPA
+};
+
+struct JointFrame {
+  Mat3 R;
+  Vec3 p;
+};
+DRC_HD JointFrame load_joint_frame(const double* oMi, long long Bc, int b, int j) {
+  JointFrame f;
+  if (j < 0) { f.R = identity3(); f.p = v3(0, 0, 0); return f; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f.R.m[3 * r + c] = oMi[(12 * j + 4 * r + c) * Bc + b];
+  }
+  f.p = v3(oMi[(12 * j + 3) * Bc + b], oMi[(12 * j + 7) * Bc + b], oMi[(12 * j + 11) * Bc + b]);
+  return f;
+}
+// geometry g of the model, placed by the transform (R, p) applied to its joint-frame placement
+DRC_HD Prim place_prim(const DrcModelDev& m, int g, const Mat3& R, Vec3 p, bool identity) {
+  Prim s;
+  s.type = m.geom_type[g];
+  s.r = m.geom_prm[g][0]; s.h = m.geom_prm[g][1];
+  s.hb = v3(m.geom_prm[g][0], m.geom_prm[g][1], m.geom_prm[g][2]);
+  const Vec3 cl = v3(m.geom_p[g][0], m.geom_p[g][1], m.geom_p[g][2]);
+  const Vec3 al = v3(m.geom_R[g][2], m.geom_R[g][5], m.geom_R[g][8]);
+  if (identity) { s.c = cl; s.a = al; }
+  else { s.c = mul(R, cl) + p; s.a = mul(R, al); }
+  if (s.type == kBox) s.R = identity ? mat3_from(m.geom_R[g]) : mul(R, mat3_from(m.geom_R[g]));
+  else s.R = identity3();
+  return s;
+}
+
+struct BestPair {
+  double d;
+  int id;       // reference pair order (tie-break: smallest id wins, robot_data.cpp:434-443)
+  int ja, jb;
+  Vec3 pa, pb;  // in joint A's frame
+};
+DRC_HD void consider(BestPair& best, double d, int id, int ja, int jb, Vec3 pa, Vec3 pb) {
+  if (d < best.d || (d == best.d && id < best.id)) { best.d = d; best.id = id; best.ja = ja; best.jb = jb; best.pa = pa; best.pb = pb; }
+}
+
+// gradient (+ time variation) of the distance for the winning pair, then outputs / QP row
+template <int NV, bool CHAIN>
+DRC_HD void collision_finish(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b, const BestPair& best) {
+  // world witness points
+  const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, best.ja);
+  const Vec3 pA = mul(FA.R, best.pa) + FA.p, pB = mul(FA.R, best.pb) + FA.p;
+  const Vec3 dn = pB - pA;
+  const double ln = norm(dn);
+  const Vec3 n = ln > 1e-12 ? (1.0 / ln) * dn : v3(0, 0, 0);
+  double qd[NV];
+  Vec3 a[NV], p[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    qd[j] = io.c_qd[j * io.Bc + b];
+    const JointFrame Fj = load_joint_frame(io.c_oMi, io.Bc, b, j);
+    a[j] = mul(Fj.R, v3(m.axis[j][0], m.axis[j][1], m.axis[j][2]));
+    p[j] = Fj.p;
+  }
+  const bool with_gd = io.mode == 2 || io.grad_dot != nullptr;
+  // joint angular velocity w_j and origin velocity pd_j (for the time variation)
+  Vec3 w[NV], pd[NV];
+  Vec3 pAd = v3(0, 0, 0), pBd = v3(0, 0, 0);
+  if (with_gd) {
+    Vec3 vl[NV];  // spatial velocity (linear part at the origin)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int pr = parent_of<CHAIN>(m, j);
+      Vec3 sl, sa;
+      if (m.jtype[j] == kRevolute) { sl = cross(p[j], a[j]); sa = a[j]; } else { sl = a[j]; sa = v3(0, 0, 0); }
+      w[j] = qd[j] * sa; vl[j] = qd[j] * sl;
+      if (pr >= 0) { w[j] = w[j] + w[pr]; vl[j] = vl[j] + vl[pr]; }
+      pd[j] = vl[j] + cross(w[j], p[j]);
+    }
+    if (best.ja >= 0) pAd = vl[best.ja] + cross(w[best.ja], pA);
+    if (best.jb >= 0) pBd = vl[best.jb] + cross(w[best.jb], pB);
+  }
+  double grad[NV], gdot[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    Vec3 ja = v3(0, 0, 0), jb = v3(0, 0, 0), jad = v3(0, 0, 0), jbd = v3(0, 0, 0);
+    const bool rev = m.jtype[j] == kRevolute;
+    const bool onA = best.ja >= 0 && is_anc<CHAIN>(m, best.ja, j), onB = best.jb >= 0 && is_anc<CHAIN>(m, best.jb, j);
+    if (onA) ja = rev ? cross(a[j], pA - p[j]) : a[j];
+    if (onB) jb = rev ? cross(a[j], pB - p[j]) : a[j];
+    double gj = dot(n, jb - ja);
+    if (best.d < 0) gj = -gj;
+    grad[j] = gj;
+    if (with_gd) {
+      const Vec3 ad = cross(w[j], a[j]);
+      if (onA) jad = rev ? cross(ad, pA - p[j]) + cross(a[j], pAd - pd[j]) : ad;
+      if (onB) jbd = rev ? cross(ad, pB - p[j]) + cross(a[j], pBd - pd[j]) : ad;
+      gdot[j] = dot(n, jbd - jad);  // n_dot neglected, no sign flip (robot_data.cpp:513)
+    } else {
+      gdot[j] = 0;
+    }
+  }
+  if (io.dist) io.dist[b] = best.d;
+  if (io.pair_out) io.pair_out[b] = best.id;
+  if (io.witness) {
+    io.witness[6 * b + 0] = pA.x; io.witness[6 * b + 1] = pA.y; io.witness[6 * b + 2] = pA.z;
+    io.witness[6 * b + 3] = pB.x; io.witness[6 * b + 4] = pB.y; io.witness[6 * b + 5] = pB.z;
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (io.grad) io.grad[b * io.sgrad.sb + j * io.sgrad.sk] = grad[j];
+    if (io.grad_dot) io.grad_dot[b * io.sgd.sb + j * io.sgd.sk] = gdot[j];
+  }
+  if (io.mode != 0) {
+    double* row = io.qp + (long long)b * io.qp_stride + io.qp_row_off;
+    const double al = prm.alpha;
+    double gq = 0, gdq = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { row[j] = grad[j]; gq += grad[j] * qd[j]; gdq += gdot[j] * qd[j]; }
+    row[NV] = io.mode == 2 ? (-gdq - (al + al) * gq - al * al * (best.d - prm.dist_thresh)) : (-al * (best.d - prm.dist_thresh));
+  }
+}
+
+// Main self-distance pass.  Closed-form pairs are evaluated exactly; GJK-type pairs first by their
+// lower bound, then (only those that can still win) by GJK.  Pairs that overlap are deferred to
+// the EPA kernel through cand_mask / epa_flag; robots without deferred pairs are finished here.
+template <int NV, bool CHAIN>
+DRC_HD void collision_job(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b) {
+  BestPair best;
+  best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
+  unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair (model order) whose bound beats the current best
+  int gi = 0;
+  for (int grp = 0; grp < m.ngroup; ++grp) {
+    const int ja = m.group_ja[grp], jb = m.group_jb[grp];
+    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+    const Mat3 Rab = tmul(FA.R, FB.R);
+    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    for (int t = 0; t < m.group_count[grp]; ++t) {
+      const int k = m.group_first[grp] + t;
+      const int ga = m.pair_a[k], gb = m.pair_b[k];
+      const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
+      if (has_closed_form(A.type, Bp.type)) {
+        const PairResult r = closed_form_distance(A, Bp);
+        consider(best, r.d, m.pair_id[k], ja, jb, r.pa, r.pb);
+      } else {
+        if (gi < 64 && pair_lower_bound(A, Bp) <= best.d) cand |= 1ull << gi;
+        ++gi;
+      }
+    }
+  }
+  // GJK pass over the candidates (bounds re-tested against the improving best)
+  unsigned long long deferred = 0ull;
+  if (cand) {
+    gi = 0;
+    for (int grp = 0; grp < m.ngroup; ++grp) {
+      const int ja = m.group_ja[grp], jb = m.group_jb[grp];
+      bool loaded = false;
+      Mat3 Rab = identity3();
+      Vec3 pab = v3(0, 0, 0);
+      for (int t = 0; t < m.group_count[grp]; ++t) {
+        const int k = m.group_first[grp] + t;
+        const int ga = m.pair_a[k], gb = m.pair_b[k];
+        if (has_closed_form(m.geom_type[ga], m.geom_type[gb])) continue;
+        const int bit = gi++;
+        if (bit >= 64 || !((cand >> bit) & 1ull)) continue;
+        if (!loaded) {
+          const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+          Rab = tmul(FA.R, FB.R); pab = tmul(FA.R, FB.p - FA.p); loaded = true;
+        }
+        const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
+        if (pair_lower_bound(A, Bp) > best.d) continue;
+        GjkOut g;
+        gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+        if (g.intersect) deferred |= 1ull << bit;
+        else consider(best, g.dist, m.pair_id[k], ja, jb, g.pa, g.pb);
+      }
+    }
+  }
+  if (deferred) {
+    io.cand_mask[b] = deferred;
+    io.epa_flag[b] = 1;
+    // provisional result so that the EPA kernel can resume from the best separated pair
+    io.witness[6 * b + 0] = best.pa.x; io.witness[6 * b + 1] = best.pa.y; io.witness[6 * b + 2] = best.pa.z;
+    io.witness[6 * b + 3] = best.pb.x; io.witness[6 * b + 4] = best.pb.y; io.witness[6 * b + 5] = best.pb.z;
+    io.dist[b] = best.d;
+    io.pair_out[b] = best.id;
+    return;
+  }
+  io.epa_flag[b] = 0;
+  collision_finish<NV, CHAIN>(m, prm, io, b, best);
+}
+
+// EPA pass: only robots flagged by collision_job.
+template <int NV, bool CHAIN>
+DRC_HD void collision_epa_job(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b) {
+  if (!io.epa_flag[b]) return;
+  const unsigned long long deferred = io.cand_mask[b];
+  BestPair best;
+  best.d = io.dist[b]; best.id = io.pair_out[b];
+  best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
+  best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
+  best.ja = -1; best.jb = -1;
+  // recover the joints of the provisional best pair
+  for (int k = 0; k < m.npair; ++k)
+    if (m.pair_id[k] == best.id) { best.ja = m.geom_parent[m.pair_a[k]]; best.jb = m.geom_parent[m.pair_b[k]]; }
+  int gi = 0;
+  for (int grp = 0; grp < m.ngroup; ++grp) {
+    const int ja = m.group_ja[grp], jb = m.group_jb[grp];
+    for (int t = 0; t < m.group_count[grp]; ++t) {
+      const int k = m.group_first[grp] + t;
+      const int ga = m.pair_a[k], gb = m.pair_b[k];
+      if (has_closed_form(m.geom_type[ga], m.geom_type[gb])) continue;
+      const int bit = gi++;
+      if (bit >= 64 || !((deferred >> bit) & 1ull)) continue;
+      const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+      const Mat3 Rab = tmul(FA.R, FB.R);
+      const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+      const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
+      GjkOut g;
+      gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+      PairResult r;
+      r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+      if (g.intersect) epa_penetration(A, Bp, g, prm.epa_tol, prm.epa_max_iter, r);
+      consider(best, r.d, m.pair_id[k], ja, jb, r.pa, r.pb);
+    }
+  }
+  collision_finish<NV, CHAIN>(m, prm, io, b, best);
+}
+
+// ------------------------------------------------------------------------------------------------
+// QP solve + reference fallbacks (robot_controller.cpp:277-290: zeros on failure; :319-333: gravity)
+// ------------------------------------------------------------------------------------------------
+struct SolveIO {
+  int B;
+  const double* qp;
+  double* out; Strided sout;    // QPIK: qdot* (NC) | QPID: tau* (NC)
+  double* out2; Strided sout2;  // QPID: qddot* (optional)
+  int* status; int* iters;      // per robot (optional)
+  const double* c_g; long long Bc;  // gravity cache for the QPID fallback
+  double* qp_x;                 // optional debug: [core x (NC) | unit slacks (KU*NC) | row singletons (NR)] per robot
+};
+
+template <class Cfg, bool ID, class W>
+DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpOptions& o) {
+  admm_solve<Cfg>(w, io.qp, robots, o);
+  w.each([&](Lane<Cfg>& L, GroupShared<Cfg>& S) {
+    const int b = S.robot;
+    if (b < 0) return;
+    const bool ok = S.status == kQpSolved;
+    if (L.gl == 0) {
+      if (io.status) io.status[b] = S.status;
+      if (io.iters) io.iters[b] = S.iters;
+    }
+    if (L.is_core) {
+      const int j = L.gl;
+      const double xc = L.D * L.x;
+      if (!ID) io.out[b * io.sout.sb + j * io.sout.sk] = ok ? xc : 0.0;
+      else if (io.out2) io.out2[b * io.sout2.sb + j * io.sout2.sk] = ok ? xc : 0.0;
+      if (io.qp_x) {
+        double* xr = io.qp_x + (long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR);
+        xr[j] = xc;
+#pragma unroll
+        for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = L.ub[k].has_sing ? L.ub[k].Dd * L.ub[k].xd : 0.0;
+      }
+    } else {
+      const int r = L.gl - Cfg::NC;
+      if (ID && r >= Cfg::ND) {
+        const int j = r - Cfg::ND;
+        io.out[b * io.sout.sb + j * io.sout.sk] = ok ? L.rb.Dd * L.rb.xd : io.c_g[j * io.Bc + b];
+      }
+      if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = L.rb.has_sing ? L.rb.Dd * L.rb.xd : 0.0;
+    }
+  });
+}
+
+// lane -> (group, lane-in-group) assignment shared by the device kernel and the emulator
+template <class Cfg>
+DRC_HD void lane_assign(Lane<Cfg>& L, int lane) {
+  const int g = lane / Cfg::GL;
+  if (g < Cfg::NG) { L.grp = g; L.gl = lane - g * Cfg::GL; }
+  else { L.grp = 0; L.gl = -1; }
+  L.is_core = L.gl >= 0 && L.gl < Cfg::NC;
+}
+
+}  // namespace drc

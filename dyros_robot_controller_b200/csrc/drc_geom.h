@@ -1,0 +1,434 @@
+// drc_b200 -- per-thread narrow phase for primitive self-collision pairs (fp64).
+//
+// B200-native replacement of pinocchio::computeDistances -> hpp-fcl distance() as used by the
+// reference's getMinDistance (src/manipulator/robot_data.cpp:424-443).  All work is done in the
+// frame of the first shape's parent joint: shapes of link A are model constants, shapes of link B
+// are moved by the relative transform T_AB, so the pair loop touches no per-robot arrays.
+//   * sphere-X pairs: closed form (exact).
+//   * cylinder-cylinder / cylinder-box: certified LOWER BOUNDS first (capsule bound and a
+//     support-function bound); only pairs whose bound beats the best exact distance found so far
+//     run GJK (separated) and, if they overlap, EPA -- the minimum over all pairs is unchanged.
+#pragma once
+#include "drc_math.h"
+
+namespace drc {
+
+// A primitive placed in the working frame.
+struct Prim {
+  int type;
+  double r, h;   // sphere: r | cylinder/capsule: r, half length | box: unused (see hb)
+  Vec3 hb;       // box half extents
+  Vec3 c;        // centre
+  Vec3 a;        // cylinder / capsule axis (unit); box: unused
+  Mat3 R;        // box orientation (only valid for boxes)
+};
+
+struct PairResult {
+  double d;
+  Vec3 pa, pb;
+};
+
+DRC_HD Vec3 any_perp(Vec3 a) {  // some unit vector orthogonal to the unit vector a
+  Vec3 t = fabs(a.x) < 0.9 ? v3(1, 0, 0) : v3(0, 1, 0);
+  Vec3 p = cross(a, t);
+  return (1.0 / norm(p)) * p;
+}
+
+DRC_HD PairResult sphere_sphere(Vec3 c1, double r1, Vec3 c2, double r2) {
+  const Vec3 diff = c2 - c1;
+  const double len = norm(diff);
+  const Vec3 n = len > 0 ? (1.0 / len) * diff : v3(1, 0, 0);
+  return PairResult{len - r1 - r2, c1 + r1 * n, c2 - r2 * n};
+}
+
+// sphere (A) against a solid whose closest surface point q and signed centre distance sd are known
+DRC_HD PairResult sphere_vs_surface(Vec3 cs, double rs, Vec3 q, double sd) {
+  const Vec3 dir = q - cs;
+  const double len = norm(dir);
+  const Vec3 n = len > 0 ? (1.0 / len) * dir : v3(1, 0, 0);
+  PairResult r;
+  r.d = sd - rs;
+  r.pb = q;
+  r.pa = sd >= 0 ? cs + rs * n : cs - rs * n;
+  return r;
+}
+
+DRC_HD PairResult sphere_cylinder(Vec3 cs, double rs, const Prim& cy) {
+  const Vec3 x = cs - cy.c;
+  const double z = dot(x, cy.a);
+  const Vec3 rad = x - z * cy.a;
+  const double rho = norm(rad);
+  Vec3 q;
+  double sd;
+  if (fabs(z) <= cy.h && rho <= cy.r) {
+    const double dr = cy.r - rho, dz = cy.h - fabs(z);
+    if (dr < dz) {
+      const Vec3 u = rho > 0 ? (1.0 / rho) * rad : any_perp(cy.a);
+      q = cy.c + z * cy.a + cy.r * u;
+      sd = -dr;
+    } else {
+      q = cy.c + (z >= 0 ? cy.h : -cy.h) * cy.a + rad;
+      sd = -dz;
+    }
+  } else {
+    const double s = rho > cy.r ? cy.r / rho : 1.0;
+    const double zc = clampd(z, -cy.h, cy.h);
+    q = cy.c + zc * cy.a + s * rad;
+    sd = norm(cs - q);
+  }
+  return sphere_vs_surface(cs, rs, q, sd);
+}
+
+DRC_HD PairResult sphere_box(Vec3 cs, double rs, const Prim& bx) {
+  const Vec3 x = tmul(bx.R, cs - bx.c);
+  const double ax = fabs(x.x), ay = fabs(x.y), az = fabs(x.z);
+  Vec3 ql;
+  double sd;
+  if (ax <= bx.hb.x && ay <= bx.hb.y && az <= bx.hb.z) {
+    const double dx = bx.hb.x - ax, dy = bx.hb.y - ay, dz = bx.hb.z - az;
+    ql = x;
+    if (dx <= dy && dx <= dz) { ql.x = x.x >= 0 ? bx.hb.x : -bx.hb.x; sd = -dx; }
+    else if (dy <= dz) { ql.y = x.y >= 0 ? bx.hb.y : -bx.hb.y; sd = -dy; }
+    else { ql.z = x.z >= 0 ? bx.hb.z : -bx.hb.z; sd = -dz; }
+  } else {
+    ql = v3(clampd(x.x, -bx.hb.x, bx.hb.x), clampd(x.y, -bx.hb.y, bx.hb.y), clampd(x.z, -bx.hb.z, bx.hb.z));
+    sd = norm(x - ql);
+  }
+  return sphere_vs_surface(cs, rs, mul(bx.R, ql) + bx.c, sd);
+}
+
+// closest points of two segments p1 + s d1, p2 + t d2, s,t in [0,1]
+DRC_HD void segment_segment(Vec3 p1, Vec3 d1, Vec3 p2, Vec3 d2, double& s, double& t) {
+  const Vec3 r = p1 - p2;
+  const double a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+  const double eps = 1e-300;
+  if (a <= eps && e <= eps) { s = t = 0; return; }
+  if (a <= eps) { s = 0; t = clampd(f / e, 0.0, 1.0); return; }
+  const double c = dot(d1, r);
+  if (e <= eps) { t = 0; s = clampd(-c / a, 0.0, 1.0); return; }
+  const double b = dot(d1, d2), den = a * e - b * b;
+  s = den > 1e-14 * a * e ? clampd((b * f - c * e) / den, 0.0, 1.0) : 0.0;
+  t = (b * s + f) / e;
+  if (t < 0) { t = 0; s = clampd(-c / a, 0.0, 1.0); }
+  else if (t > 1) { t = 1; s = clampd((b - c) / a, 0.0, 1.0); }
+}
+
+DRC_HD PairResult capsule_capsule(const Prim& A, const Prim& B) {
+  double s, t;
+  segment_segment(A.c - A.h * A.a, (2 * A.h) * A.a, B.c - B.h * B.a, (2 * B.h) * B.a, s, t);
+  return sphere_sphere(A.c + ((2 * s - 1) * A.h) * A.a, A.r, B.c + ((2 * t - 1) * B.h) * B.a, B.r);
+}
+DRC_HD PairResult sphere_capsule(Vec3 cs, double rs, const Prim& cp) {
+  const double t = clampd(dot(cs - cp.c, cp.a), -cp.h, cp.h);
+  return sphere_sphere(cs, rs, cp.c + t * cp.a, cp.r);
+}
+
+// ---- support mapping and support width (about the centre) of a primitive
+DRC_HD Vec3 support(const Prim& S, Vec3 d) {
+  switch (S.type) {
+    case kSphere: {
+      const double n = norm(d);
+      return n > 0 ? S.c + (S.r / n) * d : S.c;
+    }
+    case kBox: {
+      const Vec3 dl = tmul(S.R, d);
+      return mul(S.R, v3(dl.x >= 0 ? S.hb.x : -S.hb.x, dl.y >= 0 ? S.hb.y : -S.hb.y, dl.z >= 0 ? S.hb.z : -S.hb.z)) + S.c;
+    }
+    case kCylinder: {
+      const double da = dot(d, S.a);
+      const Vec3 perp = d - da * S.a;
+      const double sg = norm(perp);
+      Vec3 s = S.c + (da >= 0 ? S.h : -S.h) * S.a;
+      if (sg > 0) s = s + (S.r / sg) * perp;
+      return s;
+    }
+    default: {  // capsule
+      const double n = norm(d);
+      Vec3 s = S.c + (dot(d, S.a) >= 0 ? S.h : -S.h) * S.a;
+      if (n > 0) s = s + (S.r / n) * d;
+      return s;
+    }
+  }
+}
+DRC_HD double support_width(const Prim& S, Vec3 n) {  // max over the shape of n.(x - c), |n| = 1
+  switch (S.type) {
+    case kSphere: return S.r;
+    case kBox: {
+      const Vec3 dl = tmul(S.R, n);
+      return S.hb.x * fabs(dl.x) + S.hb.y * fabs(dl.y) + S.hb.z * fabs(dl.z);
+    }
+    case kCylinder: {
+      const double da = dot(n, S.a);
+      return S.h * fabs(da) + S.r * sqrt(dmax(0.0, 1.0 - da * da));
+    }
+    default: return S.h * fabs(dot(n, S.a)) + S.r;
+  }
+}
+
+// Certified lower bound of the signed distance between two convex primitives, at least one of
+// which is a cylinder (the other a cylinder, capsule or box).
+DRC_HD double pair_lower_bound(const Prim& A, const Prim& B) {
+  // inner segments (a box is reduced to its centre with its circumscribed radius)
+  const double hA = A.type == kBox ? 0.0 : A.h, hB = B.type == kBox ? 0.0 : B.h;
+  const double rA = A.type == kBox ? norm(A.hb) : A.r, rB = B.type == kBox ? norm(B.hb) : B.r;
+  const Vec3 aA = A.type == kBox ? v3(0, 0, 1) : A.a, aB = B.type == kBox ? v3(0, 0, 1) : B.a;
+  double s, t;
+  segment_segment(A.c - hA * aA, (2 * hA) * aA, B.c - hB * aB, (2 * hB) * aB, s, t);
+  const Vec3 pA = A.c + ((2 * s - 1) * hA) * aA, pB = B.c + ((2 * t - 1) * hB) * aB;
+  const Vec3 dv = pB - pA;
+  const double dist = norm(dv);
+  double lb = dist - rA - rB;  // swept-sphere (capsule) bound
+  if (dist > 1e-12) {
+    const Vec3 n = (1.0 / dist) * dv;
+    lb = dmax(lb, dot(n, B.c - A.c) - support_width(A, n) - support_width(B, -n));
+  }
+  const Vec3 cc = B.c - A.c;
+  const double cl = norm(cc);
+  if (cl > 1e-12) {
+    const Vec3 n = (1.0 / cl) * cc;
+    lb = dmax(lb, cl - support_width(A, n) - support_width(B, -n));
+  }
+  return lb;
+}
+
+// ---------------------------------------------------------------- GJK
+struct SimplexVert {
+  Vec3 w, a, b;
+};
+
+DRC_HD void closest_segment(SimplexVert* v, int& n, double* lam) {
+  const Vec3 a = v[0].w, ab = v[1].w - v[0].w;
+  const double t = -dot(a, ab), den = dot(ab, ab);
+  if (t <= 0 || den <= 0) { n = 1; lam[0] = 1; return; }
+  if (t >= den) { v[0] = v[1]; n = 1; lam[0] = 1; return; }
+  lam[1] = t / den; lam[0] = 1 - lam[1];
+}
+DRC_HD void closest_triangle(SimplexVert* v, int& n, double* lam) {
+  const Vec3 a = v[0].w, b = v[1].w, c = v[2].w;
+  const Vec3 ab = b - a, ac = c - a;
+  const double d1 = -dot(ab, a), d2 = -dot(ac, a);
+  if (d1 <= 0 && d2 <= 0) { n = 1; lam[0] = 1; return; }
+  const double d3 = -dot(ab, b), d4 = -dot(ac, b);
+  if (d3 >= 0 && d4 <= d3) { v[0] = v[1]; n = 1; lam[0] = 1; return; }
+  const double vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { const double t = d1 / (d1 - d3); n = 2; lam[0] = 1 - t; lam[1] = t; return; }
+  const double d5 = -dot(ab, c), d6 = -dot(ac, c);
+  if (d6 >= 0 && d5 <= d6) { v[0] = v[2]; n = 1; lam[0] = 1; return; }
+  const double vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { const double t = d2 / (d2 - d6); v[1] = v[2]; n = 2; lam[0] = 1 - t; lam[1] = t; return; }
+  const double va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    const double t = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    v[0] = v[1]; v[1] = v[2]; n = 2; lam[0] = 1 - t; lam[1] = t; return;
+  }
+  const double den = 1.0 / (va + vb + vc);
+  lam[0] = va * den; lam[1] = vb * den; lam[2] = vc * den;
+}
+// true when the origin lies inside the tetrahedron
+DRC_HD bool closest_tetra(SimplexVert* v, int& n, double* lam) {
+  const int F[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
+  const int OPP[4] = {3, 1, 2, 0};
+  double best = 1e300;
+  SimplexVert bv[3];
+  double bl[3] = {0, 0, 0};
+  int bn = 0;
+  bool outside = false;
+  for (int f = 0; f < 4; ++f) {
+    const Vec3 a = v[F[f][0]].w, b = v[F[f][1]].w, c = v[F[f][2]].w, d = v[OPP[f]].w;
+    const Vec3 nrm = cross(b - a, c - a);
+    const double so = -dot(a, nrm), sd = dot(d - a, nrm);
+    if (so * sd < 0 || sd == 0) {
+      outside = true;
+      SimplexVert t[3] = {v[F[f][0]], v[F[f][1]], v[F[f][2]]};
+      double l[3] = {0, 0, 0};
+      int tn = 3;
+      closest_triangle(t, tn, l);
+      Vec3 p = v3(0, 0, 0);
+      for (int i = 0; i < tn; ++i) p = p + l[i] * t[i].w;
+      const double dd = dot(p, p);
+      if (dd < best) {
+        best = dd; bn = tn;
+        for (int i = 0; i < tn; ++i) { bv[i] = t[i]; bl[i] = l[i]; }
+      }
+    }
+  }
+  if (!outside) return true;
+  n = bn;
+  for (int i = 0; i < n; ++i) { v[i] = bv[i]; lam[i] = bl[i]; }
+  return false;
+}
+
+struct GjkOut {
+  bool intersect;
+  double dist;
+  Vec3 pa, pb;
+  SimplexVert sv[4];
+  int n, iters;
+};
+
+DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int max_iter, GjkOut& out) {
+  Vec3 d0 = B.c - A.c;
+  if (dot(d0, d0) == 0) d0 = v3(1, 0, 0);
+  SimplexVert* sv = out.sv;
+  double lam[4] = {1, 0, 0, 0};
+  int n = 1;
+  sv[0].a = support(A, d0); sv[0].b = support(B, -d0); sv[0].w = sv[0].a - sv[0].b;
+  Vec3 v = sv[0].w;
+  bool inter = false;
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    const double vv = dot(v, v);
+    if (vv <= 1e-30) { inter = true; break; }
+    SimplexVert nw;
+    nw.a = support(A, -v); nw.b = support(B, v); nw.w = nw.a - nw.b;
+    const double gap = vv - dot(v, nw.w);
+    if (gap <= tol * sqrt(vv)) break;
+    bool dup = false;
+    for (int i = 0; i < n; ++i) dup = dup || (norm2(sv[i].w - nw.w) <= 1e-30);
+    if (dup) break;
+    sv[n++] = nw;
+    bool inside = false;
+    if (n == 2) closest_segment(sv, n, lam);
+    else if (n == 3) closest_triangle(sv, n, lam);
+    else inside = closest_tetra(sv, n, lam);
+    if (inside) { lam[0] = lam[1] = lam[2] = lam[3] = 0.25; n = 4; inter = true; break; }
+    Vec3 nv = v3(0, 0, 0);
+    for (int i = 0; i < n; ++i) nv = nv + lam[i] * sv[i].w;
+    if (dot(nv, nv) >= vv) break;  // numerical floor
+    v = nv;
+  }
+  out.intersect = inter;
+  out.n = n;
+  out.iters = it + 1;
+  Vec3 pa = v3(0, 0, 0), pb = v3(0, 0, 0);
+  for (int i = 0; i < n; ++i) { pa = pa + lam[i] * sv[i].a; pb = pb + lam[i] * sv[i].b; }
+  out.pa = pa; out.pb = pb;
+  out.dist = inter ? 0.0 : norm(v);
+}
+
+// ---------------------------------------------------------------- EPA (fixed-capacity polytope)
+constexpr int kEpaMaxVert = 104, kEpaMaxFace = 208, kEpaMaxEdge = 64;
+struct EpaFace {
+  short v[3];
+  short alive;
+  Vec3 n;
+  double d;
+};
+
+DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out) {
+  SimplexVert P[kEpaMaxVert];
+  EpaFace F[kEpaMaxFace];
+  short E[kEpaMaxEdge][2];
+  int np = g.n, nf = 0;
+  for (int i = 0; i < np; ++i) P[i] = g.sv[i];
+  auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
+  auto distinct = [&](const SimplexVert& s) {
+    for (int i = 0; i < np; ++i) if (norm2(P[i].w - s.w) < 1e-20) return false;
+    return true;
+  };
+  const Vec3 axes[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
+  if (np == 1) {
+    for (int k = 0; k < 6; ++k) { SimplexVert s = sup(axes[k]); if (distinct(s)) { P[np++] = s; break; } }
+  }
+  if (np == 2) {
+    const Vec3 e = P[1].w - P[0].w;
+    Vec3 best = v3(0, 0, 0);
+    double bl = -1;
+    for (int k = 0; k < 6; ++k) {
+      const Vec3 c = cross(e, axes[k]);
+      if (dot(c, c) <= 1e-20) continue;
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const SimplexVert s = sup((double)sgn * c);
+        const double area = norm(cross(e, s.w - P[0].w));
+        if (area > bl) { bl = area; best = (double)sgn * c; }
+      }
+    }
+    P[np++] = sup(best);
+  }
+  if (np == 3) {
+    const Vec3 nrm = cross(P[1].w - P[0].w, P[2].w - P[0].w);
+    const SimplexVert s1 = sup(nrm), s2 = sup(-nrm);
+    const double h1 = fabs(dot(s1.w - P[0].w, nrm)), h2 = fabs(dot(s2.w - P[0].w, nrm));
+    P[np++] = h1 >= h2 ? s1 : s2;
+  }
+  out.d = 0; out.pa = g.pa; out.pb = g.pb;
+  if (np < 4) return;
+  auto add_face = [&](int a, int b, int c) {
+    if (nf >= kEpaMaxFace) return;
+    EpaFace& f = F[nf++];
+    f.v[0] = (short)a; f.v[1] = (short)b; f.v[2] = (short)c;
+    const Vec3 nrm = cross(P[b].w - P[a].w, P[c].w - P[a].w);
+    const double l = norm(nrm);
+    f.n = l > 0 ? (1.0 / l) * nrm : v3(0, 0, 1);
+    f.d = dot(f.n, P[a].w);
+    f.alive = l > 0 ? 1 : 0;
+  };
+  if (dot(cross(P[1].w - P[0].w, P[2].w - P[0].w), P[3].w - P[0].w) > 0) { SimplexVert t = P[1]; P[1] = P[2]; P[2] = t; }
+  add_face(0, 1, 2); add_face(0, 3, 1); add_face(0, 2, 3); add_face(1, 3, 2);
+  int bestf = -1;
+  for (int it = 0; it < max_iter; ++it) {
+    bestf = -1;
+    double bd = 1e300;
+    for (int i = 0; i < nf; ++i) if (F[i].alive && F[i].d < bd) { bd = F[i].d; bestf = i; }
+    if (bestf < 0) break;
+    const SimplexVert s = sup(F[bestf].n);
+    if (dot(F[bestf].n, s.w) - F[bestf].d <= tol) break;
+    if (np >= kEpaMaxVert) break;
+    const int idx = np;
+    P[np++] = s;
+    int ne = 0;
+    bool overflow = false;
+    for (int i = 0; i < nf; ++i) {
+      EpaFace& f = F[i];
+      if (!f.alive) continue;
+      if (dot(f.n, s.w - P[f.v[0]].w) > 0) {
+        f.alive = 0;
+        for (int e = 0; e < 3; ++e) {
+          const short a = f.v[e], b = f.v[(e + 1) % 3];
+          bool found = false;
+          for (int k = 0; k < ne; ++k)
+            if (E[k][0] == b && E[k][1] == a) { E[k][0] = E[ne - 1][0]; E[k][1] = E[ne - 1][1]; --ne; found = true; break; }
+          if (!found) { if (ne < kEpaMaxEdge) { E[ne][0] = a; E[ne][1] = b; ++ne; } else overflow = true; }
+        }
+      }
+    }
+    if (ne == 0 || overflow) break;
+    for (int k = 0; k < ne; ++k) add_face(E[k][0], E[k][1], idx);
+  }
+  if (bestf < 0) return;
+  const EpaFace& f = F[bestf];
+  const SimplexVert t0 = P[f.v[0]], t1 = P[f.v[1]], t2 = P[f.v[2]];
+  const Vec3 pr = f.d * f.n;
+  const Vec3 v0 = t1.w - t0.w, v1 = t2.w - t0.w, v2 = pr - t0.w;
+  const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+  const double den = d00 * d11 - d01 * d01;
+  const double l1 = den != 0 ? (d11 * d20 - d01 * d21) / den : 0.0, l2 = den != 0 ? (d00 * d21 - d01 * d20) / den : 0.0;
+  const double l0 = 1 - l1 - l2;
+  out.pa = l0 * t0.a + l1 * t1.a + l2 * t2.a;
+  out.pb = l0 * t0.b + l1 * t1.b + l2 * t2.b;
+  out.d = -f.d;
+}
+
+// ---------------------------------------------------------------- exact closed-form dispatcher
+DRC_HD bool has_closed_form(int ta, int tb) {
+  return ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule);
+}
+DRC_HD PairResult closed_form_distance(const Prim& A, const Prim& B) {
+  PairResult r;
+  if (A.type == kSphere) {
+    if (B.type == kSphere) r = sphere_sphere(A.c, A.r, B.c, B.r);
+    else if (B.type == kCylinder) r = sphere_cylinder(A.c, A.r, B);
+    else if (B.type == kBox) r = sphere_box(A.c, A.r, B);
+    else r = sphere_capsule(A.c, A.r, B);
+  } else if (B.type == kSphere) {
+    if (A.type == kCylinder) r = sphere_cylinder(B.c, B.r, A);
+    else if (A.type == kBox) r = sphere_box(B.c, B.r, A);
+    else r = sphere_capsule(B.c, B.r, A);
+    const Vec3 t = r.pa; r.pa = r.pb; r.pb = t;
+  } else {
+    r = capsule_capsule(A, B);
+  }
+  return r;
+}
+
+}  // namespace drc

@@ -1,0 +1,133 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of tests/kernel_emu/libdrc_emu.so (host emulation of the
+CUDA kernel bodies; see tests/kernel_emu/emu.cpp).  Never imported by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent / "kernel_emu"
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
+        _LIB = C.CDLL(str(_HERE / "libdrc_emu.so"))
+        _LIB.emu_create.restype = C.c_void_p
+    return _LIB
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _c(a, dt=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class Emu:
+    def __init__(self, urdf_path: str, srdf_path: str = ""):
+        L = lib()
+        urdf = Path(urdf_path).read_text()
+        srdf = Path(srdf_path).read_text() if srdf_path else ""
+        err = C.create_string_buffer(512)
+        h = L.emu_create(urdf.encode(), srdf.encode(), err, 512)
+        if not h:
+            raise RuntimeError(err.value.decode())
+        self.h = C.c_void_p(h)
+        self.nv = L.emu_nv(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().emu_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def frame_id(self, name):
+        return lib().emu_frame_id(self.h, name.encode())
+
+    def sizes(self):
+        out = np.zeros(6, np.int32)
+        nbytes = lib().emu_model_sizes(self.h, _i(out))
+        return dict(nv=int(out[0]), ngeom=int(out[1]), npair=int(out[2]), ngroup=int(out[3]), nframes=int(out[4]),
+                    skipped=int(out[5]), dev_bytes=int(nbytes))
+
+    def model_arrays(self):
+        s = self.sizes()
+        n, ng, npair, nf = s["nv"], s["ngeom"], s["npair"], s["nframes"]
+        a = dict(parent=np.zeros(n, np.int32), jtype=np.zeros(n, np.int32), axis=np.zeros((n, 3)), jR=np.zeros((n, 3, 3)),
+                 jp=np.zeros((n, 3)), mass=np.zeros(n), com=np.zeros((n, 3)), inertia6=np.zeros((n, 6)), q_lo=np.zeros(n),
+                 q_hi=np.zeros(n), v_lim=np.zeros(n), geom_type=np.zeros(ng, np.int32), geom_parent=np.zeros(ng, np.int32),
+                 geom_prm=np.zeros((ng, 3)), geom_R=np.zeros((ng, 3, 3)), geom_p=np.zeros((ng, 3)),
+                 pairs=np.zeros((npair, 2), np.int32), frame_parent=np.zeros(nf, np.int32), frame_R=np.zeros((nf, 3, 3)),
+                 frame_p=np.zeros((nf, 3)))
+        lib().emu_model_arrays(self.h, _i(a["parent"]), _i(a["jtype"]), _d(a["axis"]), _d(a["jR"]), _d(a["jp"]), _d(a["mass"]),
+                               _d(a["com"]), _d(a["inertia6"]), _d(a["q_lo"]), _d(a["q_hi"]), _d(a["v_lim"]),
+                               _i(a["geom_type"]), _i(a["geom_parent"]), _d(a["geom_prm"]), _d(a["geom_R"]), _d(a["geom_p"]),
+                               _i(a["pairs"]), _i(a["frame_parent"]), _d(a["frame_R"]), _d(a["frame_p"]))
+        return a
+
+    def set_params(self, kp_task=None, kv_task=None, kp_joint=None, kv_joint=None, adaptive_rho_interval=-1, max_iter=0,
+                   gjk_tol=0.0):
+        lib().emu_set_params(self.h, _d(_c(kp_task)), _d(_c(kv_task)), _d(_c(kp_joint)), _d(_c(kv_joint)),
+                             C.c_int(adaptive_rho_interval), C.c_int(max_iter), C.c_double(gjk_tol))
+
+    def update_and_get(self, q, qd, frame):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        o = dict(pose=np.zeros((B, 12)), J=np.zeros((B, 6, n)), Jdot=np.zeros((B, 6, n)), vel=np.zeros((B, 6)),
+                 M=np.zeros((B, n, n)), Minv=np.zeros((B, n, n)), g=np.zeros((B, n)), nle=np.zeros((B, n)),
+                 oMi=np.zeros((B, 12 * n)), mani=np.zeros(B), mgrad=np.zeros((B, n)), mgraddot=np.zeros((B, n)))
+        rc = lib().emu_update_and_get(self.h, C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(o["pose"]), _d(o["J"]),
+                                      _d(o["Jdot"]), _d(o["vel"]), _d(o["M"]), _d(o["Minv"]), _d(o["g"]), _d(o["nle"]),
+                                      _d(o["oMi"]), _d(o["mani"]), _d(o["mgrad"]), _d(o["mgraddot"]))
+        assert rc == 0
+        return o
+
+    def min_distance(self, q, qd):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        o = dict(d=np.zeros(B), grad=np.zeros((B, n)), grad_dot=np.zeros((B, n)), pair=np.zeros(B, np.int32),
+                 witness=np.zeros((B, 6)))
+        o["nepa"] = lib().emu_min_distance(self.h, C.c_int(B), _d(q), _d(qd), _d(o["d"]), _d(o["grad"]), _d(o["grad_dot"]),
+                                           _i(o["pair"]), _d(o["witness"]))
+        return o
+
+    def cycle(self, mode, q, qd, x_target, xdot_target, frame, want_records=False):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        xt = None if x_target is None else _c(x_target).reshape(B, 12)
+        xd = _c(xdot_target).reshape(B, 6)
+        ku, nr = (2, 2) if mode < 2 else (4, 2 + n)
+        o = dict(out=np.zeros((B, n)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
+                 x=np.zeros((B, n * (1 + ku) + nr)))
+        rec = np.zeros((B, lib().emu_qp_stride(C.c_int(mode)))) if want_records else None
+        rc = lib().emu_cycle(self.h, C.c_int(mode), C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), _d(o["out"]),
+                             _i(o["status"]), _i(o["iters"]), _d(o["x"]), _d(rec))
+        assert rc == 0
+        if want_records:
+            o["records"] = rec
+        return o
+
+    def taskspace(self, mode, q, qd, x_target, xdot_target, frame, aux=None, aux2=None):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        xt = None if x_target is None else _c(x_target).reshape(B, 12)
+        xd = None if xdot_target is None else _c(xdot_target).reshape(B, 6)
+        a1 = None if aux is None else _c(aux).reshape(B, n)
+        a2 = None if aux2 is None else _c(aux2).reshape(B, n)
+        out = np.zeros((B, n))
+        rc = lib().emu_taskspace(self.h, C.c_int(mode), C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), _d(a1),
+                                 _d(a2), _d(out))
+        assert rc == 0
+        return out

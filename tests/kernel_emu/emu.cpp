@@ -1,0 +1,231 @@
+// TEST INFRASTRUCTURE ONLY -- host emulation of the CUDA kernel bodies.
+//
+// The device code of dyros_robot_controller_b200/csrc (drc_kin.h, drc_geom.h, drc_qp.h, drc_cycle.h)
+// is written as host+device inlines; this file instantiates the SAME bodies with g++ and runs
+// thread-per-robot stages in a plain loop and warp-per-robot stages through WarpEmu (32 lanes
+// emulated sequentially, __syncwarp() == end of a lane loop).  It lets `pytest -m "not gpu"` check
+// kernel logic against the oracle in the CPU-only build container.
+// It is NOT part of the product: libdrc_b200.so never links it and the package never loads it.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../dyros_robot_controller_b200/csrc/drc_cycle.h"
+#include "../../dyros_robot_controller_b200/csrc/model.h"
+
+using namespace drc;
+
+struct EmuHandle {
+  HostModel hm;
+  DrcParams prm;
+};
+
+static DrcFrame make_frame(const HostModel& hm, int fid) {
+  DrcFrame f;
+  f.parent = hm.frames[fid].parent;
+  std::memcpy(f.R, hm.frames[fid].R, sizeof f.R);
+  std::memcpy(f.p, hm.frames[fid].p, sizeof f.p);
+  return f;
+}
+
+struct Cache {
+  std::vector<double> q, qd, oMi, M, Minv, g, nle;
+  long long Bc;
+  explicit Cache(int nv, int B) : q(nv * B), qd(nv * B), oMi(12 * nv * B), M(nv * nv * B), Minv(nv * nv * B), g(nv * B), nle(nv * B), Bc(B) {}
+  void bind(JobIO& io) {
+    io.c_q = q.data(); io.c_qd = qd.data(); io.c_oMi = oMi.data(); io.c_M = M.data(); io.c_Minv = Minv.data();
+    io.c_g = g.data(); io.c_nle = nle.data(); io.Bc = Bc;
+  }
+};
+
+template <int NV, bool CHAIN, unsigned FLAGS>
+static void run_job(const EmuHandle* h, const DrcFrame& fr, const JobIO& io) {
+  for (int b = 0; b < io.B; ++b) robot_job<NV, CHAIN, FLAGS>(h->hm.dev, h->prm, fr, io, b);
+}
+
+template <int NV, bool CHAIN>
+static void run_collision(const EmuHandle* h, CollisionIO& io, std::vector<int>& flag, std::vector<unsigned long long>& mask,
+                          std::vector<double>& dist, std::vector<int>& pair, std::vector<double>& wit) {
+  flag.assign(io.B, 0); mask.assign(io.B, 0ull);
+  if (!io.dist) { dist.assign(io.B, 0.0); io.dist = dist.data(); }
+  if (!io.pair_out) { pair.assign(io.B, 0); io.pair_out = pair.data(); }
+  if (!io.witness) { wit.assign(6 * (size_t)io.B, 0.0); io.witness = wit.data(); }
+  io.epa_flag = flag.data(); io.cand_mask = mask.data();
+  for (int b = 0; b < io.B; ++b) collision_job<NV, CHAIN>(h->hm.dev, h->prm, io, b);
+  for (int b = 0; b < io.B; ++b) collision_epa_job<NV, CHAIN>(h->hm.dev, h->prm, io, b);
+}
+
+template <class Cfg, bool ID>
+static void run_solve(const EmuHandle* h, const SolveIO& io, unsigned unit_mask) {
+  const QpOptions o = qp_options(h->prm, unit_mask);
+  std::vector<GroupShared<Cfg>> sh(Cfg::NG);
+  std::unique_ptr<WarpEmu<Cfg>> w(new WarpEmu<Cfg>);
+  for (int b0 = 0; b0 < io.B; b0 += Cfg::NG) {
+    int robots[8];
+    for (int g = 0; g < Cfg::NG; ++g) robots[g] = (b0 + g < io.B) ? b0 + g : -1;
+    w->sh = sh.data();
+    for (int t = 0; t < 32; ++t) lane_assign<Cfg>(w->Ls[t], t);
+    solve_and_emit<Cfg, ID>(*w, robots, io, o);
+  }
+}
+
+extern "C" {
+
+EmuHandle* emu_create(const char* urdf_text, const char* srdf_text, char* err, int errlen) {
+  try {
+    std::unique_ptr<EmuHandle> h(new EmuHandle);
+    h->hm = compile_model(urdf_text, srdf_text ? srdf_text : "");
+    for (int i = 0; i < kMaxV; ++i) { h->prm.Kp_joint[i] = 400; h->prm.Kv_joint[i] = 40; }
+    return h.release();
+  } catch (const std::exception& e) {
+    if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return nullptr;
+  }
+}
+void emu_destroy(EmuHandle* h) { delete h; }
+int emu_nv(EmuHandle* h) { return h->hm.dev.nv; }
+int emu_is_chain(EmuHandle* h) { return h->hm.chain ? 1 : 0; }
+int emu_frame_id(EmuHandle* h, const char* name) { return h->hm.frame_id(name); }
+int emu_model_sizes(EmuHandle* h, int* out) {
+  const DrcModelDev& d = h->hm.dev;
+  out[0] = d.nv; out[1] = d.ngeom; out[2] = d.npair; out[3] = d.ngroup; out[4] = (int)h->hm.frames.size(); out[5] = h->hm.skipped_geoms;
+  return (int)sizeof(DrcModelDev);
+}
+// flat copy of the compiled model for comparison with the oracle's independent loader
+void emu_model_arrays(EmuHandle* h, int* parent, int* jtype, double* axis, double* jR, double* jp, double* mass, double* com,
+                      double* inertia6, double* q_lo, double* q_hi, double* v_lim, int* geom_type, int* geom_parent,
+                      double* geom_prm, double* geom_R, double* geom_p, int* pairs_ref_order, int* frame_parent,
+                      double* frame_R, double* frame_p) {
+  const DrcModelDev& d = h->hm.dev;
+  for (int i = 0; i < d.nv; ++i) {
+    parent[i] = d.parent[i]; jtype[i] = d.jtype[i];
+    std::memcpy(axis + 3 * i, d.axis[i], 24); std::memcpy(jR + 9 * i, d.jR[i], 72); std::memcpy(jp + 3 * i, d.jp[i], 24);
+    mass[i] = d.mass[i]; std::memcpy(com + 3 * i, d.com[i], 24); std::memcpy(inertia6 + 6 * i, d.inertia[i], 48);
+    q_lo[i] = d.q_lo[i]; q_hi[i] = d.q_hi[i]; v_lim[i] = d.v_lim[i];
+  }
+  for (int g = 0; g < d.ngeom; ++g) {
+    geom_type[g] = d.geom_type[g]; geom_parent[g] = d.geom_parent[g];
+    std::memcpy(geom_prm + 3 * g, d.geom_prm[g], 24); std::memcpy(geom_R + 9 * g, d.geom_R[g], 72); std::memcpy(geom_p + 3 * g, d.geom_p[g], 24);
+  }
+  for (int k = 0; k < d.npair; ++k) { pairs_ref_order[2 * d.pair_id[k]] = d.pair_a[k]; pairs_ref_order[2 * d.pair_id[k] + 1] = d.pair_b[k]; }
+  for (size_t f = 0; f < h->hm.frames.size(); ++f) {
+    frame_parent[f] = h->hm.frames[f].parent;
+    std::memcpy(frame_R + 9 * f, h->hm.frames[f].R, 72); std::memcpy(frame_p + 3 * f, h->hm.frames[f].p, 24);
+  }
+}
+void emu_set_params(EmuHandle* h, const double* kp_task, const double* kv_task, const double* kp_joint, const double* kv_joint,
+                    int adaptive_rho_interval, int max_iter, double gjk_tol) {
+  if (kp_task) for (int i = 0; i < 6; ++i) { h->prm.Kp_task[i] = kp_task[i]; h->prm.Kv_task[i] = kv_task[i]; }
+  if (kp_joint) for (int i = 0; i < h->hm.dev.nv; ++i) { h->prm.Kp_joint[i] = kp_joint[i]; h->prm.Kv_joint[i] = kv_joint[i]; }
+  if (adaptive_rho_interval >= 0) h->prm.adaptive_rho_interval = adaptive_rho_interval;
+  if (max_iter > 0) h->prm.max_iter = max_iter;
+  if (gjk_tol > 0) { h->prm.gjk_tol = gjk_tol; h->prm.epa_tol = gjk_tol; }
+}
+
+// ---- stage: updateState + frame getters + manipulability (all arrays batch-major / AoS)
+int emu_update_and_get(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* J,
+                       double* Jdot, double* vel, double* M, double* Minv, double* g, double* nle, double* oMi,
+                       double* mani, double* mgrad, double* mgraddot) {
+  const int n = h->hm.dev.nv;
+  if (n != 7 || !h->hm.chain) return -1;
+  const DrcFrame fr = make_frame(h->hm, frame_id);
+  Cache c(n, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(n); io.qd = qd; io.sqd = aos(n);
+  c.bind(io);
+  io.pose = pose; io.spose = aos(12); io.J = J; io.sJ = aos(6 * n); io.Jdot = Jdot; io.sJd = aos(6 * n); io.vel = vel; io.svel = aos(6);
+  io.mani = mani; io.mani_grad = mgrad; io.smg = aos(n); io.mani_graddot = mgraddot; io.smgd = aos(n);
+  run_job<7, true, F_DYN | F_STORE | F_FRAME_OUT | F_MANIP_OUT | F_GRADDOT>(h, fr, io);
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < n * n; ++i) { if (M) M[b * n * n + i] = c.M[i * B + b]; if (Minv) Minv[b * n * n + i] = c.Minv[i * B + b]; }
+    for (int i = 0; i < n; ++i) { if (g) g[b * n + i] = c.g[i * B + b]; if (nle) nle[b * n + i] = c.nle[i * B + b]; }
+    if (oMi) for (int i = 0; i < 12 * n; ++i) oMi[b * 12 * n + i] = c.oMi[i * B + b];
+  }
+  return 0;
+}
+
+// ---- stage: min self-distance with gradients
+int emu_min_distance(EmuHandle* h, int B, const double* q, const double* qd, double* dist, double* grad, double* grad_dot,
+                     int* pair, double* witness) {
+  const int n = h->hm.dev.nv;
+  if (n != 7 || !h->hm.chain) return -1;
+  Cache c(n, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(n); io.qd = qd; io.sqd = aos(n);
+  c.bind(io);
+  DrcFrame fr = make_frame(h->hm, 0);
+  run_job<7, true, F_STORE>(h, fr, io);
+  CollisionIO cio;
+  std::memset(&cio, 0, sizeof cio);
+  cio.B = B; cio.c_q = c.q.data(); cio.c_qd = c.qd.data(); cio.c_oMi = c.oMi.data(); cio.Bc = B; cio.mode = 0;
+  cio.dist = dist; cio.grad = grad; cio.sgrad = aos(n); cio.grad_dot = grad_dot; cio.sgd = aos(n); cio.pair_out = pair; cio.witness = witness;
+  std::vector<int> flag, pr; std::vector<unsigned long long> mask; std::vector<double> ds, wt;
+  run_collision<7, true>(h, cio, flag, mask, ds, pr, wt);
+  int nepa = 0;
+  for (int b = 0; b < B; ++b) nepa += flag[b];
+  return nepa;
+}
+
+// ---- full control cycle: updateState + QPIKStep / QPIDStep (mode 1 / 3) or QPIK / QPID with the
+//      desired task signal given in xdot_target (mode 0 / 2)
+int emu_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records) {
+  const int n = h->hm.dev.nv;
+  if (n != 7 || !h->hm.chain) return -1;
+  const DrcFrame fr = make_frame(h->hm, frame_id);
+  Cache c(n, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(n); io.qd = qd; io.sqd = aos(n);
+  io.x_target = x_target; io.sxt = aos(12); io.xdot_target = xdot_target; io.sxd = aos(6);
+  c.bind(io);
+  const bool ID = mode >= 2;
+  const int stride = ID ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE;
+  std::vector<double> rec((size_t)stride * B, 0.0);
+  io.qp = rec.data();
+  if (mode == 0) run_job<7, true, F_DYN | F_STORE | F_QPIK>(h, fr, io);
+  else if (mode == 1) run_job<7, true, F_DYN | F_STORE | F_QPIK | F_STEP>(h, fr, io);
+  else if (mode == 2) run_job<7, true, F_DYN | F_STORE | F_QPID>(h, fr, io);
+  else run_job<7, true, F_DYN | F_STORE | F_QPID | F_STEP>(h, fr, io);
+  CollisionIO cio;
+  std::memset(&cio, 0, sizeof cio);
+  cio.B = B; cio.c_q = c.q.data(); cio.c_qd = c.qd.data(); cio.c_oMi = c.oMi.data(); cio.Bc = B;
+  cio.mode = ID ? 2 : 1; cio.qp = rec.data(); cio.qp_stride = stride;
+  cio.qp_row_off = (ID ? QpidCfg<7>::OFF_ROW : QpikCfg<7>::OFF_ROW) + (n + 1);
+  std::vector<int> flag, pr; std::vector<unsigned long long> mask; std::vector<double> ds, wt;
+  run_collision<7, true>(h, cio, flag, mask, ds, pr, wt);
+  if (qp_records) std::memcpy(qp_records, rec.data(), rec.size() * sizeof(double));
+  SolveIO sio;
+  std::memset(&sio, 0, sizeof sio);
+  sio.B = B; sio.qp = rec.data(); sio.out = out; sio.sout = aos(n); sio.status = status; sio.iters = iters;
+  sio.c_g = c.g.data(); sio.Bc = B; sio.qp_x = qp_x;
+  if (ID) run_solve<QpidCfg<7>, true>(h, sio, 0x7f);
+  else run_solve<QpikCfg<7>, false>(h, sio, 0x7f);
+  return 0;
+}
+int emu_qp_stride(int mode) { return mode >= 2 ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE; }
+
+// ---- CLIKStep (mode 0) / OSFStep (mode 1) / OSF (mode 2) / joint PD torque (mode 3: aux=q_t, aux2=qd_t)
+int emu_taskspace(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                  const double* xdot_target, const double* aux, const double* aux2, double* out) {
+  const int n = h->hm.dev.nv;
+  if (n != 7 || !h->hm.chain) return -1;
+  const DrcFrame fr = make_frame(h->hm, frame_id);
+  Cache c(n, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(n); io.qd = qd; io.sqd = aos(n);
+  io.x_target = x_target; io.sxt = aos(12); io.xdot_target = xdot_target; io.sxd = aos(6);
+  io.aux = aux; io.saux = aos(n); io.aux2 = aux2; io.saux2 = aos(n); io.out = out; io.sout = aos(n);
+  c.bind(io);
+  if (mode == 0) run_job<7, true, F_CLIK | F_STEP>(h, fr, io);
+  else if (mode == 1) run_job<7, true, F_DYN | F_OSF | F_STEP>(h, fr, io);
+  else if (mode == 2) run_job<7, true, F_DYN | F_OSF>(h, fr, io);
+  else run_job<7, true, F_DYN | F_TORQUE>(h, fr, io);
+  return 0;
+}
+
+}  // extern "C"
