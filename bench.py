@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""bench.py -- batched QP-IK control cycles/s (FR3, batch 65536 per GPU), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One "step" = one full control cycle for every robot of the batch:
+    RobotData::updateState  +  RobotController::QPIKStep   (reference call sequence)
+i.e. FK / Jacobians / CRBA / RNEA / M^-1 -> task error -> manipulability + self-collision rows ->
+23-variable / 39-row QP solved with OSQP's algorithm -> qdot* (zeros on failure).
+
+Printed JSON (one line, rank 0):
+  value      whole-job cycles/s with inputs resident in HBM, device-timed (CUDA events on the launch
+             stream, L2 flushed between steps, max over ranks)
+  e2e        the same metric through the host-buffer C-ABI call (drc_host_cycle_qpik_step): pinned
+             host inputs -> H2D -> kernels -> D2H inside the timed region
+  roofline   dominant kernel (ADMM): algorithmic fp64 flops / measured duration vs the FP64 FMA peak
+             measured on this device by drc_bench_fp64_peak (the path is fp64-ALU bound, not HBM or
+             tensor bound: BASELINE.md section 4); the HBM view is reported next to it
+  cpu_baseline  the oracle (CPU restatement, kind "port": the reference cannot be built here) timed
+             on the box's host cores on a bounded sample
+--impl reference times the oracle port on all host threads (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "batched QP-IK control cycles/sec (FR3, batch 65536)"
+UNIT = "cycles/s"
+LINK = "fr3_link8"
+# Algorithmic fp64 flop model of the structured ADMM kernel for FR3 QPIK (NC=7, KU=2, ND=2; FMA = 2 flops),
+# derived in DESIGN.md section "ADMM flop model": per iteration, per termination check, per (re)factorisation,
+# and the one-off Ruiz scaling.
+FLOPS_ITER, FLOPS_CHECK, FLOPS_FACTOR, FLOPS_SCALE = 867.0, 1450.0, 1900.0, 4300.0
+BYTES_PER_CYCLE = 320.0  # q, qdot, x_target(12), xdot_target in; qdot*, status, iters out
+
+
+def make_workload(model, B: int, seed: int):
+    """BASELINE.md section 4 inputs (numpy default_rng(seed))."""
+    rng = np.random.default_rng(seed)
+    lo, hi, vl = model.q_lower, model.q_upper, model.v_limit
+    q = lo + (0.1 + 0.8 * rng.random((B, model.dof))) * (hi - lo)
+    qd = rng.uniform(-0.5, 0.5, (B, model.dof)) * vl
+    dq = rng.normal(size=(B, model.dof)) * 0.05
+    xdot_t = rng.normal(size=(B, 6)) * 0.05
+    return q, qd, q + dq, xdot_t
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cycles_per_s(B: int, threads: int, seed: int = 0, passes: int = 1):
+    """Time the CPU restatement (oracle port) on `threads` host threads."""
+    from oracle.c_oracle import Oracle
+    import dyros_robot_controller_b200 as drc
+    o = Oracle(drc.FR3_URDF, drc.FR3_SRDF, threads=threads)
+    f = o.frame_id(LINK)
+
+    class M:  # the oracle's own model view, same fields as engine.Model
+        dof, q_lower, q_upper, v_limit = o.nv, o.model.q_lo, o.model.q_hi, o.model.v_lim
+    q, qd, q_t, xdot_t = make_workload(M, B, seed)
+    x_t = o.update_state(q_t, qd, f)["pose"]
+    o.cycle(1, q[:256], qd[:256], x_t[:256], xdot_t[:256], f)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        r = o.cycle(1, q, qd, x_t, xdot_t, f)
+    dt = time.perf_counter() - t0
+    return B * passes / dt, dt / passes, r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 8192
+    times = []
+    for i in range(args.warmup + args.steps):
+        cps, dt, _ = oracle_cycles_per_s(sample, threads, seed=i)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "FR3 updateState+QPIKStep (QP 23 vars / 39 rows), CPU oracle port of Pinocchio+OSQP path",
+                       "batch_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} cycles per step, OpenMP over all {threads} host threads"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import dyros_robot_controller_b200 as drc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B = args.batch
+    model = drc.Model(drc.FR3_URDF, drc.FR3_SRDF)
+    ctx = drc.Context(model, B, device=local)
+    # each rank owns an independent shard of the batch (no exchange on the solve path)
+    q, qd, q_t, xdot_t = make_workload(model, B, seed=1000 * rank)
+    ctx.update_state(q_t, qd)
+    x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+    tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xdot_t))
+    out = torch.empty((B, model.dof), dtype=torch.float64, device=dev)
+    st = torch.empty(B, dtype=torch.int32, device=dev)
+    it = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        ctx.cycle_qpik_step(tq, tqd, txt, txd, LINK, out=out, status=st, iters=it)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ctx.enable_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    step_ms, stage_ms = [], []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        stage_ms.append(ctx.last_timing())
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - launches0
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    total_ms = float(np.sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- e2e through the host-buffer C-ABI call (pinned host memory in, host memory out)
+    hq, hqd, hxt, hxd = (torch.from_numpy(a).pin_memory().numpy() for a in (q, qd, x_t, xdot_t))
+    hout = torch.empty((B, model.dof), dtype=torch.float64).pin_memory().numpy()
+    hst = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
+    hit = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
+    ctx.enable_timing(False)
+    for _ in range(2):
+        ctx.cycle_qpik_step(hq, hqd, hxt, hxd, LINK, out=hout, status=hst, iters=hit)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.cycle_qpik_step(hq, hqd, hxt, hxd, LINK, out=hout, status=hst, iters=hit)
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = B * (model.dof * 2 + 12 + 6) * 8
+    d2h = B * (model.dof * 8 + 4 + 4)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (ADMM), algorithmic flops from the per-robot iteration counts
+    iters = it.cpu().numpy().astype(np.float64)
+    status = st.cpu().numpy()
+    checks = np.ceil(iters / 25.0)
+    refactors = 1.0 + np.floor(iters / 50.0) * 0.5  # upper-bound model: at most one rho update per 50 iterations
+    flops = float(np.sum(FLOPS_SCALE + FLOPS_FACTOR * refactors + FLOPS_ITER * iters + FLOPS_CHECK * checks))
+    admm_ms = float(np.mean([s["admm_ms"] for s in stage_ms]))
+    build_ms = float(np.mean([s["build_ms"] for s in stage_ms]))
+    col_ms = float(np.mean([s["collision_ms"] for s in stage_ms]))
+    try:
+        peak = drc.fp64_peak_tflops(local)
+        peak_src = "measured in-run by drc_bench_fp64_peak (FP64 FMA, 8 chains/thread)"
+    except Exception as e:  # pragma: no cover
+        peak, peak_src = 37.0, f"fallback nominal B200 FP64 ({e})"
+    achieved = flops / (admm_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_achieved = BYTES_PER_CYCLE * B / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "kernel": "k_admm<QpCfg<7,2,2,0>>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": admm_ms, "kernel_share_of_step": admm_ms / ms_per_step,
+                "stage_ms": {"state_and_qp_build": build_ms, "self_collision": col_ms, "admm": admm_ms},
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
+    cores = os.cpu_count() or 1
+    sample = min(B, 32768)
+    cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "FR3 updateState+QPIKStep (QP 23 vars / 39 rows, OSQP algorithm, self-collision + "
+                                   "manipulability rows)", "batch_per_gpu": B, "global_batch": world * B,
+                       "parallelism": f"batch shard x{world}, no collective on the solve path",
+                       "l2": "256 MiB buffer zeroed between timed steps", "seed": "default_rng(1000*rank)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} cycles of the same workload, one pass, OpenMP over {cores} host threads "
+                                       f"({cpu_dt:.2f} s)"},
+            "solved_fraction": float(np.mean(status == 1)), "mean_admm_iters": float(np.mean(iters))}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=65536, help="robots per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

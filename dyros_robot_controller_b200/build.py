@@ -1,0 +1,72 @@
+"""Build recipe of the in-tree CUDA library (sm_100a only).
+
+    python -m dyros_robot_controller_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting libdrc_b200.so sits next to this file (git-ignored,
+but it travels to the GPU box with the repository snapshot).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libdrc_b200.so"
+SOURCES = [CSRC / "drc_lib.cu", CSRC / "model.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+              "-Xcompiler", "-fPIC"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found (needed to build libdrc_b200.so)")
+
+
+HASH = PKG / "libdrc_b200.so.srchash"
+
+
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "drc_b200.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def stale() -> bool:
+    """Content hash, not mtimes: the snapshot copied to the GPU box does not keep timestamps."""
+    if not LIB.exists() or not HASH.exists():
+        return True
+    return HASH.read_text().strip() != _source_hash()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not stale():
+        return LIB
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+        print(" ".join(cmd), flush=True)
+    env = dict(os.environ)
+    # the environment's CC/CXX wrappers are not nvcc host compilers; use the system gcc
+    env.pop("CC", None), env.pop("CXX", None)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    HASH.write_text(_source_hash())
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", LIB)

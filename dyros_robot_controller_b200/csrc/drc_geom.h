@@ -286,6 +286,10 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
     bool dup = false;
     for (int i = 0; i < n; ++i) dup = dup || (norm2(sv[i].w - nw.w) <= 1e-30);
     if (dup) break;
+    SimplexVert prev_sv[4];
+    double prev_lam[4];
+    const int prev_n = n;
+    for (int i = 0; i < n; ++i) { prev_sv[i] = sv[i]; prev_lam[i] = lam[i]; }
     sv[n++] = nw;
     bool inside = false;
     if (n == 2) closest_segment(sv, n, lam);
@@ -294,7 +298,11 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
     if (inside) { lam[0] = lam[1] = lam[2] = lam[3] = 0.25; n = 4; inter = true; break; }
     Vec3 nv = v3(0, 0, 0);
     for (int i = 0; i < n; ++i) nv = nv + lam[i] * sv[i].w;
-    if (dot(nv, nv) >= vv) break;  // numerical floor
+    if (dot(nv, nv) >= vv) {  // numerical floor: keep the previous simplex
+      n = prev_n;
+      for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
+      break;
+    }
     v = nv;
   }
   out.intersect = inter;

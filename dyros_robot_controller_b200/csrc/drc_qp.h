@@ -204,7 +204,7 @@ DRC_HD void bundle_post(Bundle& b, double s, double alpha, bool keep_delta) {
 // ------------------------------------------------------------------------------------------------
 // Warp executors.  Device: one register-resident Lane per thread, phases end with __syncwarp().
 // ------------------------------------------------------------------------------------------------
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 template <class Cfg>
 struct WarpExec {
   Lane<Cfg> L;

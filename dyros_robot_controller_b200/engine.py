@@ -1,0 +1,362 @@
+"""Batched control-cycle engine: thin Python front-end over the C ABI (include/drc_b200.h).
+
+* numpy arrays  -> drc_host_* entry points (host buffers, H2D/D2H inside the call, synchronous)
+* torch CUDA tensors -> drc_batch_* entry points (device pointers, asynchronous on the current
+  torch stream); torch is only plumbing here (device memory, streams).
+
+Shapes are batch-major: q (B, n), poses (B, 4, 4) / (B, 12) [top three rows of the homogeneous
+matrix], task vectors (B, 6), matrices (B, n, n) / (B, 6, n).  A leading batch axis may be omitted
+for a single robot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import DrcParams, check, lib
+
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def pose12(T) -> np.ndarray:
+    """(...,4,4) / (...,3,4) / (...,12) -> (...,12)."""
+    T = np.asarray(T, np.float64)
+    if T.shape[-1] == 12 and (T.ndim == 1 or T.shape[-2:] != (3, 4)):
+        return np.ascontiguousarray(T)
+    return np.ascontiguousarray(T[..., :3, :].reshape(T.shape[:-2] + (12,)))
+
+
+def pose44(p) -> np.ndarray:
+    p = np.asarray(p, np.float64)
+    out = np.zeros(p.shape[:-1] + (4, 4))
+    out[..., :3, :] = p.reshape(p.shape[:-1] + (3, 4))
+    out[..., 3, 3] = 1.0
+    return out
+
+
+class Model:
+    """Compiled robot model (replaces the Pinocchio model the reference builds in RobotData's ctor)."""
+
+    def __init__(self, urdf_path: str, srdf_path: str = "", packages_path: str = ""):
+        h = C.c_void_p()
+        check(lib().drc_model_create_from_urdf(str(urdf_path).encode(), str(srdf_path).encode(),
+                                               str(packages_path).encode(), C.byref(h)), "drc_model_create_from_urdf")
+        self._h = h
+        self.dof = lib().drc_model_dof(h)
+        s = (C.c_int * 6)()
+        check(lib().drc_model_info(h, s), "drc_model_info")
+        self.info = dict(dof=s[0], geoms=s[1], pairs=s[2], groups=s[3], frames=s[4], skipped_meshes=s[5])
+        n = self.dof
+        lo, hi, vl, ef = (np.zeros(n) for _ in range(4))
+        check(lib().drc_model_limits(h, lo.ctypes.data_as(_D), hi.ctypes.data_as(_D), vl.ctypes.data_as(_D),
+                                     ef.ctypes.data_as(_D)), "drc_model_limits")
+        self.q_lower, self.q_upper, self.v_limit, self.effort_limit = lo, hi, vl, ef
+        self.frame_names = [lib().drc_model_frame_name(h, i).decode() for i in range(self.info["frames"])]
+        self.joint_names = [lib().drc_model_joint_name(h, i).decode() for i in range(n)]
+
+    def frame_id(self, link_name: str) -> int:
+        return lib().drc_model_frame_id(self._h, link_name.encode())
+
+    def verbose(self) -> str:
+        return lib().drc_model_verbose(self._h).decode()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().drc_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class Context:
+    """Device state cache + scratch for up to `max_batch` robots on one GPU."""
+
+    def __init__(self, model: Model, max_batch: int, device: int = 0):
+        h = C.c_void_p()
+        check(lib().drc_ctx_create(model._h, int(device), int(max_batch), C.byref(h)), "drc_ctx_create")
+        self._h = h
+        self.model = model
+        self.n = model.dof
+        self.device = device
+        self.max_batch = max_batch
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().drc_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def get_params(self) -> DrcParams:
+        p = DrcParams()
+        check(lib().drc_ctx_get_params(self._h, C.byref(p)), "drc_ctx_get_params")
+        return p
+
+    def set_params(self, **kw):
+        p = self.get_params()
+        for k, v in kw.items():
+            cur = getattr(p, k)
+            if hasattr(cur, "__len__"):
+                v = np.asarray(v, np.float64).ravel()
+                for i in range(len(v)):
+                    cur[i] = float(v[i])
+            else:
+                setattr(p, k, v)
+        check(lib().drc_ctx_set_params(self._h, C.byref(p)), "drc_ctx_set_params")
+
+    def synchronize(self):
+        check(lib().drc_ctx_synchronize(self._h), "drc_ctx_synchronize")
+
+    def enable_timing(self, on=True):
+        check(lib().drc_ctx_enable_timing(self._h, int(on)), "drc_ctx_enable_timing")
+
+    def last_timing(self):
+        ms = (C.c_float * 4)()
+        check(lib().drc_ctx_last_timing(self._h, ms), "drc_ctx_last_timing")
+        return dict(build_ms=ms[0], collision_ms=ms[1], admm_ms=ms[2], total_ms=ms[3])
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().drc_ctx_launch_count(self._h))
+
+    # ------------------------------------------------------------------ argument plumbing
+    def _frame(self, link) -> int:
+        fid = link if isinstance(link, (int, np.integer)) else self.model.frame_id(link)
+        if fid < 0:
+            raise KeyError(f"link '{link}' not found in the URDF")
+        return int(fid)
+
+    @staticmethod
+    def _np_in(a, K, B=None):
+        if a is None:
+            return None, B
+        a = np.ascontiguousarray(np.asarray(a, np.float64).reshape(-1, K))
+        if B is not None and a.shape[0] != B:
+            raise ValueError(f"expected batch {B}, got {a.shape[0]}")
+        return a, a.shape[0]
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(_D)
+
+    @staticmethod
+    def _pi(a):
+        return None if a is None else a.ctypes.data_as(_I)
+
+    # torch helpers (device path)
+    def _t_in(self, t, K, B=None):
+        import torch
+        if t is None:
+            return None, B
+        if t.dtype != torch.float64 or not t.is_cuda:
+            raise TypeError("device entry points need float64 CUDA tensors")
+        t = t.reshape(-1, K).contiguous()
+        if B is not None and t.shape[0] != B:
+            raise ValueError(f"expected batch {B}, got {t.shape[0]}")
+        return t, t.shape[0]
+
+    @staticmethod
+    def _tp(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    @staticmethod
+    def _stream():
+        import torch
+        h = torch.cuda.current_stream().cuda_stream
+        return C.c_void_p(h if h else 1)  # handle 0 is torch's default stream = cudaStreamLegacy (0x1); NULL means "ctx stream"
+
+    # ------------------------------------------------------------------ RobotData
+    def update_state(self, q, qdot):
+        if _is_torch(q):
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            check(lib().drc_batch_update_state(self._h, B, self._tp(q), self._tp(qd), _capi.LAYOUT_AOS, self._stream()),
+                  "drc_batch_update_state")
+            self._B = B
+            return True
+        q, B = self._np_in(q, self.n)
+        qd, _ = self._np_in(qdot, self.n, B)
+        check(lib().drc_host_update_state(self._h, B, self._p(q), self._p(qd)), "drc_host_update_state")
+        self._B = B
+        return True
+
+    def get_frame(self, link, want=("pose", "J", "Jdot", "vel")):
+        B, n, f = self._B, self.n, self._frame(link)
+        o = dict(pose=np.zeros((B, 12)) if "pose" in want else None, J=np.zeros((B, 6, n)) if "J" in want else None,
+                 Jdot=np.zeros((B, 6, n)) if "Jdot" in want else None, vel=np.zeros((B, 6)) if "vel" in want else None)
+        check(lib().drc_host_get_frame(self._h, B, f, self._p(o["pose"]), self._p(o["J"]), self._p(o["Jdot"]),
+                                       self._p(o["vel"])), "drc_host_get_frame")
+        return {k: v for k, v in o.items() if v is not None}
+
+    def get_dynamics(self, want=("M", "Minv", "g", "c", "nle")):
+        B, n = self._B, self.n
+        o = dict(M=np.zeros((B, n, n)) if "M" in want else None, Minv=np.zeros((B, n, n)) if "Minv" in want else None,
+                 g=np.zeros((B, n)) if "g" in want else None, c=np.zeros((B, n)) if "c" in want else None,
+                 nle=np.zeros((B, n)) if "nle" in want else None)
+        check(lib().drc_host_get_dynamics(self._h, B, self._p(o["M"]), self._p(o["Minv"]), self._p(o["g"]), self._p(o["c"]),
+                                          self._p(o["nle"])), "drc_host_get_dynamics")
+        return {k: v for k, v in o.items() if v is not None}
+
+    def get_manipulability(self, link, with_graddot=False):
+        B, n, f = self._B, self.n, self._frame(link)
+        m, g, gd = np.zeros(B), np.zeros((B, n)), np.zeros((B, n))
+        check(lib().drc_host_get_manipulability(self._h, B, f, int(with_graddot), self._p(m), self._p(g), self._p(gd)),
+              "drc_host_get_manipulability")
+        return m, g, gd
+
+    def get_min_distance(self, with_graddot=False):
+        B, n = self._B, self.n
+        d, g, gd, pr = np.zeros(B), np.zeros((B, n)), np.zeros((B, n)), np.zeros(B, np.int32)
+        check(lib().drc_host_get_min_distance(self._h, B, int(with_graddot), self._p(d), self._p(g), self._p(gd), self._pi(pr)),
+              "drc_host_get_min_distance")
+        return d, g, gd, pr
+
+    # ------------------------------------------------------------------ RobotController (cached state)
+    def _qp_host(self, fn, name, B, args, n_out2=False):
+        out, st, it = np.zeros((B, self.n)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        if n_out2:
+            out2 = np.zeros((B, self.n))
+            check(fn(self._h, B, *args, self._p(out), self._p(out2), self._pi(st), self._pi(it)), name)
+            return dict(out=out, qddot=out2, status=st, iters=it)
+        check(fn(self._h, B, *args, self._p(out), self._pi(st), self._pi(it)), name)
+        return dict(out=out, status=st, iters=it)
+
+    def qpik(self, xdot_des, link):
+        x, B = self._np_in(xdot_des, 6, self._B)
+        return self._qp_host(lib().drc_host_qpik, "drc_host_qpik", B, (self._p(x), self._frame(link)))
+
+    def qpik_step(self, x_target, xdot_target, link):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        return self._qp_host(lib().drc_host_qpik_step, "drc_host_qpik_step", B, (self._p(xt), self._p(xd), self._frame(link)))
+
+    def qpid(self, xddot_des, link):
+        x, B = self._np_in(xddot_des, 6, self._B)
+        return self._qp_host(lib().drc_host_qpid, "drc_host_qpid", B, (self._p(x), self._frame(link)), n_out2=True)
+
+    def qpid_step(self, x_target, xdot_target, link):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        return self._qp_host(lib().drc_host_qpid_step, "drc_host_qpid_step", B, (self._p(xt), self._p(xd), self._frame(link)),
+                             n_out2=True)
+
+    def clik_step(self, x_target, xdot_target, link, null_qdot=None):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        nq, _ = self._np_in(null_qdot, self.n, B)
+        out = np.zeros((B, self.n))
+        check(lib().drc_host_clik_step(self._h, B, self._p(xt), self._p(xd), self._p(nq), self._frame(link), self._p(out)),
+              "drc_host_clik_step")
+        return out
+
+    def osf(self, xddot_target, link, null_torque=None):
+        x, B = self._np_in(xddot_target, 6, self._B)
+        nt, _ = self._np_in(null_torque, self.n, B)
+        out = np.zeros((B, self.n))
+        check(lib().drc_host_osf(self._h, B, self._p(x), self._p(nt), self._frame(link), self._p(out)), "drc_host_osf")
+        return out
+
+    def osf_step(self, x_target, xdot_target, link, null_torque=None):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        nt, _ = self._np_in(null_torque, self.n, B)
+        out = np.zeros((B, self.n))
+        check(lib().drc_host_osf_step(self._h, B, self._p(xt), self._p(xd), self._p(nt), self._frame(link), self._p(out)),
+              "drc_host_osf_step")
+        return out
+
+    def joint_torque_step(self, q_target, qdot_target):
+        qt, B = self._np_in(q_target, self.n, self._B)
+        qdt, _ = self._np_in(qdot_target, self.n, B)
+        out = np.zeros((B, self.n))
+        check(lib().drc_host_joint_torque_step(self._h, B, self._p(qt), self._p(qdt), self._p(out)),
+              "drc_host_joint_torque_step")
+        return out
+
+    def task_space_cubic(self, x_target, xdot_target, x_init, xdot_init, t, t0, duration):
+        xt, B = self._np_in(pose12(x_target), 12)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        xi, _ = self._np_in(pose12(x_init), 12, B)
+        xdi, _ = self._np_in(xdot_init, 6, B)
+        o1, o2 = np.zeros((B, 12)), np.zeros((B, 6))
+        check(lib().drc_host_task_space_cubic(self._h, B, self._p(xt), self._p(xd), self._p(xi), self._p(xdi), C.c_double(t),
+                                              C.c_double(t0), C.c_double(duration), self._p(o1), self._p(o2)),
+              "drc_host_task_space_cubic")
+        return o1, o2
+
+    # ------------------------------------------------------------------ fused control cycle
+    def cycle_qpik_step(self, q, qdot, x_target, xdot_target, link, out=None, status=None, iters=None):
+        """updateState + QPIKStep.  numpy in -> numpy out (host path); torch CUDA in -> torch out (async)."""
+        f = self._frame(link)
+        if _is_torch(q):
+            import torch
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            xt, _ = self._t_in(x_target, 12, B)
+            xd, _ = self._t_in(xdot_target, 6, B)
+            out = torch.empty((B, self.n), dtype=torch.float64, device=q.device) if out is None else out
+            status = torch.empty(B, dtype=torch.int32, device=q.device) if status is None else status
+            iters = torch.empty(B, dtype=torch.int32, device=q.device) if iters is None else iters
+            check(lib().drc_batch_cycle_qpik_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
+                                                  self._tp(out), self._tp(status), self._tp(iters), _capi.LAYOUT_AOS,
+                                                  self._stream()), "drc_batch_cycle_qpik_step")
+            self._B = B
+            return dict(out=out, status=status, iters=iters)
+        q, B = self._np_in(q, self.n)
+        qd, _ = self._np_in(qdot, self.n, B)
+        xt, _ = self._np_in(pose12(x_target), 12, B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        out = np.zeros((B, self.n)) if out is None else out
+        status = np.zeros(B, np.int32) if status is None else status
+        iters = np.zeros(B, np.int32) if iters is None else iters
+        check(lib().drc_host_cycle_qpik_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
+                                             self._pi(status), self._pi(iters)), "drc_host_cycle_qpik_step")
+        self._B = B
+        return dict(out=out, status=status, iters=iters)
+
+    def cycle_qpid_step(self, q, qdot, x_target, xdot_target, link):
+        f = self._frame(link)
+        if _is_torch(q):
+            import torch
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            xt, _ = self._t_in(x_target, 12, B)
+            xd, _ = self._t_in(xdot_target, 6, B)
+            out = torch.empty((B, self.n), dtype=torch.float64, device=q.device)
+            status = torch.empty(B, dtype=torch.int32, device=q.device)
+            iters = torch.empty(B, dtype=torch.int32, device=q.device)
+            check(lib().drc_batch_cycle_qpid_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
+                                                  self._tp(out), self._tp(status), self._tp(iters), _capi.LAYOUT_AOS,
+                                                  self._stream()), "drc_batch_cycle_qpid_step")
+            self._B = B
+            return dict(out=out, status=status, iters=iters)
+        q, B = self._np_in(q, self.n)
+        qd, _ = self._np_in(qdot, self.n, B)
+        xt, _ = self._np_in(pose12(x_target), 12, B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        out, status, iters = np.zeros((B, self.n)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        check(lib().drc_host_cycle_qpid_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
+                                             self._pi(status), self._pi(iters)), "drc_host_cycle_qpid_step")
+        self._B = B
+        return dict(out=out, status=status, iters=iters)
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    v = C.c_double()
+    check(lib().drc_bench_fp64_peak(int(device), C.byref(v)), "drc_bench_fp64_peak")
+    return float(v.value)
+
+
+def device_count() -> int:
+    return int(lib().drc_device_count())

@@ -1,0 +1,180 @@
+/* drc_b200 -- C ABI of the B200 batched control-cycle engine.
+ *
+ * Drop-in boundary for the per-cycle hot path of YoungWook0533/dyros_robot_controller: each entry
+ * point names the reference interface it replaces (file:line under the reference checkout).  The
+ * reference's C++ classes / Python `drc` package keep their method names and forward here
+ * (INTEGRATION.md shows the bindings).  No C++/torch types cross this boundary: plain pointers,
+ * sizes and opaque handles; every function returns 0 on success or a negative DRC_E_* code, with a
+ * message available from drc_last_error().  No exceptions propagate.
+ *
+ * Batched arrays: element (b, k) of a (B, K) array
+ *     DRC_LAYOUT_AOS  -> ptr[b*K + k]     batch-major, what numpy (B, K) gives
+ *     DRC_LAYOUT_SOA  -> ptr[k*B + b]     component-major, coalesced for one-robot-per-thread kernels
+ * Matrices are flattened row-major into K (M: n*n, J: 6*n).  Poses are K = 12: the top three rows of
+ * the 4x4 homogeneous matrix, row-major (R00 R01 R02 px R10 ...).  All reals are fp64.
+ *
+ * drc_batch_* : DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*, NULL = the
+ *               context's own stream).  The context owns only handles and scratch.
+ * drc_host_*  : HOST pointers (AoS), synchronous: H2D copy, the same kernels, D2H copy.
+ */
+#ifndef DRC_B200_H
+#define DRC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct drc_model drc_model_t;
+typedef struct drc_ctx drc_ctx_t;
+
+enum { DRC_OK = 0, DRC_E_INVALID = -1, DRC_E_IO = -2, DRC_E_PARSE = -3, DRC_E_UNSUPPORTED = -4, DRC_E_CUDA = -5,
+       DRC_E_NOMEM = -6 };
+enum { DRC_LAYOUT_AOS = 0, DRC_LAYOUT_SOA = 1 };
+enum { DRC_DRIVE_DIFFERENTIAL = 0, DRC_DRIVE_MECANUM = 1, DRC_DRIVE_CASTER = 2 };
+/* per-robot QP status (OSQP's vocabulary); only DRC_QP_SOLVED counts as success, as in QP_base.h:167 */
+enum { DRC_QP_UNSOLVED = 0, DRC_QP_SOLVED = 1, DRC_QP_MAX_ITER = 2, DRC_QP_PRIMAL_INFEASIBLE = 3,
+       DRC_QP_DUAL_INFEASIBLE = 4, DRC_QP_NON_CONVEX = 5, DRC_QP_SOLVED_INACCURATE = 6 };
+
+/* Constants the reference hard-codes (src/manipulator/QP_IK.cpp:81-86,101,122,130,
+ * src/manipulator/robot_controller.cpp:12-15, include/math_type_define.h:7) and the OSQP settings it
+ * leaves at their defaults (include/dyros_robot_controller/QP_base.h:146-149). */
+typedef struct drc_params {
+  double alpha, slack_weight, ik_reg, moma_ik_reg, mani_thresh, dist_thresh;
+  double Kp_task[6], Kv_task[6];
+  double Kp_joint[16], Kv_joint[16];
+  double rho, sigma, osqp_alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+  int max_iter, check_termination, scaling, adaptive_rho, adaptive_rho_interval;
+  double adaptive_rho_tolerance;
+  double gjk_tol, epa_tol;
+  int gjk_max_iter, epa_max_iter;
+  double pinv_threshold;
+} drc_params_t;
+
+const char* drc_last_error(void);
+int drc_version(void);
+/* number of CUDA devices visible (0 when no GPU / driver) */
+int drc_device_count(void);
+
+/* ---- model: replaces Manipulator::RobotData::RobotData (src/manipulator/robot_data.cpp:7-70), i.e.
+ * pinocchio::urdf::buildModel/buildGeom + addAllCollisionPairs + srdf::removeCollisionPairs.  A missing
+ * URDF is an error code here (the reference calls std::exit, :15-19); a missing SRDF enables every pair
+ * (:45-49).  packages_path is accepted for signature parity; mesh collision geometry is not supported. */
+int drc_model_create_from_urdf(const char* urdf_path, const char* srdf_path, const char* packages_path,
+                               drc_model_t** out);
+int drc_model_create_from_text(const char* urdf_text, const char* srdf_text, drc_model_t** out);
+void drc_model_destroy(drc_model_t* m);
+int drc_model_dof(const drc_model_t* m);                         /* getDof() */
+int drc_model_frame_id(const drc_model_t* m, const char* link);  /* model_.getFrameId(); -1 = unknown link */
+int drc_model_num_frames(const drc_model_t* m);
+const char* drc_model_frame_name(const drc_model_t* m, int frame);
+const char* drc_model_joint_name(const drc_model_t* m, int joint);
+/* getJointPositionLimit / getJointVelocityLimit (robot_data.cpp:59-62); any pointer may be NULL */
+int drc_model_limits(const drc_model_t* m, double* q_lo, double* q_hi, double* v_lim, double* effort);
+/* sizes: [0] dof [1] collision primitives [2] enabled pairs [3] link-pair groups [4] frames [5] skipped meshes */
+int drc_model_info(const drc_model_t* m, int* sizes6);
+/* getVerbose() (robot_data.cpp:72-89); returns a string owned by the model */
+const char* drc_model_verbose(const drc_model_t* m);
+
+/* ---- context: device state cache + scratch for up to max_batch robots on one GPU */
+int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** out);
+void drc_ctx_destroy(drc_ctx_t* c);
+int drc_ctx_get_params(const drc_ctx_t* c, drc_params_t* p);
+int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p);
+int drc_ctx_max_batch(const drc_ctx_t* c);
+int drc_ctx_synchronize(drc_ctx_t* c);
+void* drc_ctx_stream(drc_ctx_t* c); /* the context's cudaStream_t */
+
+/* ---- RobotData::updateState (robot_data.cpp:91-124): FK, joint Jacobians, CRBA M, M^-1, g, nle -> cache */
+int drc_batch_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot, int layout, void* stream);
+/* getPose / getJacobian / getJacobianTimeVariation / getVelocity (robot_data.cpp:378-422); NULL = skip.
+ * Always the fresh pose oMi[parent]*placement. */
+int drc_batch_get_frame(drc_ctx_t* c, int B, int frame, double* pose12, double* J, double* Jdot, double* vel,
+                        int layout, void* stream);
+/* getMassMatrix / getMassMatrixInv / getGravity / getCoriolis / getNonlinearEffects; NULL = skip */
+int drc_batch_get_dynamics(drc_ctx_t* c, int B, double* M, double* Minv, double* g, double* coriolis, double* nle,
+                           int layout, void* stream);
+/* getManipulability(with_grad, with_graddot, link) (robot_data.cpp:519-573) */
+int drc_batch_get_manipulability(drc_ctx_t* c, int B, int frame, int with_graddot, double* mani, double* grad,
+                                 double* grad_dot, int layout, void* stream);
+/* getMinDistance(with_grad, with_graddot, verbose) (robot_data.cpp:424-517); pair (int, B) may be NULL */
+int drc_batch_get_min_distance(drc_ctx_t* c, int B, int with_graddot, double* dist, double* grad, double* grad_dot,
+                               int* pair, int layout, void* stream);
+
+/* ---- RobotController (src/manipulator/robot_controller.cpp), all on the cached state
+ * QPIK(xdot_target, link) :277-290  -> qdot* (zeros when the QP is not Solved)
+ * QPIKStep(x_target, xdot_target, link) :292-300
+ * QPID(xddot_target, link) :319-333 -> tau* (gravity when the QP is not Solved); qddot_out optional
+ * QPIDStep :335-343 */
+int drc_batch_qpik(drc_ctx_t* c, int B, const double* xdot_des, int frame, double* qdot_out, int* status, int* iters,
+                   int layout, void* stream);
+int drc_batch_qpik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                        double* qdot_out, int* status, int* iters, int layout, void* stream);
+int drc_batch_qpid(drc_ctx_t* c, int B, const double* xddot_des, int frame, double* tau_out, double* qddot_out,
+                   int* status, int* iters, int layout, void* stream);
+int drc_batch_qpid_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                        double* tau_out, double* qddot_out, int* status, int* iters, int layout, void* stream);
+/* CLIKStep :156-171 (null_qdot may be NULL), OSF :208-225, OSFStep :232-240 (null_torque may be NULL),
+ * moveJointTorqueStep(q_target, qdot_target) :115-125 */
+int drc_batch_clik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* null_qdot,
+                        int frame, double* qdot_out, int layout, void* stream);
+int drc_batch_osf(drc_ctx_t* c, int B, const double* xddot_target, const double* null_torque, int frame, double* tau_out,
+                  int layout, void* stream);
+int drc_batch_osf_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* null_torque,
+                       int frame, double* tau_out, int layout, void* stream);
+int drc_batch_joint_torque_step(drc_ctx_t* c, int B, const double* q_target, const double* qdot_target, double* tau_out,
+                                int layout, void* stream);
+/* DyrosMath::getTaskSpaceCubic (include/math_type_define.h:647-685) for per-robot targets and a common time */
+int drc_batch_task_space_cubic(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* x_init,
+                               const double* xdot_init, double t, double t0, double duration, double* x_des,
+                               double* xdot_des, int layout, void* stream);
+
+/* ---- fused control cycle: updateState + QPIKStep / QPIDStep in one call (the BASELINE.json metric).
+ * The state cache is refreshed exactly as by drc_batch_update_state. */
+int drc_batch_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                              const double* xdot_target, int frame, double* qdot_out, int* status, int* iters, int layout,
+                              void* stream);
+int drc_batch_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                              const double* xdot_target, int frame, double* tau_out, int* status, int* iters, int layout,
+                              void* stream);
+
+/* ---- host-buffer variants (AoS, synchronous): what a CPU caller of the reference classes uses */
+int drc_host_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot);
+int drc_host_get_frame(drc_ctx_t* c, int B, int frame, double* pose12, double* J, double* Jdot, double* vel);
+int drc_host_get_dynamics(drc_ctx_t* c, int B, double* M, double* Minv, double* g, double* coriolis, double* nle);
+int drc_host_get_manipulability(drc_ctx_t* c, int B, int frame, int with_graddot, double* mani, double* grad,
+                                double* grad_dot);
+int drc_host_get_min_distance(drc_ctx_t* c, int B, int with_graddot, double* dist, double* grad, double* grad_dot, int* pair);
+int drc_host_qpik(drc_ctx_t* c, int B, const double* xdot_des, int frame, double* qdot_out, int* status, int* iters);
+int drc_host_qpik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame, double* qdot_out,
+                       int* status, int* iters);
+int drc_host_qpid(drc_ctx_t* c, int B, const double* xddot_des, int frame, double* tau_out, double* qddot_out, int* status,
+                  int* iters);
+int drc_host_qpid_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame, double* tau_out,
+                       double* qddot_out, int* status, int* iters);
+int drc_host_clik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* null_qdot,
+                       int frame, double* qdot_out);
+int drc_host_osf(drc_ctx_t* c, int B, const double* xddot_target, const double* null_torque, int frame, double* tau_out);
+int drc_host_osf_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* null_torque,
+                      int frame, double* tau_out);
+int drc_host_joint_torque_step(drc_ctx_t* c, int B, const double* q_target, const double* qdot_target, double* tau_out);
+int drc_host_task_space_cubic(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* x_init,
+                              const double* xdot_init, double t, double t0, double duration, double* x_des, double* xdot_des);
+int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                             const double* xdot_target, int frame, double* qdot_out, int* status, int* iters);
+int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                             const double* xdot_target, int frame, double* tau_out, int* status, int* iters);
+
+/* ---- instrumentation (replaces QP::TimeDuration / SuhanBenchmark, QP_base.h:19-43) */
+/* device time in ms of the stages of the LAST cycle/QP call on this context (CUDA events on its stream):
+ * [0] state/QP build  [1] self-collision  [2] ADMM solve  [3] total; requires drc_ctx_enable_timing(c,1) */
+int drc_ctx_enable_timing(drc_ctx_t* c, int on);
+int drc_ctx_last_timing(drc_ctx_t* c, float* ms4);
+/* number of kernels this library launched on the context since creation */
+long long drc_ctx_launch_count(const drc_ctx_t* c);
+/* measured FP64 FMA throughput of the device (TFLOP/s) -- the roofline denominator of this fp64 path */
+int drc_bench_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

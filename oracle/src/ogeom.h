@@ -263,6 +263,10 @@ inline GjkResult gjk(const Shape& A, const Shape& B, const GeomParams& gp) {
       if (dot(e, e) <= 1e-30) dup = true;
     }
     if (dup) return finish(false);
+    SVert prev_sv[4];
+    double prev_lam[4];
+    const int prev_n = n;
+    for (int i = 0; i < n; ++i) { prev_sv[i] = sv[i]; prev_lam[i] = lam[i]; }
     sv[n++] = nw;
     bool inside = false;
     if (n == 2) closest_on_segment(sv, n, lam);
@@ -271,7 +275,9 @@ inline GjkResult gjk(const Shape& A, const Shape& B, const GeomParams& gp) {
     if (inside) { for (int i = 0; i < 4; ++i) lam[i] = 0.25; n = 4; return finish(true); }
     V3 nv;
     for (int i = 0; i < n; ++i) nv += lam[i] * sv[i].w;
-    if (dot(nv, nv) >= vv) {  // no progress: numerical floor reached
+    if (dot(nv, nv) >= vv) {  // no progress: numerical floor reached, keep the previous simplex
+      n = prev_n;
+      for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
       return finish(false);
     }
     v = nv;
