@@ -48,6 +48,17 @@ struct DrcParams {
   double pinv_threshold = 1e-6;  // COD rank threshold (math_type_define.h:7)
 };
 
+// Collision primitives (kept as one block so a kernel can stage it into shared memory).
+struct GeomTable {
+  int type[kMaxGeom];
+  int parent[kMaxGeom];
+  double prm[kMaxGeom][3];  // sphere r | cylinder/capsule r, half length | box half extents
+  double R[kMaxGeom][9];    // placement in the parent joint frame
+  double p[kMaxGeom][3];
+  unsigned char pair_a[kMaxPair], pair_b[kMaxPair];  // geometry indices of the enabled pairs, sorted by group
+  short pair_id[kMaxPair];                           // index in the reference's pair order (tie-break)
+};
+
 // Flat, fixed-topology robot model.  Passed to kernels BY VALUE as a __grid_constant__ parameter
 // (constant bank: uniform broadcast reads, private to each launch, no cross-stream hazards).
 struct DrcModelDev {
@@ -65,14 +76,9 @@ struct DrcModelDev {
   double gravity[3];
   // collision geometry, grouped by (parent joint A, parent joint B)
   int ngeom;
-  int geom_type[kMaxGeom];
-  int geom_parent[kMaxGeom];
-  double geom_prm[kMaxGeom][3];  // sphere r | cylinder/capsule r, half length | box half extents
-  double geom_R[kMaxGeom][9];    // placement in the parent joint frame
-  double geom_p[kMaxGeom][3];
-  int npair, ngroup;
-  unsigned char pair_a[kMaxPair], pair_b[kMaxPair];  // geometry indices, sorted by group
-  short pair_id[kMaxPair];                           // index in the reference's pair order (tie-break)
+  GeomTable geom;
+  int npair, ngroup, ngjk;
+  unsigned short gjk_pair[64];   // i-th pair (sorted order) that needs GJK (cylinder/box vs cylinder/box)
   short group_ja[kMaxGroup], group_jb[kMaxGroup], group_first[kMaxGroup], group_count[kMaxGroup];
   // mobile manipulator (drive_type == kNoBase for a plain arm)
   int drive_type, wheel_num, virtual_start, mani_start, mobi_start, act_mani_start, act_mobi_start, mani_dof;

@@ -362,6 +362,7 @@ struct CollisionIO {
   // hand-over to the EPA kernel
   int* epa_flag;                     // per robot: number of overlapping GJK pairs still to resolve
   unsigned long long* cand_mask;     // per robot: bit i = GJK-type pair i must be resolved by EPA
+  int* epa_list; int* epa_count;     // compacted list of flagged robots (device: atomic append), may be null
 };
 
 struct JointFrame {
@@ -380,16 +381,16 @@ DRC_HD JointFrame load_joint_frame(const double* oMi, long long Bc, int b, int j
   return f;
 }
 // geometry g of the model, placed by the transform (R, p) applied to its joint-frame placement
-DRC_HD Prim place_prim(const DrcModelDev& m, int g, const Mat3& R, Vec3 p, bool identity) {
+DRC_HD Prim place_prim(const GeomTable& G, int g, const Mat3& R, Vec3 p, bool identity) {
   Prim s;
-  s.type = m.geom_type[g];
-  s.r = m.geom_prm[g][0]; s.h = m.geom_prm[g][1];
-  s.hb = v3(m.geom_prm[g][0], m.geom_prm[g][1], m.geom_prm[g][2]);
-  const Vec3 cl = v3(m.geom_p[g][0], m.geom_p[g][1], m.geom_p[g][2]);
-  const Vec3 al = v3(m.geom_R[g][2], m.geom_R[g][5], m.geom_R[g][8]);
+  s.type = G.type[g];
+  s.r = G.prm[g][0]; s.h = G.prm[g][1];
+  s.hb = v3(G.prm[g][0], G.prm[g][1], G.prm[g][2]);
+  const Vec3 cl = v3(G.p[g][0], G.p[g][1], G.p[g][2]);
+  const Vec3 al = v3(G.R[g][2], G.R[g][5], G.R[g][8]);
   if (identity) { s.c = cl; s.a = al; }
   else { s.c = mul(R, cl) + p; s.a = mul(R, al); }
-  if (s.type == kBox) s.R = identity ? mat3_from(m.geom_R[g]) : mul(R, mat3_from(m.geom_R[g]));
+  if (s.type == kBox) s.R = identity ? mat3_from(G.R[g]) : mul(R, mat3_from(G.R[g]));
   else s.R = identity3();
   return s;
 }
@@ -481,14 +482,16 @@ DRC_HD void collision_finish(const DrcModelDev& m, const DrcParams& prm, const C
   }
 }
 
-// Main self-distance pass.  Closed-form pairs are evaluated exactly; GJK-type pairs first by their
-// lower bound, then (only those that can still win) by GJK.  Pairs that overlap are deferred to
-// the EPA kernel through cand_mask / epa_flag; robots without deferred pairs are finished here.
+// Main self-distance pass.  Closed-form pairs are evaluated exactly in a loop that is uniform across
+// threads (model indices are warp-uniform -> constant-bank broadcasts); GJK-type pairs get their
+// certified lower bound there, and only those that can still win run GJK afterwards, each thread on
+// ITS OWN candidate (divergent model indices -> `G` is the shared-memory copy of the geometry table).
+// Pairs that overlap are deferred to the EPA kernel through cand_mask / epa_flag.
 template <int NV, bool CHAIN>
-DRC_HD void collision_job(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b) {
+DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io, int b) {
   BestPair best;
   best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
-  unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair (model order) whose bound beats the current best
+  unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair whose bound beats the best exact distance so far
   int gi = 0;
   for (int grp = 0; grp < m.ngroup; ++grp) {
     const int ja = m.group_ja[grp], jb = m.group_jb[grp];
@@ -497,48 +500,46 @@ DRC_HD void collision_job(const DrcModelDev& m, const DrcParams& prm, const Coll
     const Vec3 pab = tmul(FA.R, FB.p - FA.p);
     for (int t = 0; t < m.group_count[grp]; ++t) {
       const int k = m.group_first[grp] + t;
-      const int ga = m.pair_a[k], gb = m.pair_b[k];
-      const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
+      const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
+      const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
       if (has_closed_form(A.type, Bp.type)) {
         const PairResult r = closed_form_distance(A, Bp);
-        consider(best, r.d, m.pair_id[k], ja, jb, r.pa, r.pb);
+        consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
       } else {
-        if (gi < 64 && pair_lower_bound(A, Bp) <= best.d) cand |= 1ull << gi;
+        if (pair_lower_bound(A, Bp) <= best.d) cand |= 1ull << gi;
         ++gi;
       }
     }
   }
-  // GJK pass over the candidates (bounds re-tested against the improving best)
+  // GJK pass: every thread walks its own candidate list (bounds re-tested against the improving best)
   unsigned long long deferred = 0ull;
-  if (cand) {
-    gi = 0;
-    for (int grp = 0; grp < m.ngroup; ++grp) {
-      const int ja = m.group_ja[grp], jb = m.group_jb[grp];
-      bool loaded = false;
-      Mat3 Rab = identity3();
-      Vec3 pab = v3(0, 0, 0);
-      for (int t = 0; t < m.group_count[grp]; ++t) {
-        const int k = m.group_first[grp] + t;
-        const int ga = m.pair_a[k], gb = m.pair_b[k];
-        if (has_closed_form(m.geom_type[ga], m.geom_type[gb])) continue;
-        const int bit = gi++;
-        if (bit >= 64 || !((cand >> bit) & 1ull)) continue;
-        if (!loaded) {
-          const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
-          Rab = tmul(FA.R, FB.R); pab = tmul(FA.R, FB.p - FA.p); loaded = true;
-        }
-        const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
-        if (pair_lower_bound(A, Bp) > best.d) continue;
-        GjkOut g;
-        gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
-        if (g.intersect) deferred |= 1ull << bit;
-        else consider(best, g.dist, m.pair_id[k], ja, jb, g.pa, g.pb);
-      }
-    }
+  while (cand) {
+    int bit = 0;
+    while (!((cand >> bit) & 1ull)) ++bit;
+    cand &= cand - 1ull;
+    const int k = m.gjk_pair[bit];
+    const int ga = G.pair_a[k], gb = G.pair_b[k];
+    const int ja = G.parent[ga], jb = G.parent[gb];
+    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+    const Mat3 Rab = tmul(FA.R, FB.R);
+    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    const Prim A = place_prim(G, ga, Rab, pab, true), Bp = place_prim(G, gb, Rab, pab, false);
+    if (pair_lower_bound(A, Bp) > best.d) continue;
+    GjkOut g;
+    gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+    if (g.intersect) deferred |= 1ull << bit;
+    else consider(best, g.dist, G.pair_id[k], ja, jb, g.pa, g.pb);
   }
   if (deferred) {
     io.cand_mask[b] = deferred;
     io.epa_flag[b] = 1;
+    if (io.epa_list) {
+#if defined(__CUDA_ARCH__)
+      io.epa_list[atomicAdd(io.epa_count, 1)] = b;
+#else
+      io.epa_list[(*io.epa_count)++] = b;
+#endif
+    }
     // provisional result so that the EPA kernel can resume from the best separated pair
     io.witness[6 * b + 0] = best.pa.x; io.witness[6 * b + 1] = best.pa.y; io.witness[6 * b + 2] = best.pa.z;
     io.witness[6 * b + 3] = best.pb.x; io.witness[6 * b + 4] = best.pb.y; io.witness[6 * b + 5] = best.pb.z;
@@ -554,7 +555,7 @@ DRC_HD void collision_job(const DrcModelDev& m, const DrcParams& prm, const Coll
 template <int NV, bool CHAIN>
 DRC_HD void collision_epa_job(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b) {
   if (!io.epa_flag[b]) return;
-  const unsigned long long deferred = io.cand_mask[b];
+  unsigned long long deferred = io.cand_mask[b];
   BestPair best;
   best.d = io.dist[b]; best.id = io.pair_out[b];
   best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
@@ -562,27 +563,24 @@ DRC_HD void collision_epa_job(const DrcModelDev& m, const DrcParams& prm, const 
   best.ja = -1; best.jb = -1;
   // recover the joints of the provisional best pair
   for (int k = 0; k < m.npair; ++k)
-    if (m.pair_id[k] == best.id) { best.ja = m.geom_parent[m.pair_a[k]]; best.jb = m.geom_parent[m.pair_b[k]]; }
-  int gi = 0;
-  for (int grp = 0; grp < m.ngroup; ++grp) {
-    const int ja = m.group_ja[grp], jb = m.group_jb[grp];
-    for (int t = 0; t < m.group_count[grp]; ++t) {
-      const int k = m.group_first[grp] + t;
-      const int ga = m.pair_a[k], gb = m.pair_b[k];
-      if (has_closed_form(m.geom_type[ga], m.geom_type[gb])) continue;
-      const int bit = gi++;
-      if (bit >= 64 || !((deferred >> bit) & 1ull)) continue;
-      const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
-      const Mat3 Rab = tmul(FA.R, FB.R);
-      const Vec3 pab = tmul(FA.R, FB.p - FA.p);
-      const Prim A = place_prim(m, ga, Rab, pab, true), Bp = place_prim(m, gb, Rab, pab, false);
-      GjkOut g;
-      gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
-      PairResult r;
-      r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
-      if (g.intersect) epa_penetration(A, Bp, g, prm.epa_tol, prm.epa_max_iter, r);
-      consider(best, r.d, m.pair_id[k], ja, jb, r.pa, r.pb);
-    }
+    if (m.geom.pair_id[k] == best.id) { best.ja = m.geom.parent[m.geom.pair_a[k]]; best.jb = m.geom.parent[m.geom.pair_b[k]]; }
+  while (deferred) {
+    int bit = 0;
+    while (!((deferred >> bit) & 1ull)) ++bit;
+    deferred &= deferred - 1ull;
+    const int k = m.gjk_pair[bit];
+    const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
+    const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
+    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+    const Mat3 Rab = tmul(FA.R, FB.R);
+    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
+    GjkOut g;
+    gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+    PairResult r;
+    r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+    if (g.intersect) epa_penetration(A, Bp, g, prm.epa_tol, prm.epa_max_iter, r);
+    consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
   }
   collision_finish<NV, CHAIN>(m, prm, io, b, best);
 }
@@ -611,24 +609,25 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
       if (io.status) io.status[b] = S.status;
       if (io.iters) io.iters[b] = S.iters;
     }
+    const ColdLane<Cfg>& C = S.cold[L.gl];
     if (L.is_core) {
       const int j = L.gl;
-      const double xc = L.D * L.x;
+      const double xc = C.D * L.x;
       if (!ID) io.out[b * io.sout.sb + j * io.sout.sk] = ok ? xc : 0.0;
       else if (io.out2) io.out2[b * io.sout2.sb + j * io.sout2.sk] = ok ? xc : 0.0;
       if (io.qp_x) {
         double* xr = io.qp_x + (long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR);
         xr[j] = xc;
 #pragma unroll
-        for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = L.ub[k].has_sing ? L.ub[k].Dd * L.ub[k].xd : 0.0;
+        for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = C.has_sing[k] ? C.Dd[k] * L.b[k].xd : 0.0;
       }
     } else {
       const int r = L.gl - Cfg::NC;
       if (ID && r >= Cfg::ND) {
         const int j = r - Cfg::ND;
-        io.out[b * io.sout.sb + j * io.sout.sk] = ok ? L.rb.Dd * L.rb.xd : io.c_g[j * io.Bc + b];
+        io.out[b * io.sout.sb + j * io.sout.sk] = ok ? C.Dd[0] * L.b[0].xd : io.c_g[j * io.Bc + b];
       }
-      if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = L.rb.has_sing ? L.rb.Dd * L.rb.xd : 0.0;
+      if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = C.has_sing[0] ? C.Dd[0] * L.b[0].xd : 0.0;
     }
   });
 }

@@ -361,9 +361,13 @@ DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut&
   }
   out.d = 0; out.pa = g.pa; out.pb = g.pb;
   if (np < 4) return;
+  short freed[kEpaMaxFace];  // slots of removed faces, reused so that capacity is bounded by 2*vertices - 4
+  int nfree = 0;
   auto add_face = [&](int a, int b, int c) {
-    if (nf >= kEpaMaxFace) return;
-    EpaFace& f = F[nf++];
+    int slot;
+    if (nfree > 0) slot = freed[--nfree];
+    else { if (nf >= kEpaMaxFace) return; slot = nf++; }
+    EpaFace& f = F[slot];
     f.v[0] = (short)a; f.v[1] = (short)b; f.v[2] = (short)c;
     const Vec3 nrm = cross(P[b].w - P[a].w, P[c].w - P[a].w);
     const double l = norm(nrm);
@@ -391,6 +395,7 @@ DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut&
       if (!f.alive) continue;
       if (dot(f.n, s.w - P[f.v[0]].w) > 0) {
         f.alive = 0;
+        freed[nfree++] = (short)i;
         for (int e = 0; e < 3; ++e) {
           const short a = f.v[e], b = f.v[(e + 1) % 3];
           bool found = false;

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -34,20 +35,217 @@ __global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcMo
 template <int NV, bool CHAIN>
 __global__ void __launch_bounds__(128) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ CollisionIO io) {
+  // stage the geometry table in shared memory: the GJK pass indexes it with per-thread pair ids
+  __shared__ GeomTable G;
+  {
+    const int* src = reinterpret_cast<const int*>(&m.geom);
+    int* dst = reinterpret_cast<int*>(&G);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeomTable) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) collision_job<NV, CHAIN>(m, prm, io, b);
+  if (b < io.B) collision_job<NV, CHAIN>(m, G, prm, io, b);
 }
-template <int NV, bool CHAIN>
-__global__ void __launch_bounds__(64) k_collision_epa(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
-                                                       const __grid_constant__ CollisionIO io) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) collision_epa_job<NV, CHAIN>(m, prm, io, b);
+// ---- EPA, one WARP per flagged robot (~0.1 % of a random batch): the polytope lives in shared memory, the face
+// scans (closest face, visibility, horizon) are spread over the 32 lanes; everything else is warp-uniform.
+constexpr int kEpaWarpMaxEdge = 96;
+struct EpaWarpSmem {
+  SimplexVert P[kEpaMaxVert];
+  double fd[kEpaMaxFace];
+  double fn[kEpaMaxFace][3];
+  short fv[kEpaMaxFace][3];
+  unsigned char alive[kEpaMaxFace];
+  short edge[kEpaWarpMaxEdge][2];
+  short killed[kEpaWarpMaxEdge / 3];
+  unsigned char hor[kEpaWarpMaxEdge];
+};
+__device__ __forceinline__ void epa_make_face(EpaWarpSmem& S, int slot, int a, int b, int c) {
+  const Vec3 nrm = cross(S.P[b].w - S.P[a].w, S.P[c].w - S.P[a].w);
+  const double l = norm(nrm);
+  const Vec3 n = l > 0 ? (1.0 / l) * nrm : v3(0, 0, 1);
+  S.fv[slot][0] = (short)a; S.fv[slot][1] = (short)b; S.fv[slot][2] = (short)c;
+  S.fn[slot][0] = n.x; S.fn[slot][1] = n.y; S.fn[slot][2] = n.z;
+  S.fd[slot] = dot(n, S.P[a].w);
+  S.alive[slot] = l > 0 ? 1 : 0;
+}
+__device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out,
+                         int lane) {
+  const unsigned full = 0xffffffffu;
+  auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
+  // seed: grow the GJK simplex to a tetrahedron (warp-uniform, every lane on its private copy)
+  SimplexVert T[4];
+  int np = g.n;
+  for (int i = 0; i < np; ++i) T[i] = g.sv[i];
+  const Vec3 axes[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
+  if (np == 1) {
+    for (int k = 0; k < 6; ++k) {
+      const SimplexVert s = sup(axes[k]);
+      if (norm2(T[0].w - s.w) >= 1e-20) { T[np++] = s; break; }
+    }
+  }
+  if (np == 2) {
+    const Vec3 e = T[1].w - T[0].w;
+    Vec3 best = v3(0, 0, 0);
+    double bl = -1;
+    for (int k = 0; k < 6; ++k) {
+      const Vec3 c = cross(e, axes[k]);
+      if (dot(c, c) <= 1e-20) continue;
+      for (int sgn = -1; sgn <= 1; sgn += 2) {
+        const SimplexVert s = sup((double)sgn * c);
+        const double area = norm(cross(e, s.w - T[0].w));
+        if (area > bl) { bl = area; best = (double)sgn * c; }
+      }
+    }
+    T[np++] = sup(best);
+  }
+  if (np == 3) {
+    const Vec3 nrm = cross(T[1].w - T[0].w, T[2].w - T[0].w);
+    const SimplexVert s1 = sup(nrm), s2 = sup(-nrm);
+    const double h1 = fabs(dot(s1.w - T[0].w, nrm)), h2 = fabs(dot(s2.w - T[0].w, nrm));
+    T[np++] = h1 >= h2 ? s1 : s2;
+  }
+  out.d = 0; out.pa = g.pa; out.pb = g.pb;
+  if (np < 4) return;
+  if (dot(cross(T[1].w - T[0].w, T[2].w - T[0].w), T[3].w - T[0].w) > 0) { const SimplexVert t = T[1]; T[1] = T[2]; T[2] = t; }
+  __syncwarp();
+  if (lane < 4) S.P[lane] = T[lane];
+  __syncwarp();
+  if (lane == 0) epa_make_face(S, 0, 0, 1, 2);
+  if (lane == 1) epa_make_face(S, 1, 0, 3, 1);
+  if (lane == 2) epa_make_face(S, 2, 0, 2, 3);
+  if (lane == 3) epa_make_face(S, 3, 1, 3, 2);
+  int nf = 4;
+  __syncwarp();
+  int bestf = -1;
+  for (int it = 0; it < max_iter; ++it) {
+    // closest face to the origin (ties: smallest index)
+    double bd = 1e300;
+    int bf = -1;
+    for (int f = lane; f < nf; f += 32)
+      if (S.alive[f] && S.fd[f] < bd) { bd = S.fd[f]; bf = f; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(full, bd, off);
+      const int of = __shfl_xor_sync(full, bf, off);
+      if (of >= 0 && (bf < 0 || od < bd || (od == bd && of < bf))) { bd = od; bf = of; }
+    }
+    bestf = bf;
+    if (bf < 0) break;
+    const Vec3 n = v3(S.fn[bf][0], S.fn[bf][1], S.fn[bf][2]);
+    const SimplexVert s = sup(n);
+    if (dot(n, s.w) - S.fd[bf] <= tol) break;
+    if (np >= kEpaMaxVert) break;
+    const int idx = np++;
+    if (lane == 0) S.P[idx] = s;
+    // faces visible from the new vertex die; their edges are collected
+    int nk = 0;
+    for (int base = 0; base < nf; base += 32) {
+      const int f = base + lane;
+      bool vis = false;
+      if (f < nf && S.alive[f]) {
+        const Vec3 p0 = S.P[S.fv[f][0]].w;
+        vis = S.fn[f][0] * (s.w.x - p0.x) + S.fn[f][1] * (s.w.y - p0.y) + S.fn[f][2] * (s.w.z - p0.z) > 0;
+      }
+      const unsigned mk = __ballot_sync(full, vis);
+      if (vis) {
+        const int r = nk + __popc(mk & ((1u << lane) - 1u));
+        S.alive[f] = 0;
+        if (3 * r + 2 < kEpaWarpMaxEdge) {
+          S.killed[r] = (short)f;
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { S.edge[3 * r + e][0] = S.fv[f][e]; S.edge[3 * r + e][1] = S.fv[f][(e + 1) % 3]; }
+        }
+      }
+      nk += __popc(mk);
+    }
+    if (nk == 0 || 3 * nk > kEpaWarpMaxEdge) break;
+    __syncwarp();
+    const int ne = 3 * nk;
+    for (int e = lane; e < ne; e += 32) {
+      const short a = S.edge[e][0], b = S.edge[e][1];
+      unsigned char h = 1;
+      for (int j = 0; j < ne; ++j) if (S.edge[j][0] == b && S.edge[j][1] == a) h = 0;
+      S.hor[e] = h;
+    }
+    __syncwarp();
+    // one new face per horizon edge: first into the slots just freed, the rest appended
+    int nh = 0;
+    for (int base = 0; base < ne; base += 32) {
+      const int e = base + lane;
+      const bool h = e < ne && S.hor[e];
+      const unsigned mk = __ballot_sync(full, h);
+      if (h) {
+        const int r = nh + __popc(mk & ((1u << lane) - 1u));
+        const int slot = r < nk ? (int)S.killed[r] : nf + (r - nk);
+        if (slot < kEpaMaxFace) epa_make_face(S, slot, S.edge[e][0], S.edge[e][1], idx);
+      }
+      nh += __popc(mk);
+    }
+    if (nh > nk) nf = min(nf + (nh - nk), kEpaMaxFace);
+    __syncwarp();
+  }
+  if (bestf < 0) return;
+  const SimplexVert t0 = S.P[S.fv[bestf][0]], t1 = S.P[S.fv[bestf][1]], t2 = S.P[S.fv[bestf][2]];
+  const Vec3 fnv = v3(S.fn[bestf][0], S.fn[bestf][1], S.fn[bestf][2]);
+  const double fdv = S.fd[bestf];
+  const Vec3 pr = fdv * fnv;
+  const Vec3 v0 = t1.w - t0.w, v1 = t2.w - t0.w, v2 = pr - t0.w;
+  const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+  const double den = d00 * d11 - d01 * d01;
+  const double l1 = den != 0 ? (d11 * d20 - d01 * d21) / den : 0.0, l2 = den != 0 ? (d00 * d21 - d01 * d20) / den : 0.0;
+  const double l0 = 1 - l1 - l2;
+  out.pa = l0 * t0.a + l1 * t1.a + l2 * t2.a;
+  out.pb = l0 * t0.b + l1 * t1.b + l2 * t2.b;
+  out.d = -fdv;
+  __syncwarp();
 }
 
-constexpr int kAdmmWarps = 4;
-template <class Cfg, bool ID>
-__global__ void __launch_bounds__(kAdmmWarps * 32) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
-  __shared__ GroupShared<Cfg> sh[kAdmmWarps * Cfg::NG];
+constexpr int kEpaWarps = 2;
+template <int NV, bool CHAIN>
+__global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+                                                                   const __grid_constant__ CollisionIO io) {
+  __shared__ EpaWarpSmem sm[kEpaWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  EpaWarpSmem& S = sm[warp];
+  const int count = *io.epa_count;
+  for (int i = blockIdx.x * kEpaWarps + warp; i < count; i += gridDim.x * kEpaWarps) {
+    const int b = io.epa_list[i];
+    unsigned long long deferred = io.cand_mask[b];
+    BestPair best;
+    best.d = io.dist[b]; best.id = io.pair_out[b];
+    best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
+    best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
+    best.ja = -1; best.jb = -1;
+    for (int k = 0; k < m.npair; ++k)
+      if (m.geom.pair_id[k] == best.id) { best.ja = m.geom.parent[m.geom.pair_a[k]]; best.jb = m.geom.parent[m.geom.pair_b[k]]; }
+    while (deferred) {
+      const int bit = __ffsll((long long)deferred) - 1;
+      deferred &= deferred - 1ull;
+      const int k = m.gjk_pair[bit];
+      const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
+      const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
+      const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+      const Mat3 Rab = tmul(FA.R, FB.R);
+      const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+      const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
+      GjkOut g;
+      gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+      PairResult r;
+      r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+      if (g.intersect) epa_warp(S, A, Bp, g, prm.epa_tol, prm.epa_max_iter, r, lane);
+      consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
+    }
+    __syncwarp();
+    if (lane == 0) collision_finish<NV, CHAIN>(m, prm, io, b, best);
+    __syncwarp();
+  }
+}
+
+constexpr int kAdmmWarps = 1;  // one warp per block: a finished warp frees its slot without waiting for block-mates
+template <class Cfg, bool ID, int MINB>
+__global__ void __launch_bounds__(kAdmmWarps * 32, 4 * MINB) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
+  extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
+  GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int first = (blockIdx.x * kAdmmWarps + warp) * Cfg::NG;
   if (first >= io.B) return;  // no block-level barrier below: idle warps may leave
@@ -187,6 +385,8 @@ struct drc_ctx {
   double* qp;
   int qp_stride_max;
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
+  int* epa_list; int* epa_count;
+  int sm_count;
   // device staging for host entry points
   double* stage; size_t stage_doubles;
   int* stage_i; size_t stage_ints;
@@ -214,7 +414,6 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
 // dispatch on the compile-time robot shape; extend the list to add robots
 #define DRC_DISPATCH_NV(nv, chain, CALL)                                         \
   if ((nv) == 7 && (chain)) { constexpr int NV = 7; constexpr bool CHAIN = true; CALL; } \
-  else if ((nv) == 6 && (chain)) { constexpr int NV = 6; constexpr bool CHAIN = true; CALL; } \
   else return fail(DRC_E_UNSUPPORTED, "no kernel instantiation for this robot (dof / topology)");
 
 template <int NV, bool CHAIN, unsigned FLAGS>
@@ -229,14 +428,15 @@ static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStrea
 template <int NV, bool CHAIN>
 static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s) {
   io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.Bc = c->cap;
-  io.epa_flag = c->epa_flag; io.cand_mask = c->cand_mask;
+  io.epa_flag = c->epa_flag; io.cand_mask = c->cand_mask; io.epa_list = c->epa_list; io.epa_count = c->epa_count;
+  CU(cudaMemsetAsync(c->epa_count, 0, sizeof(int), s));
   if (!io.dist) io.dist = c->col_dist;
   if (!io.pair_out) io.pair_out = c->col_pair;
   if (!io.witness) io.witness = c->col_wit;
   const int threads = 64, blocks = (io.B + threads - 1) / threads;
   k_collision<NV, CHAIN><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
-  k_collision_epa<NV, CHAIN><<<(io.B + 63) / 64, 64, 0, s>>>(c->model->hm.dev, c->prm, io);
+  k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, s>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
   c->launches += 2;
   return DRC_OK;
@@ -247,7 +447,19 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s) {
   io.qp = c->qp; io.c_g = c->c_g; io.Bc = c->cap;
   const QpOptions o = qp_options(c->prm, (1u << Cfg::NC) - 1u);
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
-  k_admm<Cfg, ID><<<blocks, kAdmmWarps * 32, 0, s>>>(io, o);
+  // blocks/SM the kernel is compiled for (register cap 65536 / (128 * MINB)); tunable for experiments
+  static const int minb = [] { const char* e = getenv("DRC_ADMM_MINB"); return e ? atoi(e) : 3; }();
+  constexpr size_t smem = sizeof(GroupShared<Cfg>) * kAdmmWarps * Cfg::NG;
+  static const cudaError_t attr = [] {
+    cudaError_t e1 = cudaFuncSetAttribute(k_admm<Cfg, ID, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_admm<Cfg, ID, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e3 = cudaFuncSetAttribute(k_admm<Cfg, ID, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  }();
+  CU(attr);
+  if (minb <= 2) k_admm<Cfg, ID, 2><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  else if (minb == 3) k_admm<Cfg, ID, 3><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  else k_admm<Cfg, ID, 4><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
   c->launches++;
   CU(cudaGetLastError());
   return DRC_OK;
@@ -412,6 +624,13 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   CU(dalloc(&c->col_dist, B));
   CU(cudaMalloc((void**)&c->col_pair, B * sizeof(int)));
   CU(dalloc(&c->col_wit, 6 * B));
+  CU(cudaMalloc((void**)&c->epa_list, B * sizeof(int)));
+  CU(cudaMalloc((void**)&c->epa_count, sizeof(int)));
+  {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+  }
   // staging: enough for the largest host call (q, qd, pose, xdot in; J/Jdot/M outs)
   c->stage_doubles = B * (size_t)(2 * n + 12 + 6 + 2 * n + 12 * n + 2 * n * n + 64);
   CU(dalloc(&c->stage, c->stage_doubles));
@@ -430,6 +649,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->epa_flag) cudaFree(c->epa_flag);
   if (c->cand_mask) cudaFree(c->cand_mask);
   if (c->col_pair) cudaFree(c->col_pair);
+  if (c->epa_list) cudaFree(c->epa_list);
+  if (c->epa_count) cudaFree(c->epa_count);
   if (c->stage_i) cudaFree(c->stage_i);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);

@@ -10,21 +10,26 @@
 //     unit row  (KU per core var j):  s x_c[j] (+ slack)        >= l      s = +1,-1,+1,-1
 //     dense row (ND):                 a' x_c   (+ slack)        >= l      manipulability / self-collision
 //     eq row    (NE):                 a' x_c   -  tau           == b      M qddot - tau = -g
-//   every singleton appears in exactly one non-bound row.
-// Hence K = P + sigma I + A' diag(rho) A is [K_cc K_cd; K_dc diag] and the OSQP linear system
-// reduces EXACTLY to the NC x NC Schur complement S; with U = [I; A_dense] the per-iteration solve is
+//   every singleton appears in exactly one non-bound row ("bundle" = row + singleton + its bound row).
+// Hence K = P + sigma I + A' diag(rho) A is [K_cc K_cd; K_dc diag] and OSQP's linear system reduces
+// EXACTLY to the NC x NC Schur complement S; with U = [I; A_dense] one iteration's solve is
 //   [x~_c ; A_dense x~_c] = (U S^-1 U') u          u = [local right-hand sides ; dense-row terms]
-// i.e. one dot product of length GL = NC+ND+NE per lane against a vector exchanged through shared
-// memory.  The iterates are those of OSQP (same scaling, rho vector, relaxation, termination,
+// i.e. ONE dot product of length GL = NC+ND+NE per lane against a vector exchanged through shared
+// memory.  The iterates are OSQP's (same Ruiz scaling, rho vector, relaxation, termination and
 // infeasibility tests, adaptive rho); only the linear algebra of the KKT solve differs (QDLDL vs
-// Schur complement), which changes results at rounding level.
+// Schur complement) -- rounding-level differences.
+//
+// Row state is carried as v = alpha z~ + (1-alpha) z + y/rho, from which OSQP's iterates follow:
+//   z = Proj(v),  y = rho (v - Proj(v)),  rho z - y = rho (2 Proj(v) - v),  v+ = v + alpha (z~+ - Proj(v))
+// (one register per row instead of two, no divisions in the loop).
 //
 // Work mapping: a GROUP of GL lanes owns one robot; a warp carries NG = 32/GL robots.
-//   lane j < NC          : core variable j, its bound row, its KU unit rows (+slacks, +slack bounds)
-//   lane NC+r (r<ND+NE)  : dense / equality row r (+ singleton, + singleton bound)
-// Per-lane state lives in registers; the only cross-lane traffic is shared memory + __syncwarp().
-// The kernel body is written against a `Warp` executor so that tests/kernel_emu can run the
-// identical code on the CPU (lanes emulated by a loop).
+//   lane j < NC          : core variable j, its bound row, its KU unit bundles
+//   lane NC+r (r<ND+NE)  : dense / equality row r as bundle 0
+// Hot per-lane state lives in registers, cold data (scalings, deltas) in shared memory; the only
+// cross-lane traffic is shared memory + __syncwarp().  The hot loop is branch-free: absent rows /
+// singletons are encoded as zero coefficients.  The body is written against a `Warp` executor so
+// tests/kernel_emu can run the identical code on the CPU (lanes emulated by a loop).
 #pragma once
 #include "drc_math.h"
 
@@ -41,7 +46,7 @@ struct QpCfg {
   static constexpr int NR = ND + NE;                       // rows with a dense core part
   static constexpr int GL = NC + NR;                       // lanes per robot
   static constexpr int NG = 32 / GL;                       // robots per warp
-  static constexpr int NX = NC + (SLACK ? NC * KU + ND : 0) + NE;  // OSQP n (when every unit row is active)
+  static constexpr int NB = KU > 0 ? KU : 1;               // bundle slots per lane
   static constexpr int NPK = NC * (NC + 1) / 2;
   // per-robot record in global memory (doubles)
   static constexpr int OFF_P = 0;
@@ -53,6 +58,14 @@ struct QpCfg {
   static constexpr int STRIDE = OFF_ROW + NR * (NC + 1);
 };
 
+// 1/sqrt(x): the device uses the rsqrt sequence (cheaper than sqrt + divide), the host emulation 1/sqrt
+DRC_HD double inv_sqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 DRC_HD double limit_scaling(double d) {
   d = d < kMinScaling ? 1.0 : d;
   return d > kMaxScaling ? kMaxScaling : d;
@@ -67,56 +80,60 @@ DRC_HD int row_class(double l, double u) {
 }
 DRC_HD double class_rho(int cls, double rho) { return cls < 0 ? kRhoMin : (cls > 0 ? kRhoEqOverIneq * rho : rho); }
 
-// One constraint row together with the singleton variable it owns (if any) and that variable's
-// bound row (if any).  "cp" = core part of the row: a scalar on the lane's own core variable for unit
-// rows, a dense NC-vector (held by the lane) for dense/equality rows.
-struct Bundle {
-  // row
-  double E, l, u, z, y, dy;
-  int cls;
-  // singleton variable
-  double Dd, e, qd, xd, dxd;       // e = scaled coefficient of the singleton in the row
-  // singleton bound row
-  double Eb, beta, lb, ub, zb, yb, dyb;
-  int clsb;
-  // per-factorisation constants
-  double rho, rinv, rhob, rinvb, kinv, gam;
-  // scratch carried between phases
-  double bd, zt_keep;
-  bool active, has_sing, has_sb;
+// Hot part of a bundle (registers).
+struct BundleHot {
+  double c;      // core multiplier: scaled coefficient of the own variable (unit rows) | 1 (dense rows) | 0 (absent)
+  double v, vb;  // row state, singleton-bound-row state
+  double xd;     // singleton value (scaled)
+  double e, qd, beta, l;  // singleton coefficient in the row, its cost, its bound-row coefficient, row lower bound
+  double kinv, gam;       // 1/kappa, rho e / kappa
+  double pz, pzb, bd;     // scratch carried from phase A to phase B
 };
 
 template <class Cfg>
 struct Lane {
-  // group bookkeeping
-  int gl;        // lane within the group (0..GL-1), -1 for idle lanes
-  int grp;       // group within the warp
-  bool is_core;  // gl < NC
-  // core variable (core lanes)
-  double D, q, x, dx;
-  double Ecb, betac, lc, uc, zc, yc, dyc, rhoc, rinvc;  // core bound row
-  int clsc;
-  double a_unit[Cfg::KU > 0 ? Cfg::KU : 1];             // scaled coefficient of own variable in unit row k
-  Bundle ub[Cfg::KU > 0 ? Cfg::KU : 1];
-  // dense / equality row (row lanes)
-  Bundle rb;
-  // operator row  W' = U S^-1 U'
-  double w[Cfg::GL];
-  double ucore;  // scratch: local right-hand side
+  int gl, grp;            // lane within the group (-1 = idle), group within the warp
+  bool is_core;
+  bool done;               // register copy of the group's done flag (refreshed after every termination check)
+  bool row_eq;            // this lane's bundle rows are equalities  (projection onto {l})
+  bool sb_free;           // this lane's singleton bound rows are (-inf, inf)
+  double x, vc, q, betac, lc, uc, rhoc;  // core variable and its bound row
+  double sig, al;         // sigma / alpha on core lanes, 0 on row lanes
+  double rho_r, rho_b;    // rho of this lane's bundle rows / singleton bound rows
+  double pzc;             // scratch
+  double et;              // scratch (E_temp of a dense row during scaling)
+  BundleHot b[Cfg::NB];
+  double w[Cfg::GL];      // operator row of U S^-1 U'
 };
 
-// Shared scratch of one robot (group).
+// Cold per-lane data (shared memory; each slot is touched by its own lane only).
+template <class Cfg>
+struct ColdLane {
+  double D, Ecb, dx, dyc, Dinv, Ecbinv;
+  double E[Cfg::NB], Eb[Cfg::NB], Dd[Cfg::NB], dxd[Cfg::NB], dy[Cfg::NB], dyb[Cfg::NB];
+  double Einv[Cfg::NB], Ebinv[Cfg::NB], Ddinv[Cfg::NB];
+  int clsc, cls[Cfg::NB], clsb[Cfg::NB];
+  unsigned char active[Cfg::NB], has_sing[Cfg::NB], has_sb[Cfg::NB];
+};
+
 constexpr int kNumRed = 22;  // group-wide reductions of one termination check
 template <class Cfg>
 struct GroupShared {
+  double u[Cfg::GL];                                 // exchange vector of the hot loop
+  double v[Cfg::GL];                                 // second exchange vector (checks, setup)
   double P[Cfg::NC * Cfg::NC];                       // scaled P_cc (symmetric, dense)
   double A[(Cfg::NR > 0 ? Cfg::NR : 1) * Cfg::NC];   // scaled dense-row coefficients
-  double S[Cfg::NC * Cfg::NC];                       // Schur complement -> its inverse
-  double T[(Cfg::NR > 0 ? Cfg::NR : 1) * Cfg::NC];   // S^-1 a_r
-  double u[Cfg::GL];                                 // exchange vector (x_c | row terms)
-  double v[Cfg::GL];                                 // second exchange vector
-  double red[Cfg::GL * kNumRed];                     // per-lane partial reductions
-  double c, cinv, rho;
+  // S (Schur complement -> inverse) and T (S^-1 a_r) live only inside factor(); red (per-lane partial
+  // reductions) only inside the scaling / check phases: they share storage.
+  static constexpr int kST = Cfg::NC * Cfg::NC + (Cfg::NR > 0 ? Cfg::NR : 1) * Cfg::NC;
+  static constexpr int kScr = kST > Cfg::GL * kNumRed ? kST : Cfg::GL * kNumRed;
+  union {
+    struct { double S[Cfg::NC * Cfg::NC]; double T[(Cfg::NR > 0 ? Cfg::NR : 1) * Cfg::NC]; };
+    double red[kScr];
+  };
+  ColdLane<Cfg> cold[Cfg::GL];
+  double tot[kNumRed];                               // group totals of one termination check
+  double c, cinv, rho, rho_prev;
   double pri_res, dua_res;
   int status, iters, done, robot, nx, rho_updates, need_factor;
 };
@@ -134,71 +151,6 @@ DRC_HD QpOptions qp_options(const DrcParams& p, unsigned unit_mask) {
   o.scaling = p.scaling; o.adaptive_rho = p.adaptive_rho; o.adaptive_rho_interval = p.adaptive_rho_interval;
   o.unit_mask = unit_mask;
   return o;
-}
-
-// ------------------------------------------------------------------------------------------------
-// bundle helpers
-// ------------------------------------------------------------------------------------------------
-DRC_HD void bundle_init(Bundle& b, bool active, double l, double u, bool has_sing, double e, double qd, bool has_sb,
-                        double lb, double ub) {
-  b.active = active; b.has_sing = active && has_sing; b.has_sb = b.has_sing && has_sb;
-  b.E = 1.0; b.l = l; b.u = u; b.z = 0; b.y = 0; b.dy = 0; b.cls = 0;
-  b.Dd = 1.0; b.e = b.has_sing ? e : 0.0; b.qd = b.has_sing ? qd : 0.0; b.xd = 0; b.dxd = 0;
-  b.Eb = 1.0; b.beta = b.has_sb ? 1.0 : 0.0; b.lb = lb; b.ub = ub; b.zb = 0; b.yb = 0; b.dyb = 0; b.clsb = 0;
-  b.rho = b.rinv = b.rhob = b.rinvb = b.kinv = b.gam = 0; b.bd = 0; b.zt_keep = 0;
-}
-// finish scaling: scaled bounds + OSQP constraint classes
-DRC_HD void bundle_finalize(Bundle& b) {
-  if (!b.active) return;
-  b.l *= b.E; b.u *= b.E;
-  b.cls = row_class(b.l, b.u);
-  if (b.has_sb) { b.lb *= b.Eb; b.ub *= b.Eb; b.clsb = row_class(b.lb, b.ub); }
-}
-// per-factorisation constants; returns omega = effective rho of the row after eliminating the singleton
-DRC_HD double bundle_factor(Bundle& b, double rho, double sigma) {
-  if (!b.active) return 0.0;
-  b.rho = class_rho(b.cls, rho); b.rinv = 1.0 / b.rho;
-  if (!b.has_sing) { b.kinv = 0; b.gam = 0; return b.rho; }
-  double kap = sigma + b.rho * b.e * b.e;
-  if (b.has_sb) { b.rhob = class_rho(b.clsb, rho); b.rinvb = 1.0 / b.rhob; kap += b.rhob * b.beta * b.beta; }
-  b.kinv = 1.0 / kap;
-  b.gam = b.rho * b.e * b.kinv;
-  return b.rho * (1.0 - b.gam * b.e);
-}
-// first half of an iteration: returns t (the row's contribution weight to the core right-hand side)
-DRC_HD double bundle_pre(Bundle& b, double sigma) {
-  if (!b.active) return 0.0;
-  const double wr = b.rho * b.z - b.y;
-  if (!b.has_sing) return wr;
-  double bd = sigma * b.xd - b.qd + b.e * wr;
-  if (b.has_sb) bd += b.beta * (b.rhob * b.zb - b.yb);
-  b.bd = bd;
-  return wr - b.gam * bd;
-}
-DRC_HD double proj(double v, double l, double u) { return dmin(dmax(v, l), u); }
-// second half: s = core part of the row applied to x~_c
-DRC_HD void bundle_post(Bundle& b, double s, double alpha, bool keep_delta) {
-  if (!b.active) return;
-  double zt = s;
-  if (b.has_sing) {
-    const double xtd = b.kinv * b.bd - b.gam * s;
-    zt += b.e * xtd;
-    const double xn = alpha * xtd + (1.0 - alpha) * b.xd;
-    if (keep_delta) b.dxd = xn - b.xd;
-    b.xd = xn;
-    if (b.has_sb) {
-      const double zr = alpha * (b.beta * xtd) + (1.0 - alpha) * b.zb;
-      const double zn = proj(zr + b.yb * b.rinvb, b.lb, b.ub);
-      const double d = b.rhob * (zr - zn);
-      if (keep_delta) b.dyb = d;
-      b.yb += d; b.zb = zn;
-    }
-  }
-  const double zr = alpha * zt + (1.0 - alpha) * b.z;
-  const double zn = proj(zr + b.y * b.rinv, b.l, b.u);
-  const double d = b.rho * (zr - zn);
-  if (keep_delta) b.dy = d;
-  b.y += d; b.z = zn;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -231,23 +183,30 @@ struct WarpEmu {
   GroupShared<Cfg>& group(int g) { return sh[g]; }
 };
 
+// projections of the row kinds
+template <class LaneT>
+DRC_HD double proj_row(const LaneT& L, double v, double l) { return L.row_eq ? l : dmax(v, l); }
+template <class LaneT>
+DRC_HD double proj_sb(const LaneT& L, double v) { return L.sb_free ? v : dmax(v, 0.0); }
 
 // ------------------------------------------------------------------------------------------------
 // The solver.  `qp` points at the per-robot records (Cfg::STRIDE doubles each); robots[g] is the
-// robot handled by group g of this warp (-1 = none).  On return the (scaled) iterates are still in
-// the lanes; the caller unscales what it needs:  x_c[j] = D * x   (core lane j),
-// singleton = Dd * xd (bundle), and reads status / iters from the group's shared record.
+// robot handled by group g of this warp (-1 = none).  On return the scaled iterates are still in
+// the lanes; the caller unscales what it needs (x_c[j] = D x, singleton = Dd xd with D, Dd in the
+// group's cold data) and reads status / iters from the group's shared record.
 // ------------------------------------------------------------------------------------------------
 template <class Cfg, class W>
 DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOptions& o) {
-  constexpr int NC = Cfg::NC, KU = Cfg::KU, ND = Cfg::ND, NR = Cfg::NR, GL = Cfg::GL, NG = Cfg::NG;
+  constexpr int NC = Cfg::NC, KU = Cfg::KU, ND = Cfg::ND, NR = Cfg::NR, GL = Cfg::GL, NG = Cfg::NG, NB = Cfg::NB;
   typedef Lane<Cfg> LaneT;
   typedef GroupShared<Cfg> GS;
-  const double sigma = o.sigma, alpha = o.alpha;
+  typedef ColdLane<Cfg> Cold;
+  const double sigma = o.sigma, alpha = o.alpha, oma = 1.0 - o.alpha;
 
   // ---------------------------------------------------------------- load
   w.each([&](LaneT& L, GS& S) {
     const int rb = robots[L.grp];
+    Cold& C = S.cold[L.gl];
     if (L.gl == 0) {
       S.robot = rb; S.status = kQpUnsolved; S.iters = 0; S.done = rb < 0 ? 1 : 0; S.c = 1.0; S.rho_updates = 0;
       S.need_factor = 0; S.pri_res = 0; S.dua_res = 0;
@@ -255,11 +214,19 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       for (int j = 0; j < NC; ++j) na += (int)((o.unit_mask >> j) & 1u);
       S.nx = NC + (Cfg::SLACK ? na * KU + ND : 0) + Cfg::NE;
     }
-    L.dx = 0; L.dyc = 0; L.x = 0; L.zc = 0; L.yc = 0; L.ucore = 0; L.q = 0; L.D = 1; L.Ecb = 1; L.betac = 0;
-    L.lc = -kOsqpInfty; L.uc = kOsqpInfty; L.rhoc = 0; L.rinvc = 0; L.clsc = -1;
+    L.x = 0; L.vc = 0; L.q = 0; L.betac = 0; L.lc = -kOsqpInfty; L.uc = kOsqpInfty; L.rhoc = 0;
+    L.sig = L.is_core ? sigma : 0.0; L.al = L.is_core ? alpha : 0.0;
+    L.rho_r = 0; L.rho_b = 0; L.pzc = 0; L.et = 1.0;
+    L.row_eq = false; L.sb_free = false; L.done = rb < 0;
+    C.D = 1; C.Ecb = 1; C.dx = 0; C.dyc = 0; C.clsc = -1;
 #pragma unroll
-    for (int k = 0; k < KU; ++k) { L.a_unit[k] = 0; bundle_init(L.ub[k], false, 0, 0, false, 0, 0, false, 0, 0); }
-    bundle_init(L.rb, false, 0, 0, false, 0, 0, false, 0, 0);
+    for (int k = 0; k < NB; ++k) {
+      BundleHot& b = L.b[k];
+      b.c = 0; b.v = 0; b.vb = 0; b.xd = 0; b.e = 0; b.qd = 0; b.beta = 0; b.l = -kOsqpInfty; b.kinv = 0; b.gam = 0;
+      b.pz = 0; b.pzb = 0; b.bd = 0;
+      C.E[k] = 1; C.Eb[k] = 1; C.Dd[k] = 1; C.dxd[k] = 0; C.dy[k] = 0; C.dyb[k] = 0; C.cls[k] = 0; C.clsb[k] = 0;
+      C.active[k] = 0; C.has_sing[k] = 0; C.has_sb[k] = 0;
+    }
     if (rb < 0) return;
     const double* rec = qp + (long long)rb * Cfg::STRIDE;
     if (L.is_core) {
@@ -271,18 +238,33 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       const bool act = ((o.unit_mask >> j) & 1u) != 0u;
 #pragma unroll
       for (int k = 0; k < KU; ++k) {
-        L.a_unit[k] = act ? ((k & 1) ? -1.0 : 1.0) : 0.0;
-        bundle_init(L.ub[k], act, rec[Cfg::OFF_UNIT + k * NC + j], kOsqpInfty, Cfg::SLACK, 1.0, o.slack_weight,
-                    Cfg::BOUNDS, 0.0, kOsqpInfty);
+        if (!act) continue;
+        BundleHot& b = L.b[k];
+        C.active[k] = 1;
+        b.c = (k & 1) ? -1.0 : 1.0;
+        b.l = rec[Cfg::OFF_UNIT + k * NC + j];
+        if (Cfg::SLACK) {
+          C.has_sing[k] = 1; b.e = 1.0; b.qd = o.slack_weight;
+          if (Cfg::BOUNDS) { C.has_sb[k] = 1; b.beta = 1.0; }
+        }
       }
     } else {
       const int r = L.gl - NC;
       const double* row = rec + Cfg::OFF_ROW + r * (NC + 1);
 #pragma unroll
       for (int i = 0; i < NC; ++i) S.A[r * NC + i] = row[i];
-      const double l = row[NC];
-      if (r >= ND) bundle_init(L.rb, true, l, l, true, -1.0, 0.0, Cfg::BOUNDS, -kOsqpInfty, kOsqpInfty);
-      else bundle_init(L.rb, true, l, kOsqpInfty, Cfg::SLACK, 1.0, o.slack_weight, Cfg::BOUNDS, 0.0, kOsqpInfty);
+      BundleHot& b = L.b[0];
+      C.active[0] = 1;
+      b.c = 1.0;
+      b.l = row[NC];
+      if (r >= ND) {  // equality row with its torque singleton
+        L.row_eq = true; L.sb_free = true;
+        C.has_sing[0] = 1; b.e = -1.0; b.qd = 0.0;
+        if (Cfg::BOUNDS) { C.has_sb[0] = 1; b.beta = 1.0; }
+      } else if (Cfg::SLACK) {
+        C.has_sing[0] = 1; b.e = 1.0; b.qd = o.slack_weight;
+        if (Cfg::BOUNDS) { C.has_sb[0] = 1; b.beta = 1.0; }
+      }
     }
   });
 
@@ -298,48 +280,51 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
 #pragma unroll
       for (int r = 0; r < NR; ++r) cn = dmax(cn, fabs(S.A[r * NC + j]));
 #pragma unroll
-      for (int k = 0; k < KU; ++k) cn = dmax(cn, fabs(L.a_unit[k]));
-      S.u[j] = 1.0 / sqrt(limit_scaling(cn));
+      for (int k = 0; k < KU; ++k) cn = dmax(cn, fabs(L.b[k].c));
+      S.u[j] = inv_sqrt(limit_scaling(cn));
     });
     // (2) E_temp of every row, D_temp of the singleton columns; apply to everything lane-local
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
-      auto scale_bundle = [&](Bundle& b, double core_norm) -> double {
-        if (!b.active) return 1.0;
+      Cold& C = S.cold[L.gl];
+      auto scale_bundle = [&](int k, double core_norm) -> double {
+        BundleHot& b = L.b[k];
+        if (!C.active[k]) return 1.0;
         double dt = 1.0, eb = 1.0;
-        if (b.has_sing) {
+        if (C.has_sing[k]) {
           double cn = fabs(b.e);
-          if (b.has_sb) { cn = dmax(cn, fabs(b.beta)); eb = 1.0 / sqrt(limit_scaling(fabs(b.beta))); }
-          dt = 1.0 / sqrt(limit_scaling(cn));
+          if (C.has_sb[k]) { cn = dmax(cn, fabs(b.beta)); eb = inv_sqrt(limit_scaling(fabs(b.beta))); }
+          dt = inv_sqrt(limit_scaling(cn));
         }
-        const double et = 1.0 / sqrt(limit_scaling(dmax(core_norm, fabs(b.e))));
-        b.E *= et;
-        if (b.has_sing) {
-          b.e *= et * dt; b.Dd *= dt; b.qd *= dt;
-          if (b.has_sb) { b.beta *= eb * dt; b.Eb *= eb; }
+        const double et = inv_sqrt(limit_scaling(dmax(core_norm, fabs(b.e))));
+        C.E[k] *= et;
+        if (C.has_sing[k]) {
+          b.e *= et * dt; C.Dd[k] *= dt; b.qd *= dt;
+          if (C.has_sb[k]) { b.beta *= eb * dt; C.Eb[k] *= eb; }
         }
         return et;
       };
       if (L.is_core) {
         const double dj = S.u[L.gl];
-        if (Cfg::BOUNDS) { const double eb = 1.0 / sqrt(limit_scaling(fabs(L.betac))); L.betac *= eb * dj; L.Ecb *= eb; }
+        if (Cfg::BOUNDS) { const double eb = inv_sqrt(limit_scaling(fabs(L.betac))); L.betac *= eb * dj; C.Ecb *= eb; }
 #pragma unroll
         for (int k = 0; k < KU; ++k) {
-          const double et = scale_bundle(L.ub[k], fabs(L.a_unit[k]));
-          L.a_unit[k] *= et * dj;
+          const double et = scale_bundle(k, fabs(L.b[k].c));
+          L.b[k].c *= et * dj;
         }
-        L.q *= dj; L.D *= dj;
+        L.q *= dj; C.D *= dj;
       } else {
         const int r = L.gl - NC;
         double rn = 0;
 #pragma unroll
         for (int i = 0; i < NC; ++i) rn = dmax(rn, fabs(S.A[r * NC + i]));
-        L.ucore = scale_bundle(L.rb, rn);  // E_temp of the dense row, applied to S.A in (3)
+        L.et = scale_bundle(0, rn);  // E_temp of the dense row, applied to S.A in (3)
       }
     });
     // (3) scale P and the dense rows; publish the inputs of the cost normalisation
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
+      Cold& C = S.cold[L.gl];
       double cn = 0, qm = 0;
       if (L.is_core) {
         const int j = L.gl;
@@ -348,12 +333,12 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         for (int i = 0; i < NC; ++i) { const double pv = S.P[j * NC + i] * dj * S.u[i]; S.P[j * NC + i] = pv; cn = dmax(cn, fabs(pv)); }
         qm = fabs(L.q);
 #pragma unroll
-        for (int k = 0; k < KU; ++k) if (L.ub[k].has_sing) qm = dmax(qm, fabs(L.ub[k].qd));
+        for (int k = 0; k < KU; ++k) if (C.has_sing[k]) qm = dmax(qm, fabs(L.b[k].qd));
       } else {
         const int r = L.gl - NC;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) S.A[r * NC + i] *= L.ucore * S.u[i];
-        if (L.rb.has_sing) qm = fabs(L.rb.qd);
+        for (int i = 0; i < NC; ++i) S.A[r * NC + i] *= L.et * S.u[i];
+        if (C.has_sing[0]) qm = fabs(L.b[0].qd);
       }
       S.red[L.gl] = cn; S.red[GL + L.gl] = qm;
     });
@@ -368,44 +353,74 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         const int j = L.gl;
         L.q *= ct;
 #pragma unroll
-        for (int k = 0; k < KU; ++k) L.ub[k].qd *= ct;
-#pragma unroll
         for (int i = 0; i < NC; ++i) S.P[j * NC + i] *= ct;
-      } else {
-        L.rb.qd *= ct;
       }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) L.b[k].qd *= ct;
       if (L.gl == 0) S.c *= ct;
     });
   }
   // scaled bounds, constraint classes
   w.each([&](LaneT& L, GS& S) {
     if (S.done) return;
-    if (L.is_core) {
-      if (Cfg::BOUNDS) { L.lc *= L.Ecb; L.uc *= L.Ecb; L.clsc = row_class(L.lc, L.uc); }
+    Cold& C = S.cold[L.gl];
+    if (L.is_core && Cfg::BOUNDS) { L.lc *= C.Ecb; L.uc *= C.Ecb; C.clsc = row_class(L.lc, L.uc); }
+    C.Dinv = 1.0 / C.D; C.Ecbinv = 1.0 / C.Ecb;
 #pragma unroll
-      for (int k = 0; k < KU; ++k) bundle_finalize(L.ub[k]);
-    } else {
-      bundle_finalize(L.rb);
+    for (int k = 0; k < NB; ++k) {
+      C.Einv[k] = 1.0 / C.E[k]; C.Ebinv[k] = 1.0 / C.Eb[k]; C.Ddinv[k] = 1.0 / C.Dd[k];
+      if (!C.active[k]) continue;
+      L.b[k].l *= C.E[k];
+      const double us = L.row_eq ? L.b[k].l : kOsqpInfty * C.E[k];
+      C.cls[k] = row_class(L.b[k].l, us);
+      if (C.has_sb[k]) C.clsb[k] = L.sb_free ? row_class(-kOsqpInfty * C.Eb[k], kOsqpInfty * C.Eb[k]) : row_class(0.0, kOsqpInfty * C.Eb[k]);
     }
-    if (L.gl == 0) { S.cinv = 1.0 / S.c; S.rho = dmin(dmax(o.rho, kRhoMin), kRhoMax); S.need_factor = 1; }
+    if (L.gl == 0) { S.cinv = 1.0 / S.c; S.rho = dmin(dmax(o.rho, kRhoMin), kRhoMax); S.rho_prev = S.rho; S.need_factor = 1; }
   });
 
   // ---------------------------------------------------------------- factorisation (setup and rho updates)
   auto factor = [&]() {
-    // (a) Schur complement S = P + sigma I + diag(bound, unit rows) + sum_r omega_r a_r a_r'
+    // (a) rho vector, per-bundle constants, Schur complement S = P + sigma I + diag(...) + sum_r omega_r a_r a_r'
     w.each([&](LaneT& L, GS& S) {
       if (!S.need_factor) return;
-      const double rho = S.rho;
+      Cold& C = S.cold[L.gl];
+      const double rho = S.rho, ratio = S.rho_prev / S.rho;
+      double diag = sigma, omega0 = 0;
+      if (L.is_core && Cfg::BOUNDS) {
+        const double rn = class_rho(C.clsc, rho);
+        if (C.clsc >= 0) { const double pz = clampd(L.vc, L.lc, L.uc); L.vc = pz + ratio * (L.vc - pz); }
+        L.rhoc = rn;
+        diag += rn * L.betac * L.betac;
+      }
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        BundleHot& b = L.b[k];
+        if (!C.active[k]) continue;
+        const double rr = class_rho(C.cls[k], rho);
+        if (C.cls[k] >= 0) { const double pz = proj_row(L, b.v, b.l); b.v = pz + ratio * (b.v - pz); }
+        L.rho_r = rr;
+        double omega = rr;
+        if (C.has_sing[k]) {
+          double kap = sigma + rr * b.e * b.e;
+          if (C.has_sb[k]) {
+            const double rbv = class_rho(C.clsb[k], rho);
+            if (C.clsb[k] >= 0) { const double pz = proj_sb(L, b.vb); b.vb = pz + ratio * (b.vb - pz); }
+            L.rho_b = rbv;
+            kap += rbv * b.beta * b.beta;
+          }
+          b.kinv = 1.0 / kap;
+          b.gam = rr * b.e * b.kinv;
+          omega = rr * (1.0 - b.gam * b.e);
+        }
+        if (L.is_core) diag += omega * b.c * b.c;
+        else omega0 = omega;
+      }
       if (L.is_core) {
         const int j = L.gl;
-        double diag = sigma;
-        if (Cfg::BOUNDS) { L.rhoc = class_rho(L.clsc, rho); L.rinvc = 1.0 / L.rhoc; diag += L.rhoc * L.betac * L.betac; }
-#pragma unroll
-        for (int k = 0; k < KU; ++k) diag += bundle_factor(L.ub[k], rho, sigma) * L.a_unit[k] * L.a_unit[k];
 #pragma unroll
         for (int i = 0; i < NC; ++i) S.S[j * NC + i] = S.P[j * NC + i] + (i == j ? diag : 0.0);
       } else {
-        S.v[L.gl] = bundle_factor(L.rb, rho, sigma);
+        S.v[L.gl] = omega0;
       }
     });
     w.each([&](LaneT& L, GS& S) {
@@ -476,112 +491,197 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         }
       }
     });
-    w.each([&](LaneT& L, GS& S) { if (L.gl == 0) S.need_factor = 0; });
+    w.each([&](LaneT& L, GS& S) { if (L.gl == 0) { S.need_factor = 0; S.rho_prev = S.rho; } });
   };
-  factor();
-
   auto warp_done = [&]() {
     bool d = true;
     for (int g = 0; g < NG; ++g) d = d && (w.group(g).done != 0);
     return d;
   };
 
+  // ---------------------------------------------------------------- hot loop phases (branch-free)
+  // phase A: u = [sigma x - q + A_local'(rho z - y) ; t_r]
+  // (OSQP's cold start sets z = y = 0 without projecting: on the first iteration Proj(v) is replaced by 0)
+  auto phase_a_impl = [&](LaneT& L, GS& S, const bool first) {
+    if (L.done) return;
+    const double pzc = first ? 0.0 : clampd(L.vc, L.lc, L.uc);
+    L.pzc = pzc;
+    double u = L.sig * L.x - L.q + L.betac * (L.rhoc * (2.0 * pzc - L.vc));
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      BundleHot& b = L.b[k];
+      const double pz = first ? 0.0 : proj_row(L, b.v, b.l), pzb = first ? 0.0 : proj_sb(L, b.vb);
+      const double wr = L.rho_r * (2.0 * pz - b.v), wb = L.rho_b * (2.0 * pzb - b.vb);
+      const double bd = sigma * b.xd - b.qd + b.e * wr + b.beta * wb;
+      b.pz = pz; b.pzb = pzb; b.bd = bd;
+      u += b.c * (wr - b.gam * bd);
+    }
+    S.u[L.gl] = u;
+  };
+  auto phase_a = [&](LaneT& L, GS& S) { phase_a_impl(L, S, false); };
+  auto phase_a_first = [&](LaneT& L, GS& S) { phase_a_impl(L, S, true); };
+  // phase B: s = (U S^-1 U' u)_lane, then the x / v updates
+  auto phase_b = [&](LaneT& L, GS& S) {
+    if (L.done) return;
+    double s0 = 0, s1 = 0, s2 = 0;  // three independent chains (fp64 FMA latency)
+#pragma unroll
+    for (int i = 0; i < GL; i += 3) {
+      s0 += L.w[i] * S.u[i];
+      if (i + 1 < GL) s1 += L.w[i + 1] * S.u[i + 1];
+      if (i + 2 < GL) s2 += L.w[i + 2] * S.u[i + 2];
+    }
+    const double s = (s0 + s1) + s2;
+    L.x = L.al * s + oma * L.x;
+    L.vc += alpha * (L.betac * s - L.pzc);
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      BundleHot& b = L.b[k];
+      const double sk = b.c * s;
+      const double xtd = b.kinv * b.bd - b.gam * sk;
+      b.v += alpha * (sk + b.e * xtd - b.pz);
+      b.vb += alpha * (b.beta * xtd - b.pzb);
+      b.xd = alpha * xtd + oma * b.xd;
+    }
+  };
+  // phase B on a checked iteration: also records delta_x / delta_y of this iteration (cold data)
+  auto phase_b_keep = [&](LaneT& L, GS& S) {
+    if (L.done) return;
+    Cold& C = S.cold[L.gl];
+    double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < GL; i += 3) {
+      s0 += L.w[i] * S.u[i];
+      if (i + 1 < GL) s1 += L.w[i + 1] * S.u[i + 1];
+      if (i + 2 < GL) s2 += L.w[i + 2] * S.u[i + 2];
+    }
+    const double s = (s0 + s1) + s2;
+    const double xn = L.al * s + oma * L.x;
+    C.dx = xn - L.x;
+    L.x = xn;
+    {
+      const double y0 = L.rhoc * (L.vc - L.pzc);
+      L.vc += alpha * (L.betac * s - L.pzc);
+      C.dyc = L.rhoc * (L.vc - clampd(L.vc, L.lc, L.uc)) - y0;
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      BundleHot& b = L.b[k];
+      const double sk = b.c * s;
+      const double xtd = b.kinv * b.bd - b.gam * sk;
+      const double y0 = L.rho_r * (b.v - b.pz), yb0 = L.rho_b * (b.vb - b.pzb);
+      b.v += alpha * (sk + b.e * xtd - b.pz);
+      b.vb += alpha * (b.beta * xtd - b.pzb);
+      const double xdn = alpha * xtd + oma * b.xd;
+      C.dxd[k] = xdn - b.xd;
+      b.xd = xdn;
+      C.dy[k] = L.rho_r * (b.v - proj_row(L, b.v, b.l)) - y0;
+      C.dyb[k] = L.rho_b * (b.vb - proj_sb(L, b.vb)) - yb0;
+    }
+  };
+
   // ---------------------------------------------------------------- ADMM iterations (osqp_solve)
   int iter = 0;
   bool all_done = warp_done();
+  const int chk = o.check_termination > 0 ? o.check_termination : 0x7fffffff;
+  const int adp = (o.adaptive_rho && o.adaptive_rho_interval > 0) ? o.adaptive_rho_interval : 0x7fffffff;
+  int to_check = chk, to_adapt = adp;  // iterations left until the next termination check / rho adaptation
   while (!all_done && iter < o.max_iter) {
-    ++iter;
+    {  // (re)factorise when a group asks for it: setup, and after an accepted rho update
+      bool nf = false;
+      for (int g = 0; g < NG; ++g) nf = nf || (w.group(g).need_factor != 0 && w.group(g).done == 0);
+      if (nf) factor();
+    }
+    // plain iterations up to (excluding) the next event: nothing but the two hot phases
+    int nplain = to_check < to_adapt ? to_check : to_adapt;
+    if (nplain > o.max_iter - iter) nplain = o.max_iter - iter;
+    nplain -= 1;
+    for (int k = 0; k < nplain; ++k) {
+      ++iter;
+      if (iter == 1) w.each(phase_a_first); else w.each(phase_a);
+      w.each(phase_b);
+    }
+    to_check -= nplain; to_adapt -= nplain;
+    // the event iteration
+    ++iter; --to_check; --to_adapt;
     const bool last = iter == o.max_iter;
-    const bool can_check = (o.check_termination > 0 && (iter % o.check_termination == 0)) || last;
-    const bool can_adapt = o.adaptive_rho && o.adaptive_rho_interval > 0 && (iter % o.adaptive_rho_interval == 0);
-    // phase A: local right-hand sides  u = [sigma x - q + A_local'(rho z - y) ; t_r]
-    w.each([&](LaneT& L, GS& S) {
-      if (S.done) return;
-      if (L.is_core) {
-        double uc = sigma * L.x - L.q;
-        if (Cfg::BOUNDS) uc += L.betac * (L.rhoc * L.zc - L.yc);
-#pragma unroll
-        for (int k = 0; k < KU; ++k) uc += L.a_unit[k] * bundle_pre(L.ub[k], sigma);
-        S.u[L.gl] = uc;
-      } else {
-        S.u[L.gl] = bundle_pre(L.rb, sigma);
-      }
-    });
-    // phase B: [x~_c ; A_dense x~_c] = (U S^-1 U') u, then the x / z / y updates
-    w.each([&](LaneT& L, GS& S) {
-      if (S.done) return;
-      double s = 0;
-#pragma unroll
-      for (int i = 0; i < GL; ++i) s += L.w[i] * S.u[i];
-      if (L.is_core) {
-#pragma unroll
-        for (int k = 0; k < KU; ++k) bundle_post(L.ub[k], L.a_unit[k] * s, alpha, can_check);
-        const double xn = alpha * s + (1.0 - alpha) * L.x;
-        if (can_check) L.dx = xn - L.x;
-        L.x = xn;
-        if (Cfg::BOUNDS) {
-          const double zr = alpha * (L.betac * s) + (1.0 - alpha) * L.zc;
-          const double zn = proj(zr + L.yc * L.rinvc, L.lc, L.uc);
-          const double d = L.rhoc * (zr - zn);
-          if (can_check) L.dyc = d;
-          L.yc += d; L.zc = zn;
-        }
-      } else {
-        bundle_post(L.rb, s, alpha, can_check);
-      }
-    });
-    if (!(can_check || can_adapt)) continue;
+    const bool can_check = to_check == 0 || last;
+    const bool can_adapt = to_adapt == 0;
+    if (to_check == 0) to_check = chk;
+    if (to_adapt == 0) to_adapt = adp;
+    if (iter == 1) w.each(phase_a_first); else w.each(phase_a);
+    w.each(phase_b_keep);
 
     // ---------------- OSQP update_info + check_termination + adapt_rho
     // project delta_y onto the polar of the recession cone of [l,u] (is_primal_infeasible)
-    auto proj_dy = [](double dy, double l, double u) {
-      if (is_inf_hi(u)) return is_inf_lo(l) ? 0.0 : dmin(dy, 0.0);
-      if (is_inf_lo(l)) return dmax(dy, 0.0);
+    auto proj_dy = [](double dy, bool lo_inf, bool hi_inf) {
+      if (hi_inf) return lo_inf ? 0.0 : dmin(dy, 0.0);
+      if (lo_inf) return dmax(dy, 0.0);
       return dy;
     };
     // C0: exchange x_c | y_r and dx_c | projected dy_r
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
-      if (L.is_core) { S.u[L.gl] = L.x; S.v[L.gl] = L.dx; }
-      else { S.u[L.gl] = L.rb.y; S.v[L.gl] = proj_dy(L.rb.dy, L.rb.l, L.rb.u); }
+      Cold& C = S.cold[L.gl];
+      if (L.is_core) { S.u[L.gl] = L.x; S.v[L.gl] = C.dx; }
+      else {
+        const BundleHot& b = L.b[0];
+        S.u[L.gl] = L.rho_r * (b.v - proj_row(L, b.v, b.l));
+        S.v[L.gl] = proj_dy(C.dy[0], is_inf_lo(b.l), !L.row_eq && is_inf_hi(kOsqpInfty * C.E[0]));
+      }
     });
     // C1: per-lane partial reductions
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
-      double m[kNumRed];
+      Cold& C = S.cold[L.gl];
+      // accumulate straight into this lane's shared-memory slots (keeps the register peak of the kernel low)
+      struct Acc {
+        double* base;
+        DRC_HD double& operator[](int i) const { return base[i * Cfg::GL]; }
+      };
+      const Acc m = {S.red + L.gl};
 #pragma unroll
       for (int i = 0; i < kNumRed; ++i) m[i] = 0.0;
       m[20] = -1e300; m[21] = 1e300;
       // rows:      0 pri_u 1 ax_u 2 z_u | 7 pri_s 8 ax_s 9 z_s | 14 ||E dy|| 15 sum(u dy+ + l dy-) | 20 max Adx (finite u) 21 min Adx (finite l)
       // variables: 3 dua_u 4 px_u 5 aty_u 6 q_u | 10 dua_s 11 px_s 12 aty_s 13 q_s | 16 ||Dinv A'dy|| | 17 ||D dx|| 18 q'dx 19 ||Dinv P dx||
-      auto row_acc = [&](double ax, double z, double E, double l, double u, double dy, double adx) {
-        const double Ei = 1.0 / E, r = ax - z;
+      auto row_acc = [&](double ax, double z, double E, double Ei, double l, double u, bool lo_inf, bool hi_inf, double dy, double adx) {
+        const double r = ax - z;
         m[0] = dmax(m[0], fabs(Ei * r)); m[1] = dmax(m[1], fabs(Ei * ax)); m[2] = dmax(m[2], fabs(Ei * z));
         m[7] = dmax(m[7], fabs(r)); m[8] = dmax(m[8], fabs(ax)); m[9] = dmax(m[9], fabs(z));
-        const double pdy = proj_dy(dy, l, u);
+        const double pdy = proj_dy(dy, lo_inf, hi_inf);
         m[14] = dmax(m[14], fabs(E * pdy));
         m[15] += u * dmax(pdy, 0.0) + l * dmin(pdy, 0.0);
-        if (!is_inf_hi(u)) m[20] = dmax(m[20], Ei * adx);
-        if (!is_inf_lo(l)) m[21] = dmin(m[21], Ei * adx);
+        if (!hi_inf) m[20] = dmax(m[20], Ei * adx);
+        if (!lo_inf) m[21] = dmin(m[21], Ei * adx);
       };
-      auto var_acc = [&](double px, double aty, double q, double D, double atdy, double dx, double pdx) {
-        const double Di = 1.0 / D, r = px + q + aty;
+      auto var_acc = [&](double px, double aty, double q, double D, double Di, double atdy, double dx, double pdx) {
+        const double r = px + q + aty;
         m[3] = dmax(m[3], fabs(Di * r)); m[4] = dmax(m[4], fabs(Di * px)); m[5] = dmax(m[5], fabs(Di * aty)); m[6] = dmax(m[6], fabs(Di * q));
         m[10] = dmax(m[10], fabs(r)); m[11] = dmax(m[11], fabs(px)); m[12] = dmax(m[12], fabs(aty)); m[13] = dmax(m[13], fabs(q));
         m[16] = dmax(m[16], fabs(Di * atdy));
         m[17] = dmax(m[17], fabs(D * dx)); m[18] += q * dx; m[19] = dmax(m[19], fabs(Di * pdx));
       };
-      // a bundle: its row, its singleton variable and that variable's bound row
-      auto bundle_acc = [&](const Bundle& b, double core_ax, double core_adx) {
-        if (!b.active) return;
-        row_acc(core_ax + (b.has_sing ? b.e * b.xd : 0.0), b.z, b.E, b.l, b.u, b.dy, core_adx + (b.has_sing ? b.e * b.dxd : 0.0));
-        if (b.has_sing) {
-          double aty = b.e * b.y, atdy = b.e * proj_dy(b.dy, b.l, b.u);
-          if (b.has_sb) {
-            aty += b.beta * b.yb; atdy += b.beta * proj_dy(b.dyb, b.lb, b.ub);
-            row_acc(b.beta * b.xd, b.zb, b.Eb, b.lb, b.ub, b.dyb, b.beta * b.dxd);
+      // a bundle: its row, its singleton variable and that variable's bound row; y_out / pdy_out return the
+      // row's multiplier and projected delta for the core column sum (core lanes)
+      auto bundle_acc = [&](int k, double core_ax, double core_adx, double& y_out, double& pdy_out) {
+        y_out = 0; pdy_out = 0;
+        if (!C.active[k]) return;
+        const BundleHot& b = L.b[k];
+        const double z = proj_row(L, b.v, b.l), y = L.rho_r * (b.v - z);
+        const double us = L.row_eq ? b.l : kOsqpInfty * C.E[k];
+        const bool lo_inf = is_inf_lo(b.l), hi_inf = is_inf_hi(us);
+        row_acc(core_ax + b.e * b.xd, z, C.E[k], C.Einv[k], b.l, us, lo_inf, hi_inf, C.dy[k], core_adx + b.e * C.dxd[k]);
+        y_out = y; pdy_out = proj_dy(C.dy[k], lo_inf, hi_inf);
+        if (C.has_sing[k]) {
+          double aty = b.e * y, atdy = b.e * pdy_out;
+          if (C.has_sb[k]) {
+            const double zb = proj_sb(L, b.vb), yb = L.rho_b * (b.vb - zb);
+            const double lb = L.sb_free ? -kOsqpInfty * C.Eb[k] : 0.0, ub = kOsqpInfty * C.Eb[k];
+            const bool blo = is_inf_lo(lb), bhi = is_inf_hi(ub);
+            aty += b.beta * yb; atdy += b.beta * proj_dy(C.dyb[k], blo, bhi);
+            row_acc(b.beta * b.xd, zb, C.Eb[k], C.Ebinv[k], lb, ub, blo, bhi, C.dyb[k], b.beta * C.dxd[k]);
           }
-          var_acc(0.0, aty, b.qd, b.Dd, atdy, b.dxd, 0.0);
+          var_acc(0.0, aty, b.qd, C.Dd[k], C.Ddinv[k], atdy, C.dxd[k], 0.0);
         }
       };
       if (L.is_core) {
@@ -592,43 +692,49 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
 #pragma unroll
         for (int r = 0; r < NR; ++r) { aty += S.A[r * NC + j] * S.u[NC + r]; atdy += S.A[r * NC + j] * S.v[NC + r]; }
         if (Cfg::BOUNDS) {
-          aty += L.betac * L.yc; atdy += L.betac * proj_dy(L.dyc, L.lc, L.uc);
-          row_acc(L.betac * L.x, L.zc, L.Ecb, L.lc, L.uc, L.dyc, L.betac * L.dx);
+          const double zc = clampd(L.vc, L.lc, L.uc), yc = L.rhoc * (L.vc - zc);
+          const bool lo_inf = is_inf_lo(L.lc), hi_inf = is_inf_hi(L.uc);
+          aty += L.betac * yc; atdy += L.betac * proj_dy(C.dyc, lo_inf, hi_inf);
+          row_acc(L.betac * L.x, zc, C.Ecb, C.Ecbinv, L.lc, L.uc, lo_inf, hi_inf, C.dyc, L.betac * C.dx);
         }
 #pragma unroll
         for (int k = 0; k < KU; ++k) {
-          if (L.ub[k].active) { aty += L.a_unit[k] * L.ub[k].y; atdy += L.a_unit[k] * proj_dy(L.ub[k].dy, L.ub[k].l, L.ub[k].u); }
-          bundle_acc(L.ub[k], L.a_unit[k] * L.x, L.a_unit[k] * L.dx);
+          double y, pdy;
+          bundle_acc(k, L.b[k].c * L.x, L.b[k].c * C.dx, y, pdy);
+          aty += L.b[k].c * y; atdy += L.b[k].c * pdy;
         }
-        var_acc(px, aty, L.q, L.D, atdy, L.dx, pdx);
+        var_acc(px, aty, L.q, C.D, C.Dinv, atdy, C.dx, pdx);
       } else {
         const int r = L.gl - NC;
-        double ax = 0, adx = 0;
+        double ax = 0, adx = 0, y, pdy;
 #pragma unroll
         for (int i = 0; i < NC; ++i) { ax += S.A[r * NC + i] * S.u[i]; adx += S.A[r * NC + i] * S.v[i]; }
-        bundle_acc(L.rb, ax, adx);
+        bundle_acc(0, ax, adx, y, pdy);
       }
-#pragma unroll
-      for (int i = 0; i < kNumRed; ++i) S.red[i * GL + L.gl] = m[i];
     });
-    // C2: lane 0 reduces and decides
+    // C2a: the lanes share the kNumRed group reductions
     w.each([&](LaneT& L, GS& S) {
-      if (S.done || L.gl != 0) return;
-      double m[kNumRed];
-#pragma unroll
-      for (int i = 0; i < kNumRed; ++i) {
+      if (S.done) return;
+      for (int i = L.gl; i < kNumRed; i += GL) {
         const bool is_sum = (i == 15 || i == 18), is_min = (i == 21);
         double acc = is_sum ? 0.0 : (is_min ? 1e300 : (i == 20 ? -1e300 : 0.0));
+#pragma unroll
         for (int l = 0; l < GL; ++l) {
           const double val = S.red[i * GL + l];
           acc = is_sum ? acc + val : (is_min ? dmin(acc, val) : dmax(acc, val));
         }
-        m[i] = acc;
+        S.tot[i] = acc;
       }
+    });
+    // C2b: lane 0 decides
+    w.each([&](LaneT& L, GS& S) {
+      if (S.done || L.gl != 0) return;
+      double m[kNumRed];
+#pragma unroll
+      for (int i = 0; i < kNumRed; ++i) m[i] = S.tot[i];
       const double pri_res = m[0], dua_res = S.cinv * m[3];
       S.pri_res = pri_res; S.dua_res = dua_res;
       if (can_check) {
-        int status = kQpUnsolved;
         auto evaluate = [&](double mult) -> int {
           const double ea = o.eps_abs * mult, er = o.eps_rel * mult, epi = o.eps_prim_inf * mult, edi = o.eps_dual_inf * mult;
           if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) return kQpNonConvex;
@@ -645,7 +751,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
           if (dual_inf) return kQpDualInfeasible;
           return kQpUnsolved;
         };
-        status = evaluate(1.0);
+        int status = evaluate(1.0);
         if (status == kQpUnsolved && last) {
           status = evaluate(10.0);
           if (status == kQpUnsolved) status = kQpMaxIter;
@@ -659,15 +765,11 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         double rho_new = S.rho * sqrt(pr / (dr + 1e-10));
         rho_new = dmin(dmax(rho_new, kRhoMin), kRhoMax);
         if (rho_new > S.rho * o.adaptive_rho_tolerance || rho_new < S.rho / o.adaptive_rho_tolerance) {
-          S.rho = rho_new; S.rho_updates += 1; S.need_factor = 1;
+          S.rho_prev = S.rho; S.rho = rho_new; S.rho_updates += 1; S.need_factor = 1;
         }
       }
     });
-    {
-      bool nf = false;
-      for (int g = 0; g < NG; ++g) nf = nf || (w.group(g).need_factor != 0 && w.group(g).done == 0);
-      if (nf) factor();
-    }
+    w.each([&](LaneT& L, GS& S) { L.done = S.done != 0; });
     all_done = warp_done();
   }
 }

@@ -141,11 +141,11 @@ struct Builder {
       if (d.ngeom >= kMaxGeom) throw std::runtime_error("urdf: too many collision primitives (max 64)");
       const Tf Tg = tf_mul(T, origin_of(c));
       const int gi = d.ngeom++;
-      d.geom_type[gi] = type;
-      d.geom_parent[gi] = j;
-      std::memcpy(d.geom_prm[gi], prm, sizeof prm);
-      std::memcpy(d.geom_R[gi], Tg.R.m, sizeof Tg.R.m);
-      std::memcpy(d.geom_p[gi], Tg.p, sizeof Tg.p);
+      d.geom.type[gi] = type;
+      d.geom.parent[gi] = j;
+      std::memcpy(d.geom.prm[gi], prm, sizeof prm);
+      std::memcpy(d.geom.R[gi], Tg.R.m, sizeof Tg.R.m);
+      std::memcpy(d.geom.p[gi], Tg.p, sizeof Tg.p);
       hm.geom_names.push_back(lname + "_" + std::to_string(idx));
       geom_link.push_back(lname);
     }
@@ -260,26 +260,26 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
   int id = 0, ngjk = 0;
   for (int i = 0; i < d.ngeom; ++i)
     for (int j = i + 1; j < d.ngeom; ++j) {
-      if (d.geom_parent[i] == d.geom_parent[j]) continue;
+      if (d.geom.parent[i] == d.geom.parent[j]) continue;
       if (disabled.count({B.geom_link[i], B.geom_link[j]})) continue;
       pairs.push_back({i, j, id++});
-      const int ta = d.geom_type[i], tb = d.geom_type[j];
+      const int ta = d.geom.type[i], tb = d.geom.type[j];
       if (!(ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule))) ++ngjk;
     }
   if ((int)pairs.size() > kMaxPair) throw std::runtime_error("model: too many collision pairs (max 512)");
   if (ngjk > 64) throw std::runtime_error("model: more than 64 collision pairs need GJK (cylinder/box vs cylinder/box)");
   // group by (parent joint A, parent joint B), stable in reference order
   std::stable_sort(pairs.begin(), pairs.end(), [&](const P& x, const P& y) {
-    const int xa = d.geom_parent[x.a], xb = d.geom_parent[x.b], ya = d.geom_parent[y.a], yb = d.geom_parent[y.b];
+    const int xa = d.geom.parent[x.a], xb = d.geom.parent[x.b], ya = d.geom.parent[y.a], yb = d.geom.parent[y.b];
     return xa != ya ? xa < ya : xb < yb;
   });
   d.npair = (int)pairs.size();
   d.ngroup = 0;
   for (int k = 0; k < d.npair; ++k) {
-    d.pair_a[k] = (unsigned char)pairs[k].a;
-    d.pair_b[k] = (unsigned char)pairs[k].b;
-    d.pair_id[k] = (short)pairs[k].id;
-    const int ja = d.geom_parent[pairs[k].a], jb = d.geom_parent[pairs[k].b];
+    d.geom.pair_a[k] = (unsigned char)pairs[k].a;
+    d.geom.pair_b[k] = (unsigned char)pairs[k].b;
+    d.geom.pair_id[k] = (short)pairs[k].id;
+    const int ja = d.geom.parent[pairs[k].a], jb = d.geom.parent[pairs[k].b];
     if (d.ngroup == 0 || d.group_ja[d.ngroup - 1] != ja || d.group_jb[d.ngroup - 1] != jb) {
       if (d.ngroup >= kMaxGroup) throw std::runtime_error("model: too many link pairs (max 64)");
       d.group_ja[d.ngroup] = (short)ja; d.group_jb[d.ngroup] = (short)jb;
@@ -287,6 +287,11 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
       ++d.ngroup;
     }
     d.group_count[d.ngroup - 1]++;
+  }
+  d.ngjk = 0;
+  for (int k = 0; k < d.npair; ++k) {
+    const int ta = d.geom.type[d.geom.pair_a[k]], tb = d.geom.type[d.geom.pair_b[k]];
+    if (!(ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule))) d.gjk_pair[d.ngjk++] = (unsigned short)k;
   }
   return B.hm;
 }

@@ -18,6 +18,8 @@ def lib():
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
         _LIB = C.CDLL(str(_HERE / "libdrc_emu.so"))
         _LIB.emu_create.restype = C.c_void_p
+        _LIB.emu_shape_distance.restype = C.c_double
+        _LIB.emu_pair_lower_bound.restype = C.c_double
     return _LIB
 
 
@@ -131,3 +133,20 @@ class Emu:
                                  _d(a2), _d(out))
         assert rc == 0
         return out
+
+    def shape_distance(self, ta, prm_a, Ta, tb, prm_b, Tb):
+        """Product narrow phase (closed form / GJK / EPA) on one pair; poses are 4x4 or 12-vectors."""
+        def p12(T):
+            T = np.asarray(T, np.float64)
+            return np.ascontiguousarray(T.reshape(-1)[:12] if T.size == 12 else T[:3, :].reshape(12))
+        wa, wb, info = np.zeros(3), np.zeros(3), np.zeros(2, np.int32)
+        d = lib().emu_shape_distance(self.h, C.c_int(ta), _d(_c(prm_a)), _d(p12(Ta)), C.c_int(tb), _d(_c(prm_b)), _d(p12(Tb)),
+                                     _d(wa), _d(wb), _i(info))
+        return float(d), wa, wb, info
+
+
+def pair_lower_bound(ta, prm_a, Ta, tb, prm_b, Tb):
+    def p12(T):
+        T = np.asarray(T, np.float64)
+        return np.ascontiguousarray(T.reshape(-1)[:12] if T.size == 12 else T[:3, :].reshape(12))
+    return float(lib().emu_pair_lower_bound(C.c_int(ta), _d(_c(prm_a)), _d(p12(Ta)), C.c_int(tb), _d(_c(prm_b)), _d(p12(Tb))))

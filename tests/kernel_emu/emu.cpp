@@ -52,7 +52,7 @@ static void run_collision(const EmuHandle* h, CollisionIO& io, std::vector<int>&
   if (!io.pair_out) { pair.assign(io.B, 0); io.pair_out = pair.data(); }
   if (!io.witness) { wit.assign(6 * (size_t)io.B, 0.0); io.witness = wit.data(); }
   io.epa_flag = flag.data(); io.cand_mask = mask.data();
-  for (int b = 0; b < io.B; ++b) collision_job<NV, CHAIN>(h->hm.dev, h->prm, io, b);
+  for (int b = 0; b < io.B; ++b) collision_job<NV, CHAIN>(h->hm.dev, h->hm.dev.geom, h->prm, io, b);
   for (int b = 0; b < io.B; ++b) collision_epa_job<NV, CHAIN>(h->hm.dev, h->prm, io, b);
 }
 
@@ -105,10 +105,10 @@ void emu_model_arrays(EmuHandle* h, int* parent, int* jtype, double* axis, doubl
     q_lo[i] = d.q_lo[i]; q_hi[i] = d.q_hi[i]; v_lim[i] = d.v_lim[i];
   }
   for (int g = 0; g < d.ngeom; ++g) {
-    geom_type[g] = d.geom_type[g]; geom_parent[g] = d.geom_parent[g];
-    std::memcpy(geom_prm + 3 * g, d.geom_prm[g], 24); std::memcpy(geom_R + 9 * g, d.geom_R[g], 72); std::memcpy(geom_p + 3 * g, d.geom_p[g], 24);
+    geom_type[g] = d.geom.type[g]; geom_parent[g] = d.geom.parent[g];
+    std::memcpy(geom_prm + 3 * g, d.geom.prm[g], 24); std::memcpy(geom_R + 9 * g, d.geom.R[g], 72); std::memcpy(geom_p + 3 * g, d.geom.p[g], 24);
   }
-  for (int k = 0; k < d.npair; ++k) { pairs_ref_order[2 * d.pair_id[k]] = d.pair_a[k]; pairs_ref_order[2 * d.pair_id[k] + 1] = d.pair_b[k]; }
+  for (int k = 0; k < d.npair; ++k) { pairs_ref_order[2 * d.geom.pair_id[k]] = d.geom.pair_a[k]; pairs_ref_order[2 * d.geom.pair_id[k] + 1] = d.geom.pair_b[k]; }
   for (size_t f = 0; f < h->hm.frames.size(); ++f) {
     frame_parent[f] = h->hm.frames[f].parent;
     std::memcpy(frame_R + 9 * f, h->hm.frames[f].R, 72); std::memcpy(frame_p + 3 * f, h->hm.frames[f].p, 24);
@@ -226,6 +226,43 @@ int emu_taskspace(EmuHandle* h, int mode, int frame_id, int B, const double* q, 
   else if (mode == 2) run_job<7, true, F_DYN | F_OSF>(h, fr, io);
   else run_job<7, true, F_DYN | F_TORQUE>(h, fr, io);
   return 0;
+}
+
+// ---- narrow phase of the product on one shape pair (type, prm[3], pose12), world frame
+double emu_shape_distance(EmuHandle* h, int ta, const double* pa, const double* Ta, int tb, const double* pb, const double* Tb,
+                          double* wa, double* wb, int* info) {
+  auto mk = [](int t, const double* prm, const double* T) {
+    Prim s;
+    s.type = t; s.r = prm[0]; s.h = prm[1]; s.hb = v3(prm[0], prm[1], prm[2]);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.R.m[3 * i + j] = T[4 * i + j];
+    s.c = v3(T[3], T[7], T[11]);
+    s.a = v3(T[2], T[6], T[10]);
+    return s;
+  };
+  const Prim A = mk(ta, pa, Ta), B = mk(tb, pb, Tb);
+  PairResult r;
+  info[0] = info[1] = 0;
+  if (has_closed_form(ta, tb)) r = closed_form_distance(A, B);
+  else {
+    GjkOut g;
+    gjk_distance(A, B, h->prm.gjk_tol, h->prm.gjk_max_iter, g);
+    r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+    info[0] = g.iters;
+    if (g.intersect) { epa_penetration(A, B, g, h->prm.epa_tol, h->prm.epa_max_iter, r); info[1] = 1; }
+  }
+  wa[0] = r.pa.x; wa[1] = r.pa.y; wa[2] = r.pa.z; wb[0] = r.pb.x; wb[1] = r.pb.y; wb[2] = r.pb.z;
+  return r.d;
+}
+double emu_pair_lower_bound(int ta, const double* pa, const double* Ta, int tb, const double* pb, const double* Tb) {
+  auto mk = [](int t, const double* prm, const double* T) {
+    Prim s;
+    s.type = t; s.r = prm[0]; s.h = prm[1]; s.hb = v3(prm[0], prm[1], prm[2]);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.R.m[3 * i + j] = T[4 * i + j];
+    s.c = v3(T[3], T[7], T[11]);
+    s.a = v3(T[2], T[6], T[10]);
+    return s;
+  };
+  return pair_lower_bound(mk(ta, pa, Ta), mk(tb, pb, Tb));
 }
 
 }  // extern "C"
