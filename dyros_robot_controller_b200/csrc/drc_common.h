@@ -43,7 +43,7 @@ struct DrcParams {
   int adaptive_rho = 1, adaptive_rho_interval = 50;
   double adaptive_rho_tolerance = 5.0;
   // narrow phase
-  double gjk_tol = 1e-10, epa_tol = 1e-10;
+  double gjk_tol = 1e-10, epa_tol = 1e-6;  // EPA: hpp-fcl's default; curved pairs converge like 1/k^2
   int gjk_max_iter = 128, epa_max_iter = 96;
   double pinv_threshold = 1e-6;  // COD rank threshold (math_type_define.h:7)
 };

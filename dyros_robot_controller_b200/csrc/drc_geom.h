@@ -135,11 +135,14 @@ DRC_HD Vec3 support(const Prim& S, Vec3 d) {
       return mul(S.R, v3(dl.x >= 0 ? S.hb.x : -S.hb.x, dl.y >= 0 ? S.hb.y : -S.hb.y, dl.z >= 0 ? S.hb.z : -S.hb.z)) + S.c;
     }
     case kCylinder: {
+      // radial part of d, orthogonalised twice: for d (nearly) along the axis the first difference is rounding noise
+      // with an axial component, which would push the rim point out of the cylinder by up to r
       const double da = dot(d, S.a);
-      const Vec3 perp = d - da * S.a;
-      const double sg = norm(perp);
+      Vec3 perp = d - da * S.a;
+      perp = perp - dot(perp, S.a) * S.a;
+      const double sg2 = dot(perp, perp);
       Vec3 s = S.c + (da >= 0 ? S.h : -S.h) * S.a;
-      if (sg > 0) s = s + (S.r / sg) * perp;
+      if (sg2 > 1e-28 * dot(d, d)) s = s + (S.r / sqrt(sg2)) * perp;
       return s;
     }
     default: {  // capsule
@@ -236,8 +239,9 @@ DRC_HD bool closest_tetra(SimplexVert* v, int& n, double* lam) {
   for (int f = 0; f < 4; ++f) {
     const Vec3 a = v[F[f][0]].w, b = v[F[f][1]].w, c = v[F[f][2]].w, d = v[OPP[f]].w;
     const Vec3 nrm = cross(b - a, c - a);
-    const double so = -dot(a, nrm), sd = dot(d - a, nrm);
-    if (so * sd < 0 || sd == 0) {
+    const double so = -dot(a, nrm), sd = dot(d - a, nrm), n2 = dot(nrm, nrm);
+    // origin and the opposite vertex on different sides, or a (nearly) flat tetrahedron whose side test is noise
+    if (so * sd < 0 || sd * sd <= 1e-20 * n2 * sqrt(n2)) {
       outside = true;
       SimplexVert t[3] = {v[F[f][0]], v[F[f][1]], v[F[f][2]]};
       double l[3] = {0, 0, 0};
@@ -315,31 +319,36 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
 }
 
 // ---------------------------------------------------------------- EPA (fixed-capacity polytope)
-constexpr int kEpaMaxVert = 104, kEpaMaxFace = 208, kEpaMaxEdge = 64;
+// Expanding polytope algorithm (van den Bergen 2001) for the penetration depth of overlapping shapes.
+// Robustness rules (the same in oracle/src/ogeom.h and in the warp-parallel device variant in drc_lib.cu):
+//   * the faces removed by a new vertex are found by a FLOOD FILL from the closest face across shared edges, so the
+//     removed region is connected and its border (the horizon) is a closed loop even when large coplanar regions of
+//     the Minkowski difference (box face x cylinder cap) make the visibility sign of a face noise;
+//   * an expansion that would leave a hole (no neighbour across an edge), a degenerate new face or exceed the
+//     capacity is not committed: the current closest face is returned (a lower bound of the depth);
+//   * new face i (horizon order) reuses the slot of the i-th removed face, the last two are appended.
+constexpr int kEpaMaxVert = 104, kEpaMaxFace = 208, kEpaMaxEdge = 96;
+constexpr double kEpaVisEps = 1e-12, kEpaMinArea2 = 1e-28;
 struct EpaFace {
   short v[3];
   short alive;
   Vec3 n;
   double d;
 };
-
-DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out) {
-  SimplexVert P[kEpaMaxVert];
-  EpaFace F[kEpaMaxFace];
-  short E[kEpaMaxEdge][2];
-  int np = g.n, nf = 0;
-  for (int i = 0; i < np; ++i) P[i] = g.sv[i];
-  auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
-  auto distinct = [&](const SimplexVert& s) {
-    for (int i = 0; i < np; ++i) if (norm2(P[i].w - s.w) < 1e-20) return false;
-    return true;
-  };
+// grow the final GJK simplex to a tetrahedron (T[0..3]); returns the number of vertices reached
+template <class Sup>
+DRC_HD int epa_seed(Sup sup, const GjkOut& g, SimplexVert* T) {
+  int np = g.n;
+  for (int i = 0; i < np; ++i) T[i] = g.sv[i];
   const Vec3 axes[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
   if (np == 1) {
-    for (int k = 0; k < 6; ++k) { SimplexVert s = sup(axes[k]); if (distinct(s)) { P[np++] = s; break; } }
+    for (int k = 0; k < 6; ++k) {
+      const SimplexVert s = sup(axes[k]);
+      if (norm2(T[0].w - s.w) >= 1e-20) { T[np++] = s; break; }
+    }
   }
   if (np == 2) {
-    const Vec3 e = P[1].w - P[0].w;
+    const Vec3 e = T[1].w - T[0].w;
     Vec3 best = v3(0, 0, 0);
     double bl = -1;
     for (int k = 0; k < 6; ++k) {
@@ -347,36 +356,55 @@ DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut&
       if (dot(c, c) <= 1e-20) continue;
       for (int sgn = -1; sgn <= 1; sgn += 2) {
         const SimplexVert s = sup((double)sgn * c);
-        const double area = norm(cross(e, s.w - P[0].w));
+        const double area = norm(cross(e, s.w - T[0].w));
         if (area > bl) { bl = area; best = (double)sgn * c; }
       }
     }
-    P[np++] = sup(best);
+    T[np++] = sup(best);
   }
   if (np == 3) {
-    const Vec3 nrm = cross(P[1].w - P[0].w, P[2].w - P[0].w);
+    const Vec3 nrm = cross(T[1].w - T[0].w, T[2].w - T[0].w);
     const SimplexVert s1 = sup(nrm), s2 = sup(-nrm);
-    const double h1 = fabs(dot(s1.w - P[0].w, nrm)), h2 = fabs(dot(s2.w - P[0].w, nrm));
-    P[np++] = h1 >= h2 ? s1 : s2;
+    const double h1 = fabs(dot(s1.w - T[0].w, nrm)), h2 = fabs(dot(s2.w - T[0].w, nrm));
+    T[np++] = h1 >= h2 ? s1 : s2;
   }
+  if (np == 4 && dot(cross(T[1].w - T[0].w, T[2].w - T[0].w), T[3].w - T[0].w) > 0) { const SimplexVert t = T[1]; T[1] = T[2]; T[2] = t; }
+  return np;
+}
+// witness points: barycentric coordinates of the origin's projection on the closest face
+DRC_HD void epa_witness(const SimplexVert& t0, const SimplexVert& t1, const SimplexVert& t2, Vec3 fn, double fd, PairResult& out) {
+  const Vec3 pr = fd * fn;
+  const Vec3 v0 = t1.w - t0.w, v1 = t2.w - t0.w, v2 = pr - t0.w;
+  const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+  const double den = d00 * d11 - d01 * d01;
+  const double l1 = den != 0 ? (d11 * d20 - d01 * d21) / den : 0.0, l2 = den != 0 ? (d00 * d21 - d01 * d20) / den : 0.0;
+  const double l0 = 1 - l1 - l2;
+  out.pa = l0 * t0.a + l1 * t1.a + l2 * t2.a;
+  out.pb = l0 * t0.b + l1 * t1.b + l2 * t2.b;
+  out.d = -fd;
+}
+
+DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out) {
+  SimplexVert P[kEpaMaxVert];
+  EpaFace F[kEpaMaxFace];
+  short E[kEpaMaxEdge][2];
+  short killed[kEpaMaxEdge], stack[kEpaMaxEdge];
+  unsigned char mark[kEpaMaxFace];  // 0 untested, 1 visible, 2 tested: not visible
+  auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
+  int np = epa_seed(sup, g, P), nf = 0;
   out.d = 0; out.pa = g.pa; out.pb = g.pb;
   if (np < 4) return;
-  short freed[kEpaMaxFace];  // slots of removed faces, reused so that capacity is bounded by 2*vertices - 4
-  int nfree = 0;
-  auto add_face = [&](int a, int b, int c) {
-    int slot;
-    if (nfree > 0) slot = freed[--nfree];
-    else { if (nf >= kEpaMaxFace) return; slot = nf++; }
+  auto make_face = [&](int slot, int a, int b, int c) {
     EpaFace& f = F[slot];
     f.v[0] = (short)a; f.v[1] = (short)b; f.v[2] = (short)c;
     const Vec3 nrm = cross(P[b].w - P[a].w, P[c].w - P[a].w);
     const double l = norm(nrm);
     f.n = l > 0 ? (1.0 / l) * nrm : v3(0, 0, 1);
     f.d = dot(f.n, P[a].w);
-    f.alive = l > 0 ? 1 : 0;
+    f.alive = 1;
   };
-  if (dot(cross(P[1].w - P[0].w, P[2].w - P[0].w), P[3].w - P[0].w) > 0) { SimplexVert t = P[1]; P[1] = P[2]; P[2] = t; }
-  add_face(0, 1, 2); add_face(0, 3, 1); add_face(0, 2, 3); add_face(1, 3, 2);
+  make_face(0, 0, 1, 2); make_face(1, 0, 3, 1); make_face(2, 0, 2, 3); make_face(3, 1, 3, 2);
+  nf = 4;
   int bestf = -1;
   for (int it = 0; it < max_iter; ++it) {
     bestf = -1;
@@ -386,40 +414,49 @@ DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut&
     const SimplexVert s = sup(F[bestf].n);
     if (dot(F[bestf].n, s.w) - F[bestf].d <= tol) break;
     if (np >= kEpaMaxVert) break;
-    const int idx = np;
-    P[np++] = s;
-    int ne = 0;
-    bool overflow = false;
-    for (int i = 0; i < nf; ++i) {
-      EpaFace& f = F[i];
-      if (!f.alive) continue;
-      if (dot(f.n, s.w - P[f.v[0]].w) > 0) {
-        f.alive = 0;
-        freed[nfree++] = (short)i;
-        for (int e = 0; e < 3; ++e) {
-          const short a = f.v[e], b = f.v[(e + 1) % 3];
-          bool found = false;
-          for (int k = 0; k < ne; ++k)
-            if (E[k][0] == b && E[k][1] == a) { E[k][0] = E[ne - 1][0]; E[k][1] = E[ne - 1][1]; --ne; found = true; break; }
-          if (!found) { if (ne < kEpaMaxEdge) { E[ne][0] = a; E[ne][1] = b; ++ne; } else overflow = true; }
+    // flood fill of the faces visible from s
+    for (int i = 0; i < nf; ++i) mark[i] = 0;
+    int nk = 0, ne = 0, sp = 0;
+    bool bad = false;
+    mark[bestf] = 1; killed[nk++] = (short)bestf; stack[sp++] = (short)bestf;
+    while (sp > 0 && !bad) {
+      const int f = stack[--sp];
+      for (int e = 0; e < 3 && !bad; ++e) {
+        const short a = F[f].v[e], b = F[f].v[(e + 1) % 3];
+        int gn = -1;
+        for (int i = 0; i < nf; ++i) {
+          if (!F[i].alive) continue;
+          const short* v = F[i].v;
+          if ((v[0] == b && v[1] == a) || (v[1] == b && v[2] == a) || (v[2] == b && v[0] == a)) { gn = i; break; }
         }
+        if (gn < 0) { bad = true; break; }
+        if (mark[gn] == 1) continue;
+        if (mark[gn] == 0) {
+          const bool vis = dot(F[gn].n, s.w - P[F[gn].v[0]].w) > kEpaVisEps;
+          mark[gn] = vis ? 1 : 2;
+          if (vis) {
+            if (nk >= kEpaMaxEdge - 2) { bad = true; break; }
+            killed[nk++] = (short)gn; stack[sp++] = (short)gn;
+            continue;
+          }
+        }
+        if (ne >= kEpaMaxEdge) { bad = true; break; }
+        E[ne][0] = a; E[ne][1] = b; ++ne;
       }
     }
-    if (ne == 0 || overflow) break;
-    for (int k = 0; k < ne; ++k) add_face(E[k][0], E[k][1], idx);
+    if (bad || ne != nk + 2 || nf + 2 > kEpaMaxFace) break;
+    for (int k = 0; k < ne && !bad; ++k)
+      bad = norm2(cross(P[E[k][1]].w - P[E[k][0]].w, s.w - P[E[k][0]].w)) <= kEpaMinArea2;
+    if (bad) break;
+    // commit
+    const int idx = np;
+    P[np++] = s;
+    for (int k = 0; k < ne; ++k) make_face(k < nk ? (int)killed[k] : nf + (k - nk), E[k][0], E[k][1], idx);
+    nf += 2;
   }
   if (bestf < 0) return;
   const EpaFace& f = F[bestf];
-  const SimplexVert t0 = P[f.v[0]], t1 = P[f.v[1]], t2 = P[f.v[2]];
-  const Vec3 pr = f.d * f.n;
-  const Vec3 v0 = t1.w - t0.w, v1 = t2.w - t0.w, v2 = pr - t0.w;
-  const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
-  const double den = d00 * d11 - d01 * d01;
-  const double l1 = den != 0 ? (d11 * d20 - d01 * d21) / den : 0.0, l2 = den != 0 ? (d00 * d21 - d01 * d20) / den : 0.0;
-  const double l0 = 1 - l1 - l2;
-  out.pa = l0 * t0.a + l1 * t1.a + l2 * t2.a;
-  out.pb = l0 * t0.b + l1 * t1.b + l2 * t2.b;
-  out.d = -f.d;
+  epa_witness(P[f.v[0]], P[f.v[1]], P[f.v[2]], f.n, f.d, out);
 }
 
 // ---------------------------------------------------------------- exact closed-form dispatcher

@@ -46,18 +46,19 @@ __global__ void __launch_bounds__(128) k_collision(const __grid_constant__ DrcMo
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < io.B) collision_job<NV, CHAIN>(m, G, prm, io, b);
 }
-// ---- EPA, one WARP per flagged robot (~0.1 % of a random batch): the polytope lives in shared memory, the face
-// scans (closest face, visibility, horizon) are spread over the 32 lanes; everything else is warp-uniform.
-constexpr int kEpaWarpMaxEdge = 96;
+// ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar
+// epa_penetration (drc_geom.h: flood-fill horizon, uncommitted bad expansions, slot policy); the polytope lives in
+// shared memory and the three face scans (closest face, neighbour across an edge, new faces) are spread over the
+// lanes.  Control flow and the small flood-fill state are warp-uniform: every lane runs the same sequence.
 struct EpaWarpSmem {
   SimplexVert P[kEpaMaxVert];
   double fd[kEpaMaxFace];
   double fn[kEpaMaxFace][3];
   short fv[kEpaMaxFace][3];
-  unsigned char alive[kEpaMaxFace];
-  short edge[kEpaWarpMaxEdge][2];
-  short killed[kEpaWarpMaxEdge / 3];
-  unsigned char hor[kEpaWarpMaxEdge];
+  unsigned char mark[kEpaMaxFace];
+  short edge[kEpaMaxEdge][2];
+  short killed[kEpaMaxEdge];
+  short stack[kEpaMaxEdge];
 };
 __device__ __forceinline__ void epa_make_face(EpaWarpSmem& S, int slot, int a, int b, int c) {
   const Vec3 nrm = cross(S.P[b].w - S.P[a].w, S.P[c].w - S.P[a].w);
@@ -66,47 +67,15 @@ __device__ __forceinline__ void epa_make_face(EpaWarpSmem& S, int slot, int a, i
   S.fv[slot][0] = (short)a; S.fv[slot][1] = (short)b; S.fv[slot][2] = (short)c;
   S.fn[slot][0] = n.x; S.fn[slot][1] = n.y; S.fn[slot][2] = n.z;
   S.fd[slot] = dot(n, S.P[a].w);
-  S.alive[slot] = l > 0 ? 1 : 0;
 }
 __device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out,
                          int lane) {
   const unsigned full = 0xffffffffu;
   auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
-  // seed: grow the GJK simplex to a tetrahedron (warp-uniform, every lane on its private copy)
   SimplexVert T[4];
-  int np = g.n;
-  for (int i = 0; i < np; ++i) T[i] = g.sv[i];
-  const Vec3 axes[6] = {v3(1, 0, 0), v3(-1, 0, 0), v3(0, 1, 0), v3(0, -1, 0), v3(0, 0, 1), v3(0, 0, -1)};
-  if (np == 1) {
-    for (int k = 0; k < 6; ++k) {
-      const SimplexVert s = sup(axes[k]);
-      if (norm2(T[0].w - s.w) >= 1e-20) { T[np++] = s; break; }
-    }
-  }
-  if (np == 2) {
-    const Vec3 e = T[1].w - T[0].w;
-    Vec3 best = v3(0, 0, 0);
-    double bl = -1;
-    for (int k = 0; k < 6; ++k) {
-      const Vec3 c = cross(e, axes[k]);
-      if (dot(c, c) <= 1e-20) continue;
-      for (int sgn = -1; sgn <= 1; sgn += 2) {
-        const SimplexVert s = sup((double)sgn * c);
-        const double area = norm(cross(e, s.w - T[0].w));
-        if (area > bl) { bl = area; best = (double)sgn * c; }
-      }
-    }
-    T[np++] = sup(best);
-  }
-  if (np == 3) {
-    const Vec3 nrm = cross(T[1].w - T[0].w, T[2].w - T[0].w);
-    const SimplexVert s1 = sup(nrm), s2 = sup(-nrm);
-    const double h1 = fabs(dot(s1.w - T[0].w, nrm)), h2 = fabs(dot(s2.w - T[0].w, nrm));
-    T[np++] = h1 >= h2 ? s1 : s2;
-  }
+  int np = epa_seed(sup, g, T);  // warp-uniform, every lane on its private copy
   out.d = 0; out.pa = g.pa; out.pb = g.pb;
   if (np < 4) return;
-  if (dot(cross(T[1].w - T[0].w, T[2].w - T[0].w), T[3].w - T[0].w) > 0) { const SimplexVert t = T[1]; T[1] = T[2]; T[2] = t; }
   __syncwarp();
   if (lane < 4) S.P[lane] = T[lane];
   __syncwarp();
@@ -118,11 +87,11 @@ __device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, const Gjk
   __syncwarp();
   int bestf = -1;
   for (int it = 0; it < max_iter; ++it) {
-    // closest face to the origin (ties: smallest index)
+    // closest face to the origin (ties: smallest index); every slot below nf holds a live face
     double bd = 1e300;
     int bf = -1;
     for (int f = lane; f < nf; f += 32)
-      if (S.alive[f] && S.fd[f] < bd) { bd = S.fd[f]; bf = f; }
+      if (S.fd[f] < bd) { bd = S.fd[f]; bf = f; }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const double od = __shfl_xor_sync(full, bd, off);
@@ -135,68 +104,74 @@ __device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, const Gjk
     const SimplexVert s = sup(n);
     if (dot(n, s.w) - S.fd[bf] <= tol) break;
     if (np >= kEpaMaxVert) break;
+    // flood fill of the faces visible from s (uniform control flow; lanes share the neighbour search)
+    for (int f = lane; f < nf; f += 32) S.mark[f] = 0;
+    __syncwarp();
+    int nk = 0, ne = 0, sp = 0;
+    bool bad = false;
+    if (lane == 0) { S.mark[bf] = 1; S.killed[0] = (short)bf; S.stack[0] = (short)bf; }
+    nk = 1; sp = 1;
+    __syncwarp();
+    while (sp > 0 && !bad) {
+      const int f = S.stack[--sp];
+      for (int e = 0; e < 3 && !bad; ++e) {
+        const short a = S.fv[f][e], b = S.fv[f][(e + 1) % 3];
+        int gn = -1;
+        for (int base = 0; base < nf && gn < 0; base += 32) {
+          const int i = base + lane;
+          bool hit = false;
+          if (i < nf) {
+            const short v0 = S.fv[i][0], v1 = S.fv[i][1], v2 = S.fv[i][2];
+            hit = (v0 == b && v1 == a) || (v1 == b && v2 == a) || (v2 == b && v0 == a);
+          }
+          const unsigned mk = __ballot_sync(full, hit);
+          if (mk) gn = base + __ffs(mk) - 1;
+        }
+        if (gn < 0) { bad = true; break; }
+        const int mg = S.mark[gn];
+        if (mg == 1) continue;
+        if (mg == 0) {
+          const Vec3 p0 = S.P[S.fv[gn][0]].w;
+          const bool vis = S.fn[gn][0] * (s.w.x - p0.x) + S.fn[gn][1] * (s.w.y - p0.y) + S.fn[gn][2] * (s.w.z - p0.z) > kEpaVisEps;
+          __syncwarp();
+          if (lane == 0) S.mark[gn] = vis ? 1 : 2;
+          if (vis) {
+            if (nk >= kEpaMaxEdge - 2) { bad = true; break; }
+            if (lane == 0) { S.killed[nk] = (short)gn; S.stack[sp] = (short)gn; }
+            ++nk; ++sp;
+            __syncwarp();
+            continue;
+          }
+          __syncwarp();
+        }
+        if (ne >= kEpaMaxEdge) { bad = true; break; }
+        if (lane == 0) { S.edge[ne][0] = a; S.edge[ne][1] = b; }
+        ++ne;
+      }
+    }
+    __syncwarp();
+    if (bad || ne != nk + 2 || nf + 2 > kEpaMaxFace) break;
+    for (int base = 0; base < ne; base += 32) {
+      const int k = base + lane;
+      bool deg = false;
+      if (k < ne) {
+        const Vec3 pa = S.P[S.edge[k][0]].w;
+        deg = norm2(cross(S.P[S.edge[k][1]].w - pa, s.w - pa)) <= kEpaMinArea2;
+      }
+      if (__any_sync(full, deg)) bad = true;
+    }
+    if (bad) break;
+    // commit: the new vertex, then one new face per horizon edge
     const int idx = np++;
     if (lane == 0) S.P[idx] = s;
-    // faces visible from the new vertex die; their edges are collected
-    int nk = 0;
-    for (int base = 0; base < nf; base += 32) {
-      const int f = base + lane;
-      bool vis = false;
-      if (f < nf && S.alive[f]) {
-        const Vec3 p0 = S.P[S.fv[f][0]].w;
-        vis = S.fn[f][0] * (s.w.x - p0.x) + S.fn[f][1] * (s.w.y - p0.y) + S.fn[f][2] * (s.w.z - p0.z) > 0;
-      }
-      const unsigned mk = __ballot_sync(full, vis);
-      if (vis) {
-        const int r = nk + __popc(mk & ((1u << lane) - 1u));
-        S.alive[f] = 0;
-        if (3 * r + 2 < kEpaWarpMaxEdge) {
-          S.killed[r] = (short)f;
-#pragma unroll
-          for (int e = 0; e < 3; ++e) { S.edge[3 * r + e][0] = S.fv[f][e]; S.edge[3 * r + e][1] = S.fv[f][(e + 1) % 3]; }
-        }
-      }
-      nk += __popc(mk);
-    }
-    if (nk == 0 || 3 * nk > kEpaWarpMaxEdge) break;
     __syncwarp();
-    const int ne = 3 * nk;
-    for (int e = lane; e < ne; e += 32) {
-      const short a = S.edge[e][0], b = S.edge[e][1];
-      unsigned char h = 1;
-      for (int j = 0; j < ne; ++j) if (S.edge[j][0] == b && S.edge[j][1] == a) h = 0;
-      S.hor[e] = h;
-    }
-    __syncwarp();
-    // one new face per horizon edge: first into the slots just freed, the rest appended
-    int nh = 0;
-    for (int base = 0; base < ne; base += 32) {
-      const int e = base + lane;
-      const bool h = e < ne && S.hor[e];
-      const unsigned mk = __ballot_sync(full, h);
-      if (h) {
-        const int r = nh + __popc(mk & ((1u << lane) - 1u));
-        const int slot = r < nk ? (int)S.killed[r] : nf + (r - nk);
-        if (slot < kEpaMaxFace) epa_make_face(S, slot, S.edge[e][0], S.edge[e][1], idx);
-      }
-      nh += __popc(mk);
-    }
-    if (nh > nk) nf = min(nf + (nh - nk), kEpaMaxFace);
+    for (int k = lane; k < ne; k += 32) epa_make_face(S, k < nk ? (int)S.killed[k] : nf + (k - nk), S.edge[k][0], S.edge[k][1], idx);
+    nf += 2;
     __syncwarp();
   }
   if (bestf < 0) return;
-  const SimplexVert t0 = S.P[S.fv[bestf][0]], t1 = S.P[S.fv[bestf][1]], t2 = S.P[S.fv[bestf][2]];
-  const Vec3 fnv = v3(S.fn[bestf][0], S.fn[bestf][1], S.fn[bestf][2]);
-  const double fdv = S.fd[bestf];
-  const Vec3 pr = fdv * fnv;
-  const Vec3 v0 = t1.w - t0.w, v1 = t2.w - t0.w, v2 = pr - t0.w;
-  const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
-  const double den = d00 * d11 - d01 * d01;
-  const double l1 = den != 0 ? (d11 * d20 - d01 * d21) / den : 0.0, l2 = den != 0 ? (d00 * d21 - d01 * d20) / den : 0.0;
-  const double l0 = 1 - l1 - l2;
-  out.pa = l0 * t0.a + l1 * t1.a + l2 * t2.a;
-  out.pb = l0 * t0.b + l1 * t1.b + l2 * t2.b;
-  out.d = -fdv;
+  epa_witness(S.P[S.fv[bestf][0]], S.P[S.fv[bestf][1]], S.P[S.fv[bestf][2]], v3(S.fn[bestf][0], S.fn[bestf][1], S.fn[bestf][2]),
+              S.fd[bestf], out);
   __syncwarp();
 }
 
@@ -675,7 +650,7 @@ int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
   if (!c || !p) return fail(DRC_E_INVALID, "null argument");
   if (p->check_termination <= 0 || p->max_iter <= 0 || p->scaling < 0 || p->rho <= 0 || p->sigma <= 0)
     return fail(DRC_E_INVALID, "invalid solver settings");
-  if (p->epa_max_iter > kEpaMaxVert - 8) return fail(DRC_E_INVALID, "epa_max_iter exceeds the polytope capacity (96)");
+  if (p->epa_max_iter > kEpaMaxVert - 4) return fail(DRC_E_INVALID, "epa_max_iter exceeds the polytope capacity (100)");
   DrcParams& s = c->prm;
   s.alpha = p->alpha; s.slack_weight = p->slack_weight; s.ik_reg = p->ik_reg; s.moma_ik_reg = p->moma_ik_reg;
   s.mani_thresh = p->mani_thresh; s.dist_thresh = p->dist_thresh;

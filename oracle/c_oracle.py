@@ -113,7 +113,7 @@ class Oracle:
                                   C.c_int(max_iter), C.c_int(check_termination), C.c_int(scaling), C.c_int(adaptive_rho),
                                   C.c_int(adaptive_rho_interval), C.c_double(adaptive_rho_tolerance))
 
-    def set_geom_params(self, gjk_tol=1e-10, gjk_max_iter=128, epa_tol=1e-10, epa_max_iter=128):
+    def set_geom_params(self, gjk_tol=1e-10, gjk_max_iter=128, epa_tol=1e-6, epa_max_iter=96):
         lib().orc_set_geom_params(self.h, C.c_double(gjk_tol), C.c_int(gjk_max_iter), C.c_double(epa_tol),
                                   C.c_int(epa_max_iter))
 

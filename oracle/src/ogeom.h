@@ -26,8 +26,8 @@ struct DistResult {
 struct GeomParams {
   double gjk_tol = 1e-10;   // absolute tolerance on the distance duality gap
   int gjk_max_iter = 128;
-  double epa_tol = 1e-10;
-  int epa_max_iter = 128;
+  double epa_tol = 1e-6;   // hpp-fcl's default EPA tolerance; curved pairs converge like 1/k^2, 1e-10 is never reached
+  int epa_max_iter = 96;
 };
 
 // ---------------------------------------------------------------- closed forms
@@ -200,9 +200,9 @@ inline bool closest_on_tetra(SVert* v, int& n, double* lam) {
   for (int f = 0; f < 4; ++f) {
     const V3 &a = v[F[f][0]].w, &b = v[F[f][1]].w, &c = v[F[f][2]].w, &d = v[OPP[f]].w;
     V3 nrm = cross(b - a, c - a);
-    double so = dot(-a, nrm), sd = dot(d - a, nrm);
-    // origin and the opposite vertex on different sides (or degenerate tetra)
-    if (so * sd < 0 || sd == 0) {
+    double so = dot(-a, nrm), sd = dot(d - a, nrm), n2 = dot(nrm, nrm);
+    // origin and the opposite vertex on different sides, or a (nearly) flat tetrahedron whose side test is noise
+    if (so * sd < 0 || sd * sd <= 1e-20 * n2 * std::sqrt(n2)) {
       outside_any = true;
       SVert t[3] = {v[F[f][0]], v[F[f][1]], v[F[f][2]]};
       double l[3];
@@ -323,20 +323,27 @@ inline DistResult epa(const Shape& A, const Shape& B, const GjkResult& g, const 
   DistResult out;
   out.d = 0; out.pa = g.pa; out.pb = g.pb;
   if (P.size() < 4) return out;
+  // Robustness rules (shared with the product's EPA, csrc/drc_geom.h): removed faces found by flood fill from the
+  // closest face across shared edges (connected region, closed horizon even with coplanar faces); an expansion
+  // that would leave a hole / degenerate face / exceed the capacity is not committed; new face i reuses the slot
+  // of the i-th removed face, the last two are appended.
+  const int kMaxVert = 104, kMaxFace = 208, kMaxEdge = 96;
+  const double kVisEps = 1e-12, kMinArea2 = 1e-28;
   std::vector<EpaFace> F;
-  auto add_face = [&](int a, int b, int c) {
+  auto make_face = [&](int slot, int a, int b, int c) {
     EpaFace f;
     f.v[0] = a; f.v[1] = b; f.v[2] = c;
     V3 nrm = cross(P[b].w - P[a].w, P[c].w - P[a].w);
     double l = norm(nrm);
     f.n = l > 0 ? (1.0 / l) * nrm : V3(0, 0, 1);
     f.d = dot(f.n, P[a].w);
-    f.alive = l > 0;
-    F.push_back(f);
+    f.alive = true;
+    if (slot >= int(F.size())) F.resize(slot + 1);
+    F[slot] = f;
   };
   // orient the tetrahedron so that every face normal points away from the 4th vertex
   if (dot(cross(P[1].w - P[0].w, P[2].w - P[0].w), P[3].w - P[0].w) > 0) std::swap(P[1], P[2]);
-  add_face(0, 1, 2); add_face(0, 3, 1); add_face(0, 2, 3); add_face(1, 3, 2);
+  make_face(0, 0, 1, 2); make_face(1, 0, 3, 1); make_face(2, 0, 2, 3); make_face(3, 1, 3, 2);
   int bestf = -1;
   for (int it = 0; it < gp.epa_max_iter; ++it) {
     out.epa_iters = it + 1;
@@ -348,25 +355,48 @@ inline DistResult epa(const Shape& A, const Shape& B, const GjkResult& g, const 
     SVert s = sup(F[bestf].n);
     double ext = dot(F[bestf].n, s.w) - F[bestf].d;
     if (ext <= gp.epa_tol) break;
-    int idx = int(P.size());
-    P.push_back(s);
-    // remove the faces visible from the new vertex, collect the horizon
+    if (int(P.size()) >= kMaxVert) break;
+    const int nf = int(F.size());
+    std::vector<int> mark(nf, 0), killed, stack;   // mark: 0 untested, 1 visible, 2 tested: not visible
     std::vector<std::pair<int, int>> edges;
-    for (auto& f : F) {
-      if (!f.alive) continue;
-      if (dot(f.n, s.w - P[f.v[0]].w) > 0) {
-        f.alive = false;
-        for (int e = 0; e < 3; ++e) {
-          int a = f.v[e], b = f.v[(e + 1) % 3];
-          bool found = false;
-          for (size_t k = 0; k < edges.size(); ++k)
-            if (edges[k].first == b && edges[k].second == a) { edges.erase(edges.begin() + k); found = true; break; }
-          if (!found) edges.emplace_back(a, b);
+    bool bad = false;
+    mark[bestf] = 1; killed.push_back(bestf); stack.push_back(bestf);
+    while (!stack.empty() && !bad) {
+      const int f = stack.back();
+      stack.pop_back();
+      for (int e = 0; e < 3 && !bad; ++e) {
+        const int a = F[f].v[e], b = F[f].v[(e + 1) % 3];
+        int gn = -1;
+        for (int i = 0; i < nf; ++i) {
+          if (!F[i].alive) continue;
+          const int* v = F[i].v;
+          if ((v[0] == b && v[1] == a) || (v[1] == b && v[2] == a) || (v[2] == b && v[0] == a)) { gn = i; break; }
         }
+        if (gn < 0) { bad = true; break; }
+        if (mark[gn] == 1) continue;
+        if (mark[gn] == 0) {
+          const bool vis = dot(F[gn].n, s.w - P[F[gn].v[0]].w) > kVisEps;
+          mark[gn] = vis ? 1 : 2;
+          if (vis) {
+            if (int(killed.size()) >= kMaxEdge - 2) { bad = true; break; }
+            killed.push_back(gn); stack.push_back(gn);
+            continue;
+          }
+        }
+        if (int(edges.size()) >= kMaxEdge) { bad = true; break; }
+        edges.emplace_back(a, b);
       }
     }
-    if (edges.empty()) break;
-    for (auto& e : edges) add_face(e.first, e.second, idx);
+    const int nk = int(killed.size()), ne = int(edges.size());
+    if (bad || ne != nk + 2 || nf + 2 > kMaxFace) break;
+    for (auto& e : edges) {
+      V3 c = cross(P[e.second].w - P[e.first].w, s.w - P[e.first].w);
+      if (dot(c, c) <= kMinArea2) bad = true;
+    }
+    if (bad) break;
+    const int idx = int(P.size());
+    P.push_back(s);
+    for (int k = 0; k < ne; ++k) make_face(k < nk ? killed[k] : nf + (k - nk), edges[k].first, edges[k].second, idx);
   }
   if (bestf < 0) return out;
   // witness points: barycentric coordinates of the origin's projection on the closest face

@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, both bench arms, ncu launch list, ncu --set full of the hot kernels.
+# usage: tools/gpu_round.sh <tag>      (outputs under gpurun_out/<tag>_*)
+tag=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+  python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_bench.log 2>&1
+for k in k_admm k_collision k_robot_job; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" -c 1 -f -o gpurun_out/${tag}_${k} \
+    python tools/prof_cycle.py 65536 1 > gpurun_out/${tag}_ncu_${k}.log 2>&1
+done
+tail -3 gpurun_out/${tag}_pytest.log; cat gpurun_out/${tag}_bench.json
