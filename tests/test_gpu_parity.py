@@ -206,3 +206,51 @@ def test_error_paths(gpu_ctx):
         small.update_state(np.zeros((9, 7)), np.zeros((9, 7)))   # batch larger than the context
     with pytest.raises(DrcError):
         small.set_params(max_iter=0)
+
+
+def test_reference_api_mirror(oracle):
+    """dyros_robot_controller_b200.drc mirrors the reference's Python package: the example's call sequence
+    (examples/python/fr3_controller.py:100-176: update_state -> get_pose / get_velocity -> QPIK_cubic) on one robot
+    and on a batch."""
+    from dyros_robot_controller_b200.drc.manipulator import RobotController, RobotData
+    from tests.conftest import SRDF, URDF
+    rd = RobotData(URDF, SRDF, max_batch=64)
+    rc = RobotController(0.001, rd)
+    q, qd, q_t, xdot_t = workload(oracle.model, 64, 21)
+    f = oracle.frame_id(LINK)
+    x_t = oracle.update_state(q_t, qd, f)["pose"]
+    ref = oracle.cycle(1, q, qd, x_t, xdot_t, f)
+    # single robot, reference shapes
+    assert rd.update_state(q[0], qd[0]) is True
+    T = rd.get_pose(LINK)
+    assert T.shape == (4, 4) and np.allclose(T[3], [0, 0, 0, 1])
+    assert rd.get_jacobian(LINK).shape == (6, 7) and rd.get_mass_matrix().shape == (7, 7)
+    assert np.abs(rd.get_velocity(LINK) - rd.get_jacobian(LINK) @ qd[0]).max() < 1e-12
+    lo, hi = rd.get_joint_position_limit()
+    assert lo.shape == (7,) and (hi > lo).all()
+    md = rd.get_min_distance(True, True)
+    mm = rd.get_manipulability(True, False, LINK)
+    assert np.ndim(md.distance) == 0 and md.grad.shape == (7,) and mm.grad.shape == (7,) and np.abs(mm.grad_dot).max() == 0
+    from oracle import c_oracle
+    qdot = rc.QPIK_step(c_oracle.pose44(x_t[0]), xdot_t[0], LINK)
+    assert qdot.shape == (7,) and np.abs(qdot - ref["out"][0]).max() < 1e-4
+    # stateless twin does not disturb the cache
+    M_other = rd.compute_mass_matrix(q[1])
+    assert np.abs(M_other - oracle.update_state(q[1:2], qd[1:2], f)["M"][0]).max() < 1e-9
+    rd._single = True
+    assert np.abs(rd.get_pose(LINK) - T).max() == 0.0
+    # batched sibling
+    rd.update_state(q, qd)
+    out = rc.QPIK_step(c_oracle.pose44(x_t), xdot_t, LINK)
+    same = rc.last_iters == ref["iters"]
+    assert out.shape == (64, 7) and same.mean() > 0.95 and np.abs(out - ref["out"])[same].max() < 1e-4
+    tau = rc.QPID_step(c_oracle.pose44(x_t), xdot_t, LINK)
+    ref3 = oracle.cycle(3, q, qd, x_t, xdot_t, f)
+    same = rc.last_iters == ref3["iters"]
+    assert np.abs(tau - ref3["out"])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out"]).max())
+    # QPIK_cubic at t >= t0 + duration tracks the target itself
+    x0 = rd.get_pose(LINK)
+    out2 = rc.QPIK_cubic(c_oracle.pose44(x_t), xdot_t, x0, np.zeros((64, 6)), 2.0, 0.0, 1.0, LINK)
+    assert np.abs(out2 - out).max() < 1e-9
+    with pytest.raises(RuntimeError):
+        rc.set_task_gain(np.ones(5), np.ones(6))

@@ -12,5 +12,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 for k in k_admm k_collision k_robot_job; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" -c 1 -f -o gpurun_out/${tag}_${k} \
     python tools/prof_cycle.py 65536 1 > gpurun_out/${tag}_ncu_${k}.log 2>&1
+  # gpurun_out/ is capped at 64 MiB: keep the CSV pages, drop the report
+  ncu -i gpurun_out/${tag}_${k}.ncu-rep --page raw --csv > gpurun_out/${tag}_${k}_raw.csv 2>/dev/null
+  ncu -i gpurun_out/${tag}_${k}.ncu-rep --page source --csv > gpurun_out/${tag}_${k}_src.csv 2>/dev/null
+  ncu -i gpurun_out/${tag}_${k}.ncu-rep --page details > gpurun_out/${tag}_${k}_details.txt 2>/dev/null
+  rm -f gpurun_out/${tag}_${k}.ncu-rep
 done
+du -sh gpurun_out
 tail -3 gpurun_out/${tag}_pytest.log; cat gpurun_out/${tag}_bench.json
