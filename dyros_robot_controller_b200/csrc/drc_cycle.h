@@ -27,6 +27,7 @@ enum JobFlags : unsigned {
   F_OSF = 1u << 9,
   F_TORQUE = 1u << 10,    // moveJointTorqueStep(q_target, qdot_target)
   F_GRADDOT = 1u << 11,   // manipulability gradient time variation
+  F_MOMA = 1u << 12,      // mobile manipulator: actuated quantities through the selection matrix S, whole-body QPs
 };
 
 struct JobIO {
@@ -40,6 +41,7 @@ struct JobIO {
   const double* aux2; Strided saux2;        // n per robot: qdot_target (TORQUE)
   // state cache (SoA, component stride Bc)
   double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
+  double *c_Mact, *c_Minvact, *c_gact, *c_nleact;  // mobile manipulator: actuated-space dynamics (act x act, act)
   long long Bc;
   // outputs (any layout; null = skip)
   double* pose; Strided spose;
@@ -56,13 +58,43 @@ template <int NV>
 using QpikCfg = QpCfg<NV, 2, 2, 0, true, true>;
 template <int NV>
 using QpidCfg = QpCfg<NV, 4, 2, NV, true, true>;
+// MobileManipulator::QPIK / QPID (mobile_manipulator/QP_IK.cpp:14-28, QP_ID.cpp:14-36): hard CBF rows (no slacks);
+// QPIK keeps its (free) bound rows, QPID has none.  ACT = wheels + manipulator joints.
+template <int ACT>
+using MomaIkCfg = QpCfg<ACT, 2, 2, 0, false, true>;
+template <int ACT>
+using MomaIdCfg = QpCfg<ACT, 4, 2, ACT, false, false>;
 
-template <int NV, bool CHAIN, unsigned FLAGS>
+// (row vector r of the full model, length NV) * S  ->  ACT entries.  S is the reference's selection matrix
+// (mobile_manipulator/robot_data.cpp:22-25,115-120): identity blocks for the wheel and manipulator joints plus
+// S[virtual, mobile] = Rz(yaw) * J_mobile (Sm, 3 x W row-major).
+template <int NV, int W>
+DRC_HD void row_times_S(const DrcModelDev& m, const double* Sm, const double* r, int rs, double* out, int os) {
+  constexpr int MANI = NV - 3 - W;
+#pragma unroll
+  for (int i = 0; i < MANI; ++i) out[(m.act_mani_start + i) * os] = r[(m.mani_start + i) * rs];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    double s = r[(m.mobi_start + k) * rs];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) s += r[(m.virtual_start + a) * rs] * Sm[a * W + k];
+    out[(m.act_mobi_start + k) * os] = s;
+  }
+}
+
+template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame& frame, const JobIO& io, int b) {
+  constexpr bool MOMA = (FLAGS & F_MOMA) != 0;
+  constexpr int ACT = MOMA ? NV - 3 : NV;        // actuated dof = wheels + manipulator joints
+  constexpr int MANI = MOMA ? NV - 3 - W : NV;   // manipulator dof (mobile_manipulator/robot_data.cpp:19)
+  static_assert(!MOMA || (FLAGS & F_DYN), "mobile-manipulator jobs always recompute the dynamics");
+  // mobile-manipulator jobs pick the state source and the task signal at run time (fewer heavy instantiations)
+  const bool from_cache = (FLAGS & F_FROM_CACHE) || (MOMA && io.q == nullptr);
+  const bool step = (FLAGS & F_STEP) || (MOMA && io.x_target != nullptr);
   double q[NV], qd[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    if (FLAGS & F_FROM_CACHE) { q[i] = io.c_q[i * io.Bc + b]; qd[i] = io.c_qd[i * io.Bc + b]; }
+    if (from_cache) { q[i] = io.c_q[i * io.Bc + b]; qd[i] = io.c_qd[i * io.Bc + b]; }
     else { q[i] = io.q[b * io.sq.sb + i * io.sq.sk]; qd[i] = io.qd[b * io.sqd.sb + i * io.sqd.sk]; }
   }
   KinState<NV> k;
@@ -115,6 +147,38 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     }
   }
 
+  // mobile manipulator: S, actuated dynamics M~ = S'MS, g~ = S'g, nle~ = S'nle (mobile_manipulator/robot_data.cpp:104-144)
+  double Sm[MOMA ? 3 * W : 1], Mact[MOMA ? ACT * ACT : 1], gact[MOMA ? ACT : 1], qd_act[MOMA ? ACT : 1];
+  if (MOMA) {
+    double sy, cy;
+    sincos(q[m.virtual_start + 2], &sy, &cy);
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      Sm[0 * W + k] = cy * m.J_mobile[0][k] - sy * m.J_mobile[1][k];
+      Sm[1 * W + k] = sy * m.J_mobile[0][k] + cy * m.J_mobile[1][k];
+      Sm[2 * W + k] = m.J_mobile[2][k];
+    }
+    double T[NV * ACT], nleact[ACT], nle_full[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { row_times_S<NV, W>(m, Sm, M + i * NV, 1, T + i * ACT, 1); nle_full[i] = io.c_nle[i * io.Bc + b]; }
+#pragma unroll
+    for (int a = 0; a < ACT; ++a) row_times_S<NV, W>(m, Sm, T + a, ACT, Mact + a, ACT);
+    row_times_S<NV, W>(m, Sm, g, 1, gact, 1);
+    row_times_S<NV, W>(m, Sm, nle_full, 1, nleact, 1);
+#pragma unroll
+    for (int i = 0; i < MANI; ++i) qd_act[m.act_mani_start + i] = qd[m.mani_start + i];
+#pragma unroll
+    for (int k = 0; k < W; ++k) qd_act[m.act_mobi_start + k] = qd[m.mobi_start + k];
+    if (io.c_Mact) {
+      double Mi[ACT * ACT];
+      spd_pinv<ACT>(Mact, Mi, prm.pinv_threshold);
+#pragma unroll
+      for (int i = 0; i < ACT * ACT; ++i) { io.c_Mact[i * io.Bc + b] = Mact[i]; io.c_Minvact[i * io.Bc + b] = Mi[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < ACT; ++i) { io.c_gact[i * io.Bc + b] = gact[i]; io.c_nleact[i * io.Bc + b] = nleact[i]; }
+  }
+
   if (FLAGS & F_TORQUE) {  // tau = M (Kp (q_t - q) + Kv (qd_t - qd)) + g
     double acc[NV];
 #pragma unroll
@@ -150,6 +214,16 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     xdot[r] = s;
   }
 
+  // actuated Jacobians J~ = J S, J~dot = Jdot S (S-dot neglected, mobile_manipulator/robot_data.cpp:407-415)
+  double Jt[MOMA ? 6 * ACT : 1], Jtd[MOMA ? 6 * ACT : 1];
+  if (MOMA) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      row_times_S<NV, W>(m, Sm, J + r * NV, 1, Jt + r * ACT, 1);
+      if (need_jdot) row_times_S<NV, W>(m, Sm, Jd + r * NV, 1, Jtd + r * ACT, 1);
+    }
+  }
+
   if (FLAGS & F_FRAME_OUT) {
     if (io.pose) {
 #pragma unroll
@@ -159,10 +233,18 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
         io.pose[b * io.spose.sb + (4 * r + 3) * io.spose.sk] = comp(pf, r);
       }
     }
+    if (MOMA) {  // the actuated Jacobians (getJacobianActuated / ...TimeVariation), 6 x ACT
 #pragma unroll
-    for (int i = 0; i < 6 * NV; ++i) {
-      if (io.J) io.J[b * io.sJ.sb + i * io.sJ.sk] = J[i];
-      if (io.Jdot) io.Jdot[b * io.sJd.sb + i * io.sJd.sk] = Jd[i];
+      for (int i = 0; i < 6 * ACT; ++i) {
+        if (io.J) io.J[b * io.sJ.sb + i * io.sJ.sk] = Jt[i];
+        if (io.Jdot) io.Jdot[b * io.sJd.sb + i * io.sJd.sk] = Jtd[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6 * NV; ++i) {
+        if (io.J) io.J[b * io.sJ.sb + i * io.sJ.sk] = J[i];
+        if (io.Jdot) io.Jdot[b * io.sJd.sb + i * io.sJd.sk] = Jd[i];
+      }
     }
     if (io.vel) {
 #pragma unroll
@@ -174,11 +256,11 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   double mani = 0, mgrad[NV], mgraddot[NV];
   if (FLAGS & (F_MANIP_OUT | F_QPIK | F_QPID)) {
     constexpr bool gd = (FLAGS & (F_QPID | F_GRADDOT)) != 0;
-    manipulability<NV, NV, CHAIN>(m, k, frame.parent, pf, J, Jd, 0, gd, prm.pinv_threshold, mani, mgrad, mgraddot);
-    if (FLAGS & F_MANIP_OUT) {
+    manipulability<NV, MANI, CHAIN>(m, k, frame.parent, pf, J, Jd, MOMA ? m.mani_start : 0, gd, prm.pinv_threshold, mani, mgrad, mgraddot);
+    if ((FLAGS & F_MANIP_OUT) && io.mani) {
       io.mani[b] = mani;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
+      for (int i = 0; i < MANI; ++i) {
         if (io.mani_grad) io.mani_grad[b * io.smg.sb + i * io.smg.sk] = mgrad[i];
         if (gd && io.mani_graddot) io.mani_graddot[b * io.smgd.sb + i * io.smgd.sk] = mgraddot[i];
       }
@@ -191,7 +273,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     double xd_t[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) xd_t[r] = io.xdot_target[b * io.sxd.sb + r * io.sxd.sk];
-    if (FLAGS & F_STEP) {
+    if (step) {
       Mat3 Rt;
       Vec3 pt;
 #pragma unroll
@@ -206,7 +288,9 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         // CLIKStep: Kp e + xdot_target (robot_controller.cpp:169); QPIK/QPID/OSF Step: Kp e + Kv edot (:238,:299,:342)
-        des[r] = prm.Kp_task[r] * xe[r] + ((FLAGS & F_CLIK) ? xd_t[r] : prm.Kv_task[r] * (xd_t[r] - xdot[r]));
+        // MobileManipulator QPIKStep: Kp e + xdot_target as well (mobile_manipulator/robot_controller.cpp:181)
+        constexpr bool no_kv = (FLAGS & F_CLIK) != 0 || (MOMA && (FLAGS & F_QPIK) != 0);
+        des[r] = prm.Kp_task[r] * xe[r] + (no_kv ? xd_t[r] : prm.Kv_task[r] * (xd_t[r] - xdot[r]));
       }
     } else {
 #pragma unroll
@@ -290,58 +374,78 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
 
   if (FLAGS & (F_QPIK | F_QPID)) {
     constexpr bool ID = (FLAGS & F_QPID) != 0;
-    typedef typename std::conditional<ID, QpidCfg<NV>, QpikCfg<NV>>::type Cfg;
+    typedef typename std::conditional<MOMA, typename std::conditional<ID, MomaIdCfg<ACT>, MomaIkCfg<ACT>>::type,
+                                      typename std::conditional<ID, QpidCfg<NV>, QpikCfg<NV>>::type>::type Cfg;
+    static_assert(Cfg::NC == ACT, "core variables of the QP = actuated joints");
     double* rec = io.qp + (long long)b * Cfg::STRIDE;
     const double al = prm.alpha;
+    // core-space views: the manipulator QPs act on qdot / qddot of the arm itself, the whole-body QPs on eta / eta_dot
+    const double* Jc = MOMA ? Jt : J;
+    const double* Jdc = MOMA ? Jtd : Jd;
+    const double* vc = MOMA ? qd_act : qd;
+    const int am = MOMA ? m.act_mani_start : 0, ms = MOMA ? m.mani_start : 0;
     double rhs[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       double s = des[r];
       if (ID) {
 #pragma unroll
-        for (int j = 0; j < NV; ++j) s -= Jd[r * NV + j] * qd[j];
+        for (int j = 0; j < ACT; ++j) s -= Jdc[r * ACT + j] * vc[j];
       }
       rhs[r] = s;
     }
+    const double reg = ID ? 0.0 : (MOMA ? prm.moma_ik_reg : prm.ik_reg);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < ACT; ++i) {
 #pragma unroll
-      for (int j = i; j < NV; ++j) {
+      for (int j = i; j < ACT; ++j) {
         double s = 0;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) s += J[r * NV + i] * J[r * NV + j];
-        rec[Cfg::OFF_P + symidx<NV>(i, j)] = 2.0 * s + ((!ID && i == j) ? prm.ik_reg : 0.0);
+        for (int r = 0; r < 6; ++r) s += Jc[r * ACT + i] * Jc[r * ACT + j];
+        rec[Cfg::OFF_P + symidx<ACT>(i, j)] = 2.0 * s + (i == j ? reg : 0.0);
       }
       double s = 0;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) s += J[r * NV + i] * rhs[r];
+      for (int r = 0; r < 6; ++r) s += Jc[r * ACT + i] * rhs[r];
       rec[Cfg::OFF_Q + i] = -2.0 * s;
-      rec[Cfg::OFF_LO + i] = ID ? -kOsqpInfty : -m.v_lim[i];
-      rec[Cfg::OFF_HI + i] = ID ? kOsqpInfty : m.v_lim[i];
+      // bound rows: qdot limits for the manipulator QPIK, free otherwise (QP_ID.cpp / mobile_manipulator/QP_IK.cpp:75-83)
+      const bool bounded = !ID && !MOMA;
+      rec[Cfg::OFF_LO + i] = bounded ? -m.v_lim[i] : -kOsqpInfty;
+      rec[Cfg::OFF_HI + i] = bounded ? m.v_lim[i] : kOsqpInfty;
+#pragma unroll
+      for (int k = 0; k < Cfg::KU; ++k) rec[Cfg::OFF_UNIT + k * ACT + i] = -kOsqpInfty;  // rows of non-manipulator variables are masked off
+    }
+#pragma unroll
+    for (int i = 0; i < MANI; ++i) {  // CBF rows on the manipulator joints
+      const double qi = q[ms + i], qdi = qd[ms + i], lo = m.q_lo[ms + i], hi = m.q_hi[ms + i], vl = m.v_lim[ms + i];
       if (!ID) {
-        rec[Cfg::OFF_UNIT + 0 * NV + i] = -al * (q[i] - m.q_lo[i]);
-        rec[Cfg::OFF_UNIT + 1 * NV + i] = -al * (m.q_hi[i] - q[i]);
+        rec[Cfg::OFF_UNIT + 0 * ACT + am + i] = -al * (qi - lo);
+        rec[Cfg::OFF_UNIT + 1 * ACT + am + i] = -al * (hi - qi);
       } else {
-        rec[Cfg::OFF_UNIT + 0 * NV + i] = -(al + al) * qd[i] - al * al * (q[i] - m.q_lo[i]);
-        rec[Cfg::OFF_UNIT + 1 * NV + i] = +(al + al) * qd[i] - al * al * (m.q_hi[i] - q[i]);
-        rec[Cfg::OFF_UNIT + 2 * NV + i] = -al * (qd[i] + m.v_lim[i]);
-        rec[Cfg::OFF_UNIT + 3 * NV + i] = -al * (m.v_lim[i] - qd[i]);
+        rec[Cfg::OFF_UNIT + 0 * ACT + am + i] = -(al + al) * qdi - al * al * (qi - lo);
+        rec[Cfg::OFF_UNIT + 1 * ACT + am + i] = +(al + al) * qdi - al * al * (hi - qi);
+        rec[Cfg::OFF_UNIT + 2 * ACT + am + i] = -al * (qdi + vl);
+        rec[Cfg::OFF_UNIT + 3 * ACT + am + i] = -al * (vl - qdi);
       }
     }
-    // dense row 0: singularity avoidance
+    // dense row 0: singularity avoidance (manipulator columns only)
     double* row0 = rec + Cfg::OFF_ROW;
     double gq = 0, gdq = 0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { row0[i] = mgrad[i]; gq += mgrad[i] * qd[i]; if (ID) gdq += mgraddot[i] * qd[i]; }
-    row0[NV] = ID ? (-gdq - (al + al) * gq - al * al * (mani - prm.mani_thresh)) : (-al * (mani - prm.mani_thresh));
+    for (int i = 0; i < ACT; ++i) row0[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < MANI; ++i) { row0[am + i] = mgrad[i]; gq += mgrad[i] * qd[ms + i]; if (ID) gdq += mgraddot[i] * qd[ms + i]; }
+    row0[ACT] = ID ? (-gdq - (al + al) * gq - al * al * (mani - prm.mani_thresh)) : (-al * (mani - prm.mani_thresh));
     // dense row 1 (self-collision) is written by collision_job
-    if (ID) {
+    if (ID) {  // equality rows  M qddot - tau = -g  (actuated space for the whole-body QP)
+      const double* Mc = MOMA ? Mact : M;
+      const double* gc = MOMA ? gact : g;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        double* row = rec + Cfg::OFF_ROW + (2 + i) * (NV + 1);
+      for (int i = 0; i < ACT; ++i) {
+        double* row = rec + Cfg::OFF_ROW + (2 + i) * (ACT + 1);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) row[j] = M[i * NV + j];
-        row[NV] = -g[i];
+        for (int j = 0; j < ACT; ++j) row[j] = Mc[i * ACT + j];
+        row[ACT] = -gc[i];
       }
     }
   }
@@ -356,6 +460,7 @@ struct CollisionIO {
   long long Bc;
   double* qp;                        // QP records; row written: dense row 1
   int qp_stride, qp_row_off;         // Cfg::STRIDE, offset of dense row 1 inside the record
+  int row_n, row_col0, src0, nsrc;   // row has row_n coefficients; joints src0..src0+nsrc-1 go to columns row_col0.. (0 = all NV)
   int mode;                          // 0 getter only, 1 QPIK row, 2 QPID row
   double* dist; double* grad; Strided sgrad; double* grad_dot; Strided sgd;  // getter outputs (null = skip)
   int* pair_out; double* witness;    // optional: argmin pair (reference order) and pa|pb (6, AoS)
@@ -476,9 +581,15 @@ DRC_HD void collision_finish(const DrcModelDev& m, const DrcParams& prm, const C
     double* row = io.qp + (long long)b * io.qp_stride + io.qp_row_off;
     const double al = prm.alpha;
     double gq = 0, gdq = 0;
+    // whole-body QPs keep the manipulator slice of the gradient only (mobile_manipulator/QP_IK.cpp:121)
+    const int rn = io.row_n > 0 ? io.row_n : NV, c0 = io.row_n > 0 ? io.row_col0 : 0, s0 = io.row_n > 0 ? io.src0 : 0,
+              ns = io.row_n > 0 ? io.nsrc : NV;
+    for (int j = 0; j < rn; ++j) row[j] = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) { row[j] = grad[j]; gq += grad[j] * qd[j]; gdq += gdot[j] * qd[j]; }
-    row[NV] = io.mode == 2 ? (-gdq - (al + al) * gq - al * al * (best.d - prm.dist_thresh)) : (-al * (best.d - prm.dist_thresh));
+    for (int j = 0; j < NV; ++j) {
+      if (j >= s0 && j < s0 + ns) { row[c0 + j - s0] = grad[j]; gq += grad[j] * qd[j]; gdq += gdot[j] * qd[j]; }
+    }
+    row[rn] = io.mode == 2 ? (-gdq - (al + al) * gq - al * al * (best.d - prm.dist_thresh)) : (-al * (best.d - prm.dist_thresh));
   }
 }
 

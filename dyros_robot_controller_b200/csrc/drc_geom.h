@@ -302,10 +302,22 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
     if (inside) { lam[0] = lam[1] = lam[2] = lam[3] = 0.25; n = 4; inter = true; break; }
     Vec3 nv = v3(0, 0, 0);
     for (int i = 0; i < n; ++i) nv = nv + lam[i] * sv[i].w;
-    if (dot(nv, nv) >= vv) {  // numerical floor: keep the previous simplex
-      n = prev_n;
-      for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
-      break;
+    if (dot(nv, nv) >= vv) {
+      // the simplex sub-algorithm lost precision (thin simplex): restart from the segment [current closest point,
+      // new vertex] -- a Frank-Wolfe step with exact line search, which improves whenever the gap is positive.
+      // The closest point is a valid vertex: a convex combination of support points of A and of B.
+      SimplexVert cp;
+      cp.w = v; cp.a = v3(0, 0, 0); cp.b = v3(0, 0, 0);
+      for (int i = 0; i < prev_n; ++i) { cp.a = cp.a + prev_lam[i] * prev_sv[i].a; cp.b = cp.b + prev_lam[i] * prev_sv[i].b; }
+      sv[0] = cp; sv[1] = nw; n = 2;
+      closest_segment(sv, n, lam);
+      nv = v3(0, 0, 0);
+      for (int i = 0; i < n; ++i) nv = nv + lam[i] * sv[i].w;
+      if (dot(nv, nv) >= vv) {  // numerical floor: keep the previous simplex
+        n = prev_n;
+        for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
+        break;
+      }
     }
     v = nv;
   }

@@ -393,7 +393,8 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
 
 template <int NV, bool CHAIN, unsigned FLAGS>
 static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
-  const int threads = 64, blocks = (io.B + threads - 1) / threads;
+  static const int threads = [] { const char* e = getenv("DRC_JOB_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 128 ? t : 64; }();
+  const int blocks = (io.B + threads - 1) / threads;
   k_robot_job<NV, CHAIN, FLAGS><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
   c->launches++;
   CU(cudaGetLastError());
@@ -408,7 +409,8 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s) {
   if (!io.dist) io.dist = c->col_dist;
   if (!io.pair_out) io.pair_out = c->col_pair;
   if (!io.witness) io.witness = c->col_wit;
-  const int threads = 64, blocks = (io.B + threads - 1) / threads;
+  static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 128 ? t : 64; }();
+  const int blocks = (io.B + threads - 1) / threads;
   k_collision<NV, CHAIN><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
   k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, s>>>(c->model->hm.dev, c->prm, io);

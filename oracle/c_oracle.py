@@ -218,6 +218,78 @@ class Oracle:
         return tau
 
 
+class MomaOracle(Oracle):
+    """Mobile-manipulator restatement (oracle/src/omoma.h).  kin: dict(type, wheel_radius, base_width, wheel_offset,
+    roller_angles, base2wheel_positions [(x, y)...], base2wheel_angles) like the reference's Mobile::KinematicParam
+    (type_define.h:58-72); joint_idx / actuator_idx like JointIndex / ActuatorIndex."""
+
+    DRIVE = dict(Differential=0, Mecanum=1, Caster=2)
+
+    def __init__(self, urdf_path, srdf_path, kin: dict, joint_idx: dict, actuator_idx: dict, threads: int = 1):
+        super().__init__(urdf_path, srdf_path, threads)
+        t = kin["type"] if isinstance(kin["type"], int) else self.DRIVE[kin["type"]]
+        pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+        if t == 0:
+            w = 2
+        elif t == 1:
+            w = len(kin["roller_angles"])
+        else:
+            w = 2 * len(pos)
+        self.w, self.act, self.mani = w, self.nv - 3, self.nv - 3 - w
+        self.joint_idx, self.actuator_idx = dict(joint_idx), dict(actuator_idx)
+        ra = _c(kin.get("roller_angles", np.zeros(w))) if t == 1 else None
+        ba = _c(kin.get("base2wheel_angles", np.zeros(w))) if t == 1 else None
+        bx = _c(pos[:, 0]) if len(pos) else None
+        by = _c(pos[:, 1]) if len(pos) else None
+        lib().orc_model_set_moma(self.h, C.c_int(t), C.c_double(kin.get("wheel_radius", 0.0)), C.c_double(kin.get("base_width", 0.0)),
+                                 C.c_double(kin.get("wheel_offset", 0.0)), C.c_int(w), _d(ra), _d(bx), _d(by), _d(ba),
+                                 C.c_int(joint_idx["virtual_start"]), C.c_int(joint_idx["mani_start"]),
+                                 C.c_int(joint_idx["mobi_start"]), C.c_int(actuator_idx["mani_start"]),
+                                 C.c_int(actuator_idx["mobi_start"]))
+
+    def mobile_state(self, wheel_pos, wheel_vel):
+        wp, wv = _c(wheel_pos).reshape(-1, self.w), _c(wheel_vel).reshape(-1, self.w)
+        B = wp.shape[0]
+        J, bv = np.zeros((B, 3, self.w)), np.zeros((B, 3))
+        lib().orc_mobile_state(self.h, C.c_int(B), _d(wp), _d(wv), _d(J), _d(bv))
+        return J, bv
+
+    def moma_update_state(self, q, qd, frame: int):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n, a, k = q.shape[0], self.nv, self.act, self.mani
+        o = dict(S=np.zeros((B, n, a)), M=np.zeros((B, a, a)), Minv=np.zeros((B, a, a)), g=np.zeros((B, a)), nle=np.zeros((B, a)),
+                 J=np.zeros((B, 6, a)), Jdot=np.zeros((B, 6, a)), mani=np.zeros(B), mani_grad=np.zeros((B, k)),
+                 mani_graddot=np.zeros((B, k)))
+        lib().orc_moma_update_state(self.h, C.c_int(B), _d(q), _d(qd), C.c_int(frame), _d(o["S"]), _d(o["M"]), _d(o["Minv"]),
+                                    _d(o["g"]), _d(o["nle"]), _d(o["J"]), _d(o["Jdot"]), _d(o["mani"]), _d(o["mani_grad"]),
+                                    _d(o["mani_graddot"]))
+        return o
+
+    def moma_qp_sizes(self, kind: int):
+        nx, nc = C.c_int(), C.c_int()
+        lib().orc_moma_qp_sizes(self.h, C.c_int(kind), C.byref(nx), C.byref(nc))
+        return nx.value, nc.value
+
+    def moma_build_qp(self, kind: int, q, qd, des, frame: int):
+        nx, nc = self.moma_qp_sizes(kind)
+        P, qv, A, l, u = np.zeros((nx, nx)), np.zeros(nx), np.zeros((nc, nx)), np.zeros(nc), np.zeros(nc)
+        lib().orc_moma_build_qp(self.h, C.c_int(kind), _d(_c(q)), _d(_c(qd)), _d(_c(des)), C.c_int(frame), _d(P), _d(qv), _d(A),
+                                _d(l), _d(u))
+        return P, qv, A, l, u
+
+    def moma_cycle(self, mode: int, q, qd, x_target, xdot_target, frame: int):
+        """mode 0 QPIK 1 QPIKStep 2 QPID 3 QPIDStep -> out (B, act): eta* | tau*; out2: eta_dot* (modes 2/3)."""
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B = q.shape[0]
+        xt = None if x_target is None else _c(x_target).reshape(B, 12)
+        xd = _c(xdot_target).reshape(B, 6)
+        out, out2 = np.zeros((B, self.act)), np.zeros((B, self.act))
+        st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        lib().orc_moma_cycle(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out), _d(out2),
+                             _i(st), _i(it))
+        return dict(out=out, out2=out2, status=st, iters=it)
+
+
 def task_space_cubic(x_target, xdot_target, x_init, xdot_init, t, t0, dur):
     xd, xdd = np.zeros(12), np.zeros(6)
     lib().orc_task_space_cubic(_d(pose12(x_target)), _d(_c(xdot_target)), _d(pose12(x_init)), _d(_c(xdot_init)),

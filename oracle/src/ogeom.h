@@ -275,10 +275,21 @@ inline GjkResult gjk(const Shape& A, const Shape& B, const GeomParams& gp) {
     if (inside) { for (int i = 0; i < 4; ++i) lam[i] = 0.25; n = 4; return finish(true); }
     V3 nv;
     for (int i = 0; i < n; ++i) nv += lam[i] * sv[i].w;
-    if (dot(nv, nv) >= vv) {  // no progress: numerical floor reached, keep the previous simplex
-      n = prev_n;
-      for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
-      return finish(false);
+    if (dot(nv, nv) >= vv) {
+      // the simplex sub-algorithm lost precision (thin simplex): restart from the segment [current closest point,
+      // new vertex] -- a Frank-Wolfe step with exact line search (same rule as the product's GJK)
+      SVert cp;
+      cp.w = v;
+      for (int i = 0; i < prev_n; ++i) { cp.a += prev_lam[i] * prev_sv[i].a; cp.b += prev_lam[i] * prev_sv[i].b; }
+      sv[0] = cp; sv[1] = nw; n = 2;
+      closest_on_segment(sv, n, lam);
+      nv = V3();
+      for (int i = 0; i < n; ++i) nv += lam[i] * sv[i].w;
+      if (dot(nv, nv) >= vv) {  // no progress: numerical floor reached, keep the previous simplex
+        n = prev_n;
+        for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
+        return finish(false);
+      }
     }
     v = nv;
   }

@@ -7,7 +7,7 @@
 // Poses are 12 doubles: the top three rows of the 4x4 homogeneous matrix, row-major.
 #include <omp.h>
 
-#include "octrl.h"
+#include "omoma.h"
 
 using namespace orc;
 
@@ -310,5 +310,112 @@ void orc_task_space_cubic(const double* x_target, const double* xdot_target, con
 }
 
 void orc_pinv(const double* A, int m, int n, double* out) { pinv_cod(A, m, n, out); }
+
+
+// ---- mobile base / mobile manipulator (omoma.h)
+void orc_model_set_moma(OrcHandle* h, int drive_type, double wheel_radius, double base_width, double wheel_offset, int wheel_num,
+                        const double* roller_angles, const double* b2w_x, const double* b2w_y, const double* b2w_ang,
+                        int virtual_start, int mani_start, int mobi_start, int act_mani_start, int act_mobi_start) {
+  Model& m = h->m;
+  m.drive_type = drive_type; m.wheel_radius = wheel_radius; m.base_width = base_width; m.wheel_offset = wheel_offset;
+  m.wheel_num = wheel_num; m.virtual_start = virtual_start; m.mani_start = mani_start; m.mobi_start = mobi_start;
+  m.act_mani_start = act_mani_start; m.act_mobi_start = act_mobi_start;
+  const int np = drive_type == 2 ? wheel_num / 2 : wheel_num;
+  m.roller_angles.assign(wheel_num, 0.0); m.b2w_x.assign(np, 0.0); m.b2w_y.assign(np, 0.0); m.b2w_ang.assign(wheel_num, 0.0);
+  for (int i = 0; i < wheel_num; ++i) { if (roller_angles) m.roller_angles[i] = roller_angles[i]; if (b2w_ang) m.b2w_ang[i] = b2w_ang[i]; }
+  for (int i = 0; i < np; ++i) { if (b2w_x) m.b2w_x[i] = b2w_x[i]; if (b2w_y) m.b2w_y[i] = b2w_y[i]; }
+}
+// Mobile::RobotData: FK Jacobian (3 x w) and base velocity for B wheel states
+void orc_mobile_state(OrcHandle* h, int B, const double* wheel_pos, const double* wheel_vel, double* J, double* base_vel) {
+  const Model& m = h->m;
+  const int w = m.wheel_num;
+  for (int b = 0; b < B; ++b) {
+    double Jm[3 * 8];
+    mobile_fk_jacobian(m, wheel_pos + w * b, Jm);
+    if (J) std::copy(Jm, Jm + 3 * w, J + 3 * w * b);
+    if (base_vel)
+      for (int r = 0; r < 3; ++r) {
+        double v = 0;
+        for (int k = 0; k < w; ++k) v += Jm[r * w + k] * wheel_vel[w * b + k];
+        base_vel[3 * b + r] = v;
+      }
+  }
+}
+// MobileManipulator::RobotData::updateState on full-dof vectors: S (n x act), M~, M~^-1, g~, nle~, J~, J~dot, manipulability
+void orc_moma_update_state(OrcHandle* h, int B, const double* q, const double* qd, int frame, double* S, double* Mact,
+                           double* Minv_act, double* g_act, double* nle_act, double* Jt, double* Jtd, double* mani,
+                           double* mani_grad, double* mani_graddot) {
+  const Model& m = h->m;
+  const int n = m.nv;
+#pragma omp parallel num_threads(h->threads)
+  {
+    State s;
+    MomaState ms;
+#pragma omp for schedule(static)
+    for (int b = 0; b < B; ++b) {
+      update_state(m, s, q + b * n, qd + b * n);
+      moma_update(m, s, ms);
+      const int act = ms.act, k = ms.mani;
+      if (S) std::copy(ms.S, ms.S + n * act, S + size_t(b) * n * act);
+      if (Mact) std::copy(ms.M, ms.M + act * act, Mact + size_t(b) * act * act);
+      if (Minv_act) std::copy(ms.Minv, ms.Minv + act * act, Minv_act + size_t(b) * act * act);
+      if (g_act) std::copy(ms.g, ms.g + act, g_act + size_t(b) * act);
+      if (nle_act) std::copy(ms.nle, ms.nle + act, nle_act + size_t(b) * act);
+      if (Jt) moma_jacobians(m, s, ms, frame, Jt + size_t(b) * 6 * act, Jtd ? Jtd + size_t(b) * 6 * act : nullptr);
+      if (mani) {
+        ManipResult mr;
+        manipulability(m, s, frame, true, mani_graddot != nullptr, m.mani_start, k, mr);
+        mani[b] = mr.m;
+        if (mani_grad) std::copy(mr.grad, mr.grad + k, mani_grad + size_t(b) * k);
+        if (mani_graddot) std::copy(mr.grad_dot, mr.grad_dot + k, mani_graddot + size_t(b) * k);
+      }
+    }
+  }
+}
+void orc_moma_qp_sizes(OrcHandle* h, int kind, int* nx, int* nc) {
+  const int n = h->m.nv, w = h->m.wheel_num, k = n - 3 - w, act = w + k;
+  if (kind == 0) { *nx = act; *nc = act + 2 * k + 2; }
+  else { *nx = 2 * act; *nc = 4 * k + 2 + act; }
+}
+void orc_moma_build_qp(OrcHandle* h, int kind, const double* q, const double* qd, const double* des, int frame, double* P,
+                       double* qv, double* A, double* l, double* u) {
+  Workspace ws;
+  MomaState ms;
+  update_state(h->m, ws.s, q, qd);
+  moma_update(h->m, ws.s, ms);
+  if (kind == 0) build_moma_qpik(h->m, ws.s, ms, frame, des, h->cp, h->gp, ws.pb);
+  else build_moma_qpid(h->m, ws.s, ms, frame, des, h->cp, h->gp, ws.pb);
+  std::copy(ws.pb.P.begin(), ws.pb.P.end(), P); std::copy(ws.pb.q.begin(), ws.pb.q.end(), qv);
+  std::copy(ws.pb.A.begin(), ws.pb.A.end(), A); std::copy(ws.pb.l.begin(), ws.pb.l.end(), l);
+  std::copy(ws.pb.u.begin(), ws.pb.u.end(), u);
+}
+// mode: 0 QPIK(xdot_des) 1 QPIKStep 2 QPID(xddot_des) 3 QPIDStep.  out: (B, act) eta* | tau*;  out2: (B, act) eta_dot* (modes 2/3)
+void orc_moma_cycle(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                    const double* xdot_target, int frame, double* out, double* out2, int* status, int* iters) {
+  const Model& m = h->m;
+  const int n = m.nv;
+#pragma omp parallel num_threads(h->threads)
+  {
+    Workspace ws;
+    MomaState ms;
+#pragma omp for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+      update_state(m, ws.s, q + b * n, qd + b * n);
+      moma_update(m, ws.s, ms);
+      const int act = ms.act;
+      double des[6];
+      if (mode == 0 || mode == 2) std::copy(xdot_target + 6 * b, xdot_target + 6 * b + 6, des);
+      else desired_from_error(m, ws.s, frame, pose_from12(x_target + 12 * b), xdot_target + 6 * b, h->cp, mode == 3, des);
+      int st;
+      if (mode <= 1) st = ctrl_moma_qpik(m, ws, ms, frame, des, h->cp, h->gp, h->qs, out + size_t(b) * act);
+      else {
+        double ed[MAXV];
+        st = ctrl_moma_qpid(m, ws, ms, frame, des, h->cp, h->gp, h->qs, out2 ? out2 + size_t(b) * act : ed, out + size_t(b) * act);
+      }
+      if (status) status[b] = st;
+      if (iters) iters[b] = ws.res.iters;
+    }
+  }
+}
 
 }  // extern "C"

@@ -57,3 +57,36 @@ def gpu_ctx():
     model = drc.Model(URDF, SRDF)
     ctx = drc.Context(model, 65536, device=0)
     return model, ctx
+
+
+# ---- mobile manipulators (synthesized URDFs, tools/make_moma_urdf.py): joints [virtual 0..2, wheels 3..3+w-1, arm]
+ROBOTS = ROOT / "dyros_robot_controller_b200" / "robots"
+MOMA = {
+    "husky_fr3": dict(urdf=str(ROBOTS / "husky_fr3" / "husky_fr3.urdf"), srdf=str(ROBOTS / "husky_fr3" / "husky_fr3.srdf"),
+                      kin=dict(type="Differential", wheel_radius=0.1651, base_width=0.555),
+                      joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=5), actuator_idx=dict(mobi_start=0, mani_start=2)),
+    # mecanum parameters of the reference's XLS example (examples/C++/src/xls_controller.cpp:18-27)
+    "xls_fr3": dict(urdf=str(ROBOTS / "xls_fr3" / "xls_fr3.urdf"), srdf=str(ROBOTS / "xls_fr3" / "xls_fr3.srdf"),
+                    kin=dict(type="Mecanum", wheel_radius=0.120, roller_angles=[-np.pi / 4, np.pi / 4, np.pi / 4, -np.pi / 4],
+                             base2wheel_positions=[(0.2225, 0.2045), (0.2225, -0.2045), (-0.2225, 0.2045), (-0.2225, -0.2045)],
+                             base2wheel_angles=[0.0, 0.0, 0.0, 0.0]),
+                    joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=7), actuator_idx=dict(mobi_start=0, mani_start=4)),
+}
+
+
+def moma_workload(model_like, w, B, seed):
+    """base pose U([-2,2]^2 x [-pi,pi]), wheel angles U(-pi,pi), wheel speeds U(-2,2); arm as config 1."""
+    rng = np.random.default_rng(seed)
+    n = len(model_like.q_lo)
+    lo, hi, vl = model_like.q_lo[3 + w:], model_like.q_hi[3 + w:], model_like.v_lim[3 + w:]
+    q, qd = np.zeros((B, n)), np.zeros((B, n))
+    q[:, 0:2] = rng.uniform(-2, 2, (B, 2)); q[:, 2] = rng.uniform(-np.pi, np.pi, B)
+    q[:, 3:3 + w] = rng.uniform(-np.pi, np.pi, (B, w))
+    q[:, 3 + w:] = lo + (0.1 + 0.8 * rng.random((B, n - 3 - w))) * (hi - lo)
+    qd[:, 3:3 + w] = rng.uniform(-2, 2, (B, w))
+    qd[:, 3 + w:] = rng.uniform(-0.5, 0.5, (B, n - 3 - w)) * vl
+    q_t = q.copy()
+    q_t[:, 3 + w:] += 0.05 * rng.normal(size=(B, n - 3 - w))
+    q_t[:, 0:2] += 0.05 * rng.normal(size=(B, 2))
+    xdot_t = 0.05 * rng.normal(size=(B, 6))
+    return q, qd, q_t, xdot_t

@@ -145,6 +145,56 @@ class Emu:
         return float(d), wa, wb, info
 
 
+class MomaEmu(Emu):
+    """Kernel bodies of the mobile-manipulator path (rows a15-a18) on the CPU."""
+
+    def __init__(self, urdf_path, srdf_path, kin: dict, joint_idx: dict, actuator_idx: dict):
+        super().__init__(urdf_path, srdf_path)
+        t = kin["type"] if isinstance(kin["type"], int) else dict(Differential=0, Mecanum=1, Caster=2)[kin["type"]]
+        pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+        w = 2 if t == 0 else (len(kin["roller_angles"]) if t == 1 else 2 * len(pos))
+        self.w, self.act, self.mani = w, self.nv - 3, self.nv - 3 - w
+        ra = _c(kin.get("roller_angles", np.zeros(w))) if t == 1 else None
+        ba = _c(kin.get("base2wheel_angles", np.zeros(w))) if t == 1 else None
+        bx = _c(pos[:, 0]) if len(pos) else None
+        by = _c(pos[:, 1]) if len(pos) else None
+        err = C.create_string_buffer(512)
+        rc = lib().emu_moma_attach(self.h, C.c_int(t), C.c_double(kin.get("wheel_radius", 0.0)), C.c_double(kin.get("base_width", 0.0)),
+                                   C.c_double(kin.get("wheel_offset", 0.0)), C.c_int(w), _d(ra), _d(bx), _d(by), _d(ba),
+                                   C.c_int(joint_idx["virtual_start"]), C.c_int(joint_idx["mani_start"]), C.c_int(joint_idx["mobi_start"]),
+                                   C.c_int(actuator_idx["mani_start"]), C.c_int(actuator_idx["mobi_start"]), err, 512)
+        if rc:
+            raise RuntimeError(err.value.decode())
+
+    def base_jacobian(self):
+        J = np.zeros((3, self.w))
+        lib().emu_moma_base_jacobian(self.h, _d(J))
+        return J
+
+    def moma_state(self, q, qd, frame):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, a, k = q.shape[0], self.act, self.mani
+        o = dict(pose=np.zeros((B, 12)), J=np.zeros((B, 6, a)), Jdot=np.zeros((B, 6, a)), vel=np.zeros((B, 6)), M=np.zeros((B, a, a)),
+                 Minv=np.zeros((B, a, a)), g=np.zeros((B, a)), nle=np.zeros((B, a)), mani=np.zeros(B), mani_grad=np.zeros((B, k)),
+                 mani_graddot=np.zeros((B, k)))
+        rc = lib().emu_moma_state(self.h, C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(o["pose"]), _d(o["J"]), _d(o["Jdot"]),
+                                  _d(o["vel"]), _d(o["M"]), _d(o["Minv"]), _d(o["g"]), _d(o["nle"]), _d(o["mani"]), _d(o["mani_grad"]),
+                                  _d(o["mani_graddot"]))
+        assert rc == 0, rc
+        return o
+
+    def moma_cycle(self, mode, q, qd, x_target, xdot_target, frame):
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B = q.shape[0]
+        xt = None if x_target is None else _c(x_target).reshape(B, 12)
+        xd = _c(xdot_target).reshape(B, 6)
+        o = dict(out=np.zeros((B, self.act)), out2=np.zeros((B, self.act)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
+        rc = lib().emu_moma_cycle(self.h, C.c_int(mode), C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), _d(o["out"]),
+                                  _d(o["out2"]), _i(o["status"]), _i(o["iters"]))
+        assert rc == 0, rc
+        return o
+
+
 def pair_lower_bound(ta, prm_a, Ta, tb, prm_b, Tb):
     def p12(T):
         T = np.asarray(T, np.float64)

@@ -265,4 +265,121 @@ double emu_pair_lower_bound(int ta, const double* pa, const double* Ta, int tb, 
   return pair_lower_bound(mk(ta, pa, Ta), mk(tb, pb, Tb));
 }
 
+
+// ---- mobile manipulator (rows a15-a18): attach a base, state update with actuated quantities, whole-body QP cycles
+int emu_moma_attach(EmuHandle* h, int drive_type, double wheel_radius, double base_width, double wheel_offset, int w,
+                    const double* roller, const double* b2w_x, const double* b2w_y, const double* b2w_ang, int vs, int ms,
+                    int bs, int ams, int abs_, char* err, int errlen) {
+  try {
+    MobileParam p;
+    p.drive_type = drive_type; p.wheel_radius = wheel_radius; p.base_width = base_width; p.wheel_offset = wheel_offset;
+    const int np = drive_type == kCaster ? w / 2 : w;
+    for (int i = 0; i < w && roller; ++i) p.roller_angles.push_back(roller[i]);
+    for (int i = 0; i < np && b2w_x; ++i) { p.b2w_x.push_back(b2w_x[i]); p.b2w_y.push_back(b2w_y[i]); }
+    for (int i = 0; i < w && b2w_ang; ++i) p.b2w_angles.push_back(b2w_ang[i]);
+    attach_mobile_base(h->hm, p, vs, ms, bs, ams, abs_);
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
+    return -1;
+  }
+}
+void emu_moma_base_jacobian(EmuHandle* h, double* J /* 3 x w */) {
+  const DrcModelDev& d = h->hm.dev;
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < d.wheel_num; ++k) J[r * d.wheel_num + k] = d.J_mobile[r][k];
+}
+
+}  // extern "C"
+
+struct MomaCache : Cache {
+  std::vector<double> Mact, Minvact, gact, nleact;
+  MomaCache(int nv, int act, int B) : Cache(nv, B), Mact(act * act * B), Minvact(act * act * B), gact(act * B), nleact(act * B) {}
+  void bind(JobIO& io) {
+    Cache::bind(io);
+    io.c_Mact = Mact.data(); io.c_Minvact = Minvact.data(); io.c_gact = gact.data(); io.c_nleact = nleact.data();
+  }
+};
+
+template <int NV, int W>
+static int moma_state_t(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* Jt, double* Jtd,
+                        double* vel, double* Mact, double* Minvact, double* gact, double* nleact, double* mani, double* mgrad,
+                        double* mgraddot) {
+  constexpr int ACT = NV - 3, MANI = NV - 3 - W;
+  const DrcFrame fr = make_frame(h->hm, frame_id);
+  MomaCache c(NV, ACT, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(NV); io.qd = qd; io.sqd = aos(NV);
+  c.bind(io);
+  io.pose = pose; io.spose = aos(12); io.J = Jt; io.sJ = aos(6 * ACT); io.Jdot = Jtd; io.sJd = aos(6 * ACT); io.vel = vel; io.svel = aos(6);
+  io.mani = mani; io.mani_grad = mgrad; io.smg = aos(MANI); io.mani_graddot = mgraddot; io.smgd = aos(MANI);
+  for (int b = 0; b < B; ++b)
+    robot_job<NV, false, F_DYN | F_STORE | F_FRAME_OUT | F_MANIP_OUT | F_GRADDOT | F_MOMA, W>(h->hm.dev, h->prm, fr, io, b);
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < ACT * ACT; ++i) { if (Mact) Mact[b * ACT * ACT + i] = c.Mact[i * B + b]; if (Minvact) Minvact[b * ACT * ACT + i] = c.Minvact[i * B + b]; }
+    for (int i = 0; i < ACT; ++i) { if (gact) gact[b * ACT + i] = c.gact[i * B + b]; if (nleact) nleact[b * ACT + i] = c.nleact[i * B + b]; }
+  }
+  return 0;
+}
+extern "C" {
+int emu_moma_state(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* Jt, double* Jtd,
+                   double* vel, double* Mact, double* Minvact, double* gact, double* nleact, double* mani, double* mgrad,
+                   double* mgraddot) {
+  const DrcModelDev& d = h->hm.dev;
+  if (d.drive_type == kNoBase) return -1;
+  if (d.nv == 12 && d.wheel_num == 2) return moma_state_t<12, 2>(h, frame_id, B, q, qd, pose, Jt, Jtd, vel, Mact, Minvact, gact, nleact, mani, mgrad, mgraddot);
+  if (d.nv == 14 && d.wheel_num == 4) return moma_state_t<14, 4>(h, frame_id, B, q, qd, pose, Jt, Jtd, vel, Mact, Minvact, gact, nleact, mani, mgrad, mgraddot);
+  return -2;
+}
+
+}  // extern "C"
+
+template <int NV, int W>
+static int moma_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                        const double* xdot_target, double* out, double* out2, int* status, int* iters) {
+  constexpr int ACT = NV - 3, MANI = NV - 3 - W;
+  const DrcModelDev& d = h->hm.dev;
+  const DrcFrame fr = make_frame(h->hm, frame_id);
+  MomaCache c(NV, ACT, B);
+  JobIO io;
+  std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.sq = aos(NV); io.qd = qd; io.sqd = aos(NV);
+  io.x_target = (mode == 1 || mode == 3) ? x_target : nullptr; io.sxt = aos(12); io.xdot_target = xdot_target; io.sxd = aos(6);
+  c.bind(io);
+  const bool ID = mode >= 2;
+  const int stride = ID ? MomaIdCfg<ACT>::STRIDE : MomaIkCfg<ACT>::STRIDE;
+  std::vector<double> rec((size_t)stride * B, 0.0);
+  io.qp = rec.data();
+  for (int b = 0; b < B; ++b) {
+    if (!ID) robot_job<NV, false, F_DYN | F_STORE | F_QPIK | F_MOMA, W>(d, h->prm, fr, io, b);
+    else robot_job<NV, false, F_DYN | F_STORE | F_QPID | F_MOMA, W>(d, h->prm, fr, io, b);
+  }
+  CollisionIO cio;
+  std::memset(&cio, 0, sizeof cio);
+  cio.B = B; cio.c_q = c.q.data(); cio.c_qd = c.qd.data(); cio.c_oMi = c.oMi.data(); cio.Bc = B;
+  cio.mode = ID ? 2 : 1; cio.qp = rec.data(); cio.qp_stride = stride;
+  cio.qp_row_off = (ID ? MomaIdCfg<ACT>::OFF_ROW : MomaIkCfg<ACT>::OFF_ROW) + (ACT + 1);
+  cio.row_n = ACT; cio.row_col0 = d.act_mani_start; cio.src0 = d.mani_start; cio.nsrc = MANI;
+  std::vector<int> flag, pr; std::vector<unsigned long long> mask; std::vector<double> ds, wt;
+  run_collision<NV, false>(h, cio, flag, mask, ds, pr, wt);
+  SolveIO sio;
+  std::memset(&sio, 0, sizeof sio);
+  sio.B = B; sio.qp = rec.data(); sio.out = out; sio.sout = aos(ACT); sio.out2 = out2; sio.sout2 = aos(ACT); sio.status = status; sio.iters = iters;
+  sio.c_g = c.gact.data(); sio.Bc = B;
+  const unsigned mani_mask = ((1u << MANI) - 1u) << d.act_mani_start;
+  if (ID) run_solve<MomaIdCfg<ACT>, true>(h, sio, mani_mask);
+  else run_solve<MomaIkCfg<ACT>, false>(h, sio, mani_mask);
+  return 0;
+}
+extern "C" {
+// mode 0 QPIK(xdot_des) 1 QPIKStep 2 QPID(xddot_des) 3 QPIDStep; out: eta* (modes 0/1) or tau* (2/3), out2: eta_dot* (2/3)
+int emu_moma_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                   const double* xdot_target, double* out, double* out2, int* status, int* iters) {
+  const DrcModelDev& d = h->hm.dev;
+  if (d.drive_type == kNoBase) return -1;
+  if (d.nv == 12 && d.wheel_num == 2) return moma_cycle_t<12, 2>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, out2, status, iters);
+  if (d.nv == 14 && d.wheel_num == 4) return moma_cycle_t<14, 4>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, out2, status, iters);
+  return -2;
+}
+
 }  // extern "C"

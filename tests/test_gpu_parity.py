@@ -248,9 +248,12 @@ def test_reference_api_mirror(oracle):
     ref3 = oracle.cycle(3, q, qd, x_t, xdot_t, f)
     same = rc.last_iters == ref3["iters"]
     assert np.abs(tau - ref3["out"])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out"]).max())
-    # QPIK_cubic at t >= t0 + duration tracks the target itself
+    # QPIK_cubic == getTaskSpaceCubic + QPIKStep (robot_controller.cpp:303-317)
     x0 = rd.get_pose(LINK)
-    out2 = rc.QPIK_cubic(c_oracle.pose44(x_t), xdot_t, x0, np.zeros((64, 6)), 2.0, 0.0, 1.0, LINK)
-    assert np.abs(out2 - out).max() < 1e-9
+    out2 = rc.QPIK_cubic(c_oracle.pose44(x_t), xdot_t, x0, np.zeros((64, 6)), 0.4, 0.0, 1.0, LINK)
+    x_des, xd_des = rd._ctx.task_space_cubic(c_oracle.pose44(x_t), xdot_t, x0, np.zeros((64, 6)), 0.4, 0.0, 1.0)
+    ref4 = oracle.cycle(1, q, qd, x_des, xd_des, f)
+    same = rc.last_iters == ref4["iters"]
+    assert same.mean() > 0.95 and np.abs(out2 - ref4["out"])[same].max() < 1e-4
     with pytest.raises(RuntimeError):
         rc.set_task_gain(np.ones(5), np.ones(6))
