@@ -36,7 +36,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "batched QP-IK control cycles/sec (FR3, batch 65536)"
+METRIC = "batched QP-IK control cycles/sec (FR3, batch 65536)"  # metric name of the default workload; others append theirs
 UNIT = "cycles/s"
 LINK = "fr3_link8"
 # Algorithmic fp64 flop model of the structured ADMM kernel for FR3 QPIK (NC=7, KU=2, ND=2; FMA = 2 flops),
@@ -44,6 +44,49 @@ LINK = "fr3_link8"
 # and the one-off Ruiz scaling.
 FLOPS_ITER, FLOPS_CHECK, FLOPS_FACTOR, FLOPS_SCALE = 867.0, 1450.0, 1900.0, 4300.0
 BYTES_PER_CYCLE = 320.0  # q, qdot, x_target(12), xdot_target in; qdot*, status, iters out
+
+
+# ---- workloads: "fr3_qpik" is BASELINE.json's metric (config 1 at the headline batch); the others are the sibling configs
+# (3: fr3_qpid, 4: husky_*, 5: xls_*) for `--workload`, never the default line.
+WORKLOADS = {
+    "fr3_qpik": dict(robot="fr3", kind="ik", desc="FR3 updateState+QPIKStep (QP 23 vars / 39 rows, OSQP algorithm, self-collision + manipulability rows)"),
+    "fr3_qpid": dict(robot="fr3", kind="id", desc="FR3 updateState+QPIDStep (QP 44 vars / 81 rows)"),
+    "husky_qpik": dict(robot="husky_fr3", kind="ik", desc="Husky-FR3 (diff drive, synthesized URDF) whole-body updateState+QPIKStep (9 vars / 25 rows)"),
+    "husky_qpid": dict(robot="husky_fr3", kind="id", desc="Husky-FR3 whole-body updateState+QPIDStep (18 vars / 39 rows)"),
+    "xls_qpik": dict(robot="xls_fr3", kind="ik", desc="XLS-FR3 (mecanum, synthesized URDF) whole-body updateState+QPIKStep (11 vars / 27 rows)"),
+    "xls_qpid": dict(robot="xls_fr3", kind="id", desc="XLS-FR3 whole-body updateState+QPIDStep (22 vars / 41 rows)"),
+}
+MOMA_DESC = {
+    "husky_fr3": dict(kin=dict(type="Differential", wheel_radius=0.1651, base_width=0.555), w=2,
+                      joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=5), actuator_idx=dict(mobi_start=0, mani_start=2)),
+    "xls_fr3": dict(kin=dict(type="Mecanum", wheel_radius=0.120, roller_angles=[-np.pi / 4, np.pi / 4, np.pi / 4, -np.pi / 4],
+                             base2wheel_positions=[(0.2225, 0.2045), (0.2225, -0.2045), (-0.2225, 0.2045), (-0.2225, -0.2045)],
+                             base2wheel_angles=[0.0] * 4), w=4,
+                    joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=7), actuator_idx=dict(mobi_start=0, mani_start=4)),
+}
+
+
+def robot_paths(robot):
+    import dyros_robot_controller_b200 as drc
+    d = Path(drc.FR3_URDF).parents[1] / robot
+    return str(d / f"{robot}.urdf"), str(d / f"{robot}.srdf")
+
+
+def make_moma_workload(lo, hi, vl, w, B, seed):
+    """base pose U([-2,2]^2 x [-pi,pi]), wheel angles U(-pi,pi), wheel speeds U(-2,2), arm as config 1."""
+    rng = np.random.default_rng(seed)
+    n = len(lo)
+    al, ah, av = lo[3 + w:], hi[3 + w:], vl[3 + w:]
+    q, qd = np.zeros((B, n)), np.zeros((B, n))
+    q[:, 0:2] = rng.uniform(-2, 2, (B, 2)); q[:, 2] = rng.uniform(-np.pi, np.pi, B)
+    q[:, 3:3 + w] = rng.uniform(-np.pi, np.pi, (B, w))
+    q[:, 3 + w:] = al + (0.1 + 0.8 * rng.random((B, n - 3 - w))) * (ah - al)
+    qd[:, 3:3 + w] = rng.uniform(-2, 2, (B, w))
+    qd[:, 3 + w:] = rng.uniform(-0.5, 0.5, (B, n - 3 - w)) * av
+    q_t = q.copy()
+    q_t[:, 3 + w:] += 0.05 * rng.normal(size=(B, n - 3 - w))
+    q_t[:, 0:2] += 0.05 * rng.normal(size=(B, 2))
+    return q, qd, q_t, 0.05 * rng.normal(size=(B, 6))
 
 
 def make_workload(model, B: int, seed: int):
@@ -139,21 +182,32 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
-def oracle_cycles_per_s(B: int, threads: int, seed: int = 0, passes: int = 1):
-    """Time the CPU restatement (oracle port) on `threads` host threads."""
-    from oracle.c_oracle import Oracle
-    import dyros_robot_controller_b200 as drc
-    o = Oracle(drc.FR3_URDF, drc.FR3_SRDF, threads=threads)
-    f = o.frame_id(LINK)
+def oracle_cycles_per_s(B: int, threads: int, seed: int = 0, passes: int = 1, workload: str = "fr3_qpik"):
+    """Time the CPU restatement (oracle port) of the workload on `threads` host threads."""
+    from oracle.c_oracle import MomaOracle, Oracle
+    wl = WORKLOADS[workload]
+    urdf, srdf = robot_paths(wl["robot"])
+    if wl["robot"] == "fr3":
+        o = Oracle(urdf, srdf, threads=threads)
+        f = o.frame_id(LINK)
 
-    class M:  # the oracle's own model view, same fields as engine.Model
-        dof, q_lower, q_upper, v_limit = o.nv, o.model.q_lo, o.model.q_hi, o.model.v_lim
-    q, qd, q_t, xdot_t = make_workload(M, B, seed)
+        class M:  # the oracle's own model view, same fields as engine.Model
+            dof, q_lower, q_upper, v_limit = o.nv, o.model.q_lo, o.model.q_hi, o.model.v_lim
+        q, qd, q_t, xdot_t = make_workload(M, B, seed)
+        mode = 1 if wl["kind"] == "ik" else 3
+        run = lambda *a: o.cycle(mode, *a, f)
+    else:
+        md = MOMA_DESC[wl["robot"]]
+        o = MomaOracle(urdf, srdf, md["kin"], md["joint_idx"], md["actuator_idx"], threads=threads)
+        f = o.frame_id(LINK)
+        q, qd, q_t, xdot_t = make_moma_workload(o.model.q_lo, o.model.q_hi, o.model.v_lim, md["w"], B, seed)
+        mode = 1 if wl["kind"] == "ik" else 3
+        run = lambda *a: o.moma_cycle(mode, *a, f)
     x_t = o.update_state(q_t, qd, f)["pose"]
-    o.cycle(1, q[:256], qd[:256], x_t[:256], xdot_t[:256], f)  # warm-up
+    run(q[:256], qd[:256], x_t[:256], xdot_t[:256])  # warm-up
     t0 = time.perf_counter()
     for _ in range(passes):
-        r = o.cycle(1, q, qd, x_t, xdot_t, f)
+        r = run(q, qd, x_t, xdot_t)
     dt = time.perf_counter() - t0
     return B * passes / dt, dt / passes, r
 
@@ -166,15 +220,15 @@ def run_reference(args):
     sample = 8192
     times = []
     for i in range(args.warmup + args.steps):
-        cps, dt, _ = oracle_cycles_per_s(sample, threads, seed=i)
+        cps, dt, _ = oracle_cycles_per_s(sample, threads, seed=i, workload=args.workload)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC if args.workload == "fr3_qpik" else f"batched control cycles/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "FR3 updateState+QPIKStep (QP 23 vars / 39 rows), CPU oracle port of Pinocchio+OSQP path",
+            "config": {"workload": WORKLOADS[args.workload]["desc"] + " -- CPU oracle port of the Pinocchio+OSQP path",
                        "batch_per_step": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample} cycles per step, OpenMP over all {threads} host threads"},
@@ -198,20 +252,42 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B = args.batch
-    model = drc.Model(drc.FR3_URDF, drc.FR3_SRDF)
+    wl = WORKLOADS[args.workload]
+    urdf, srdf = robot_paths(wl["robot"])
+    model = drc.Model(urdf, srdf)
+    moma = wl["robot"] != "fr3"
+    if moma:
+        md = MOMA_DESC[wl["robot"]]
+        model.attach_mobile_base(md["kin"], md["joint_idx"], md["actuator_idx"])
     ctx = drc.Context(model, B, device=local)
     # each rank owns an independent shard of the batch (no exchange on the solve path)
-    q, qd, q_t, xdot_t = make_workload(model, B, seed=1000 * rank)
-    ctx.update_state(q_t, qd)
-    x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+    if moma:
+        q, qd, q_t, xdot_t = make_moma_workload(model.q_lower, model.q_upper, model.v_limit, md["w"], B, seed=1000 * rank)
+        ctx.moma_update_state(q_t, qd)
+        x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
+        nout = model.actuated_dof
+    else:
+        q, qd, q_t, xdot_t = make_workload(model, B, seed=1000 * rank)
+        ctx.update_state(q_t, qd)
+        x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+        nout = model.dof
     tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xdot_t))
-    out = torch.empty((B, model.dof), dtype=torch.float64, device=dev)
+    out = torch.empty((B, nout), dtype=torch.float64, device=dev)
+    out2 = torch.empty((B, nout), dtype=torch.float64, device=dev)
     st = torch.empty(B, dtype=torch.int32, device=dev)
     it = torch.empty(B, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    def cycle(a_q, a_qd, a_xt, a_xd, o_out, o_st, o_it, o_out2=None):
+        if moma:
+            ctx.moma_cycle(wl["kind"], a_q, a_qd, a_xt, a_xd, LINK, out=o_out, out2=o_out2, status=o_st, iters=o_it)
+        elif wl["kind"] == "ik":
+            ctx.cycle_qpik_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
+        else:
+            ctx.cycle_qpid_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
+
     def step():
-        ctx.cycle_qpik_step(tq, tqd, txt, txd, LINK, out=out, status=st, iters=it)
+        cycle(tq, tqd, txt, txd, out, st, it, out2)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -248,17 +324,18 @@ def run_ours(args):
 
     # ---- e2e through the host-buffer C-ABI call (pinned host memory in, host memory out)
     hq, hqd, hxt, hxd = (torch.from_numpy(a).pin_memory().numpy() for a in (q, qd, x_t, xdot_t))
-    hout = torch.empty((B, model.dof), dtype=torch.float64).pin_memory().numpy()
+    hout = torch.empty((B, nout), dtype=torch.float64).pin_memory().numpy()
+    hout2 = torch.empty((B, nout), dtype=torch.float64).pin_memory().numpy()
     hst = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
     hit = torch.empty(B, dtype=torch.int32).pin_memory().numpy()
     ctx.enable_timing(False)
     for _ in range(2):
-        ctx.cycle_qpik_step(hq, hqd, hxt, hxd, LINK, out=hout, status=hst, iters=hit)
+        cycle(hq, hqd, hxt, hxd, hout, hst, hit, hout2)
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ctx.cycle_qpik_step(hq, hqd, hxt, hxd, LINK, out=hout, status=hst, iters=hit)
+        cycle(hq, hqd, hxt, hxd, hout, hst, hit, hout2)
     e2e_s = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -266,7 +343,7 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * B * args.steps / e2e_s
     h2d = B * (model.dof * 2 + 12 + 6) * 8
-    d2h = B * (model.dof * 8 + 4 + 4)
+    d2h = B * (nout * 8 * (2 if (moma and wl['kind'] == 'id') else 1) + 4 + 4)
 
     if rank != 0:
         if dist is not None:
@@ -286,7 +363,7 @@ def run_ours(args):
         peak_src = "measured in-run by drc_bench_fp64_peak (FP64 FMA, 8 chains/thread)"
     except Exception as e:  # pragma: no cover
         peak, peak_src = 37.0, f"fallback nominal B200 FP64 ({e})"
-    achieved = flops / (admm_ms * 1e-3) / 1e12
+    achieved = flops / (admm_ms * 1e-3) / 1e12 if args.workload == "fr3_qpik" else None  # flop model exists for the metric's QP only
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -294,8 +371,9 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_achieved = BYTES_PER_CYCLE * B / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "k_admm<QpCfg<7,2,2,0>>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "fp64", "kernel": "k_admm" + ("<QpCfg<7,2,2,0>>" if args.workload == "fr3_qpik" else ""), "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved is not None else None, "traffic": None,
+                "peak_source": peak_src,
                 "kernel_ms": admm_ms, "kernel_share_of_step": admm_ms / ms_per_step,
                 "stage_ms": {"state_and_qp_build": build_ms, "self_collision": col_ms, "admm": admm_ms},
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
@@ -303,12 +381,11 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
     sample = min(B, 32768)
-    cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores, workload=args.workload)
+    line = {"metric": METRIC if args.workload == "fr3_qpik" else f"batched control cycles/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "FR3 updateState+QPIKStep (QP 23 vars / 39 rows, OSQP algorithm, self-collision + "
-                                   "manipulability rows)", "batch_per_gpu": B, "global_batch": world * B,
+            "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": world * B,
                        "parallelism": f"batch shard x{world}, no collective on the solve path",
                        "l2": "256 MiB buffer zeroed between timed steps", "seed": "default_rng(1000*rank)"},
             "clocks": clocks,
@@ -331,6 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=65536, help="robots per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fr3_qpik", choices=sorted(WORKLOADS), help="default = BASELINE.json's metric")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

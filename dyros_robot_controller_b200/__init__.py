@@ -13,4 +13,7 @@ from .engine import Context, Model, device_count, fp64_peak_tflops, pose12, pose
 ROBOTS_DIR = Path(__file__).resolve().parent / "robots"
 FR3_URDF = str(ROBOTS_DIR / "fr3" / "fr3.urdf")
 FR3_SRDF = str(ROBOTS_DIR / "fr3" / "fr3.srdf")
+# synthesized mobile manipulators of BASELINE configs 4-5 (tools/make_moma_urdf.py; NOT from the reference)
+HUSKY_FR3_URDF, HUSKY_FR3_SRDF = str(ROBOTS_DIR / "husky_fr3" / "husky_fr3.urdf"), str(ROBOTS_DIR / "husky_fr3" / "husky_fr3.srdf")
+XLS_FR3_URDF, XLS_FR3_SRDF = str(ROBOTS_DIR / "xls_fr3" / "xls_fr3.urdf"), str(ROBOTS_DIR / "xls_fr3" / "xls_fr3.srdf")
 __version__ = "0.1.0"

@@ -16,9 +16,9 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libdrc_b200.so"
-SOURCES = [CSRC / "drc_lib.cu", CSRC / "model.cpp"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-              "-Xcompiler", "-fPIC"]
+SOURCES = [CSRC / "drc_lib.cu", CSRC / "drc_moma.cu", CSRC / "model.cpp"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJDIR = PKG / "build"
 
 
 def _nvcc() -> str:
@@ -49,21 +49,35 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every translation unit for sm_100a (in parallel), link libdrc_b200.so in-tree."""
     if not force and not stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-        print(" ".join(cmd), flush=True)
+    from concurrent.futures import ThreadPoolExecutor
+    src_hash = _source_hash()   # of the sources as they are NOW (edits made while nvcc runs must leave the library stale)
     env = dict(os.environ)
     # the environment's CC/CXX wrappers are not nvcc host compilers; use the system gcc
     env.pop("CC", None), env.pop("CXX", None)
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    OBJDIR.mkdir(exist_ok=True)
+
+    def compile_one(src: Path) -> Path:
+        obj = OBJDIR / (src.stem + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src.name}:\n" + r.stdout + r.stderr)
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(LIB), *map(str, objs)],
+                       capture_output=True, text=True, env=env)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
-    HASH.write_text(_source_hash())
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
+    HASH.write_text(src_hash)
     return LIB
 
 

@@ -10,10 +10,10 @@
 
 #if defined(__CUDACC__)
 #define DRC_HD __host__ __device__ __forceinline__
-#define DRC_HD_NOINLINE __host__ __device__ __noinline__
+#define DRC_HD_NOINLINE static __host__ __device__ __noinline__  // static: one private copy per translation unit
 #else
 #define DRC_HD inline
-#define DRC_HD_NOINLINE inline
+#define DRC_HD_NOINLINE static inline
 #endif
 
 namespace drc {

@@ -603,6 +603,7 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
   BestPair best;
   best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
   unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair whose bound beats the best exact distance so far
+  float lbs[64];                   // its certified lower bound (rounded DOWN to float: still a lower bound)
   int gi = 0;
   for (int grp = 0; grp < m.ngroup; ++grp) {
     const int ja = m.group_ja[grp], jb = m.group_jb[grp];
@@ -617,17 +618,32 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
         const PairResult r = closed_form_distance(A, Bp);
         consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
       } else {
-        if (pair_lower_bound(A, Bp) <= best.d) cand |= 1ull << gi;
+        const double lb = pair_lower_bound(A, Bp);
+        if (lb <= best.d) cand |= 1ull << gi;
+        float lf = (float)lb;
+        if ((double)lf > lb) lf = lf - fabsf(lf) * 1.2e-7f - 1e-30f;
+        lbs[gi] = lf;
         ++gi;
       }
     }
   }
-  // GJK pass: every thread walks its own candidate list (bounds re-tested against the improving best)
+  // GJK pass, best first: every thread resolves ITS most promising candidate (smallest lower bound) first, so that
+  // the improving minimum culls most of the others before they cost a GJK run (and the warp's lanes stay in step)
   unsigned long long deferred = 0ull;
   while (cand) {
-    int bit = 0;
-    while (!((cand >> bit) & 1ull)) ++bit;
-    cand &= cand - 1ull;
+    int bit = -1;
+    float blb = 3.0e38f;
+    for (unsigned long long rem = cand; rem; rem &= rem - 1ull) {
+#if defined(__CUDA_ARCH__)
+      const int i = __ffsll((long long)rem) - 1;
+#else
+      int i = 0;
+      while (!((rem >> i) & 1ull)) ++i;
+#endif
+      if (lbs[i] < blb) { blb = lbs[i]; bit = i; }
+    }
+    if ((double)blb > best.d) break;  // no remaining candidate can win (ties are resolved by the exact re-test below)
+    cand &= ~(1ull << bit);
     const int k = m.gjk_pair[bit];
     const int ga = G.pair_a[k], gb = G.pair_b[k];
     const int ja = G.parent[ga], jb = G.parent[gb];

@@ -1,0 +1,191 @@
+// drc_b200 -- host-side internals shared by the translation units of libdrc_b200.so: the opaque handle types of the C
+// ABI, launch helpers and the host staging used by the drc_host_* entry points.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/drc_b200.h"
+#include "drc_kernels.cuh"
+#include "model.h"
+
+using namespace drc;
+using namespace drc_kernels;
+
+// error channel of the C ABI (drc_last_error); defined in drc_lib.cu
+int drc_set_error(int code, const std::string& msg);
+static inline int fail(int code, const std::string& msg) { return drc_set_error(code, msg); }
+#define CU(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) return fail(DRC_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct drc_model {
+  HostModel hm;
+  std::string verbose;
+};
+
+struct drc_ctx {
+  const drc_model* model;
+  int device, cap;
+  DrcParams prm;
+  cudaStream_t stream;
+  // state cache (SoA, stride cap)
+  double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
+  double *c_Mact, *c_Minvact, *c_gact, *c_nleact;  // mobile manipulator only (actuated-space dynamics)
+  // QP + collision scratch
+  double* qp;
+  int qp_stride_max;
+  int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
+  int* epa_list; int* epa_count;
+  int sm_count;
+  // device staging for host entry points
+  double* stage; size_t stage_doubles;
+  int* stage_i; size_t stage_ints;
+  long long launches;
+  bool timing;
+  cudaEvent_t ev[4];
+  float last_ms[4];
+};
+
+static DrcFrame frame_of(const drc_model* m, int fid) {
+  DrcFrame f;
+  const HostFrame& hf = m->hm.frames[fid];
+  f.parent = hf.parent;
+  std::memcpy(f.R, hf.R, sizeof f.R);
+  std::memcpy(f.p, hf.p, sizeof f.p);
+  return f;
+}
+static Strided lay(int layout, int K, int B) { return layout == DRC_LAYOUT_SOA ? soa(B) : aos(K); }
+
+static void bind_cache(const drc_ctx* c, JobIO& io) {
+  io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.c_M = c->c_M; io.c_Minv = c->c_Minv; io.c_g = c->c_g;
+  io.c_nle = c->c_nle; io.Bc = c->cap;
+  io.c_Mact = c->c_Mact; io.c_Minvact = c->c_Minvact; io.c_gact = c->c_gact; io.c_nleact = c->c_nleact;
+}
+
+// dispatch on the compile-time robot shape; extend the list to add robots
+#define DRC_DISPATCH_NV(nv, chain, CALL)                                         \
+  if ((nv) == 7 && (chain)) { constexpr int NV = 7; constexpr bool CHAIN = true; CALL; } \
+  else return fail(DRC_E_UNSUPPORTED, "no kernel instantiation for this robot (dof / topology)");
+
+template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
+static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
+  static const int threads = [] { const char* e = getenv("DRC_JOB_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 128 ? t : 64; }();
+  const int blocks = (io.B + threads - 1) / threads;
+  k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
+  c->launches++;
+  CU(cudaGetLastError());
+  return DRC_OK;
+}
+
+template <int NV, bool CHAIN>
+static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s) {
+  io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.Bc = c->cap;
+  io.epa_flag = c->epa_flag; io.cand_mask = c->cand_mask; io.epa_list = c->epa_list; io.epa_count = c->epa_count;
+  CU(cudaMemsetAsync(c->epa_count, 0, sizeof(int), s));
+  if (!io.dist) io.dist = c->col_dist;
+  if (!io.pair_out) io.pair_out = c->col_pair;
+  if (!io.witness) io.witness = c->col_wit;
+  static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 128; return t >= 32 && t <= 128 ? t : 128; }();
+  const int blocks = (io.B + threads - 1) / threads;
+  k_collision<NV, CHAIN><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  CU(cudaGetLastError());
+  k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, s>>>(c->model->hm.dev, c->prm, io);
+  CU(cudaGetLastError());
+  c->launches += 2;
+  return DRC_OK;
+}
+
+template <class Cfg, bool ID>
+static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask = (1u << Cfg::NC) - 1u, const double* gravity = nullptr) {
+  io.qp = c->qp; io.c_g = gravity ? gravity : c->c_g; io.Bc = c->cap;
+  const QpOptions o = qp_options(c->prm, unit_mask);
+  const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
+  // blocks/SM the kernel is compiled for (register cap 65536 / (128 * MINB)); tunable for experiments
+  static const int minb = [] { const char* e = getenv("DRC_ADMM_MINB"); return e ? atoi(e) : 3; }();
+  constexpr size_t smem = sizeof(GroupShared<Cfg>) * kAdmmWarps * Cfg::NG;
+  static const cudaError_t attr = [] {
+    cudaError_t e1 = cudaFuncSetAttribute(k_admm<Cfg, ID, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e2 = cudaFuncSetAttribute(k_admm<Cfg, ID, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e3 = cudaFuncSetAttribute(k_admm<Cfg, ID, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  }();
+  CU(attr);
+  if (minb <= 2) k_admm<Cfg, ID, 2><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  else if (minb == 3) k_admm<Cfg, ID, 3><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  else k_admm<Cfg, ID, 4><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  c->launches++;
+  CU(cudaGetLastError());
+  return DRC_OK;
+}
+
+static int check_batch(const drc_ctx* c, int B) {
+  if (!c) return fail(DRC_E_INVALID, "null context");
+  if (B <= 0 || B > c->cap) return fail(DRC_E_INVALID, "batch size out of range for this context");
+  return DRC_OK;
+}
+static int check_frame(const drc_ctx* c, int frame) {
+  if (frame < 0 || frame >= (int)c->model->hm.frames.size()) return fail(DRC_E_INVALID, "unknown frame id");
+  return DRC_OK;
+}
+static cudaStream_t pick(drc_ctx* c, void* s) { return s ? (cudaStream_t)s : c->stream; }
+
+
+// ------------------------------------------------------------------------------------------------ host entry points
+// Carve device staging buffers, copy inputs H2D on the context stream, run the device entry point, copy back.
+struct Stage {
+  drc_ctx* c;
+  size_t used = 0, used_i = 0;
+  struct Out { void* host; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  int err = DRC_OK;
+  explicit Stage(drc_ctx* ctx) : c(ctx) {}
+  double* in(const double* h, size_t cnt) {
+    if (!h) return nullptr;
+    double* d = take(cnt);
+    if (d && cudaMemcpyAsync(d, h, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) err = DRC_E_CUDA;
+    return d;
+  }
+  double* out(double* h, size_t cnt) {
+    if (!h) return nullptr;
+    double* d = take(cnt);
+    if (d) outs.push_back({h, d, cnt * sizeof(double)});
+    return d;
+  }
+  int* out_i(int* h, size_t cnt) {
+    if (!h) return nullptr;
+    if (used_i + cnt > c->stage_ints) { err = DRC_E_NOMEM; return nullptr; }
+    int* d = c->stage_i + used_i;
+    used_i += cnt;
+    outs.push_back({h, d, cnt * sizeof(int)});
+    return d;
+  }
+  double* take(size_t cnt) {
+    if (used + cnt > c->stage_doubles) { err = DRC_E_NOMEM; return nullptr; }
+    double* d = c->stage + used;
+    used += cnt;
+    return d;
+  }
+  int finish(int rc) {
+    if (err) return fail(err, "host staging failed (buffer too small or copy error)");
+    if (rc) return rc;
+    for (auto& o : outs)
+      if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return fail(DRC_E_CUDA, "D2H copy failed");
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(DRC_E_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(e));
+    return DRC_OK;
+  }
+};
+#define HOST_PRELUDE                                   \
+  int rc0 = check_batch(c, B); if (rc0) return rc0;    \
+  CU(cudaSetDevice(c->device));                        \
+  const int n = c->model->hm.dev.nv; (void)n;          \
+  const size_t Bz = (size_t)B; (void)Bz;               \
+  Stage st(c);
+

@@ -1,0 +1,331 @@
+// drc_b200 -- CUDA kernels (sm_100a).  Included by every translation unit of libdrc_b200.so that launches them
+// (drc_lib.cu: manipulator path + C ABI core, drc_moma.cu: mobile-manipulator path); each unit instantiates the
+// robot shapes it dispatches on.
+//
+// Kernels (one launch each, all fp64):
+//   k_robot_job<NV,CHAIN,FLAGS,W> one robot per thread: state update, frame quantities, QP records
+//   k_collision / k_collision_epa one robot per thread / one warp per flagged robot: min self-distance, gradients, QP row
+//   k_admm<Cfg,ID,MINB>           GL lanes per robot (NG robots per warp): OSQP-algorithm ADMM
+//   k_task_cubic                  one robot per thread: cubic task-space trajectory
+//   k_copy_cache                  cache (SoA) -> user layout
+// The robot model travels as a __grid_constant__ kernel parameter (constant bank, broadcast reads).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "drc_cycle.h"
+
+namespace drc_kernels {
+using namespace drc;
+
+template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
+__global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+                                                    const __grid_constant__ DrcFrame frame, const __grid_constant__ JobIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < io.B) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
+}
+
+template <int NV, bool CHAIN>
+__global__ void __launch_bounds__(128) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+                                                    const __grid_constant__ CollisionIO io) {
+  // stage the geometry table in shared memory: the GJK pass indexes it with per-thread pair ids
+  __shared__ GeomTable G;
+  {
+    const int* src = reinterpret_cast<const int*>(&m.geom);
+    int* dst = reinterpret_cast<int*>(&G);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeomTable) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < io.B) collision_job<NV, CHAIN>(m, G, prm, io, b);
+}
+// ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar
+// epa_penetration (drc_geom.h: flood-fill horizon, uncommitted bad expansions, slot policy); the polytope lives in
+// shared memory and the three face scans (closest face, neighbour across an edge, new faces) are spread over the
+// lanes.  Control flow and the small flood-fill state are warp-uniform: every lane runs the same sequence.
+struct EpaWarpSmem {
+  SimplexVert P[kEpaMaxVert];
+  double fd[kEpaMaxFace];
+  double fn[kEpaMaxFace][3];
+  short fv[kEpaMaxFace][3];
+  unsigned char mark[kEpaMaxFace];
+  short edge[kEpaMaxEdge][2];
+  short killed[kEpaMaxEdge];
+  short stack[kEpaMaxEdge];
+};
+static __device__ __forceinline__ void epa_make_face(EpaWarpSmem& S, int slot, int a, int b, int c) {
+  const Vec3 nrm = cross(S.P[b].w - S.P[a].w, S.P[c].w - S.P[a].w);
+  const double l = norm(nrm);
+  const Vec3 n = l > 0 ? (1.0 / l) * nrm : v3(0, 0, 1);
+  S.fv[slot][0] = (short)a; S.fv[slot][1] = (short)b; S.fv[slot][2] = (short)c;
+  S.fn[slot][0] = n.x; S.fn[slot][1] = n.y; S.fn[slot][2] = n.z;
+  S.fd[slot] = dot(n, S.P[a].w);
+}
+static __device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, const GjkOut& g, double tol, int max_iter, PairResult& out,
+                         int lane) {
+  const unsigned full = 0xffffffffu;
+  auto sup = [&](Vec3 d) { SimplexVert s; s.a = support(A, d); s.b = support(B, -d); s.w = s.a - s.b; return s; };
+  SimplexVert T[4];
+  int np = epa_seed(sup, g, T);  // warp-uniform, every lane on its private copy
+  out.d = 0; out.pa = g.pa; out.pb = g.pb;
+  if (np < 4) return;
+  __syncwarp();
+  if (lane < 4) S.P[lane] = T[lane];
+  __syncwarp();
+  if (lane == 0) epa_make_face(S, 0, 0, 1, 2);
+  if (lane == 1) epa_make_face(S, 1, 0, 3, 1);
+  if (lane == 2) epa_make_face(S, 2, 0, 2, 3);
+  if (lane == 3) epa_make_face(S, 3, 1, 3, 2);
+  int nf = 4;
+  __syncwarp();
+  int bestf = -1;
+  for (int it = 0; it < max_iter; ++it) {
+    // closest face to the origin (ties: smallest index); every slot below nf holds a live face
+    double bd = 1e300;
+    int bf = -1;
+    for (int f = lane; f < nf; f += 32)
+      if (S.fd[f] < bd) { bd = S.fd[f]; bf = f; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(full, bd, off);
+      const int of = __shfl_xor_sync(full, bf, off);
+      if (of >= 0 && (bf < 0 || od < bd || (od == bd && of < bf))) { bd = od; bf = of; }
+    }
+    bestf = bf;
+    if (bf < 0) break;
+    const Vec3 n = v3(S.fn[bf][0], S.fn[bf][1], S.fn[bf][2]);
+    const SimplexVert s = sup(n);
+    if (dot(n, s.w) - S.fd[bf] <= tol) break;
+    if (np >= kEpaMaxVert) break;
+    // flood fill of the faces visible from s (uniform control flow; lanes share the neighbour search)
+    for (int f = lane; f < nf; f += 32) S.mark[f] = 0;
+    __syncwarp();
+    int nk = 0, ne = 0, sp = 0;
+    bool bad = false;
+    if (lane == 0) { S.mark[bf] = 1; S.killed[0] = (short)bf; S.stack[0] = (short)bf; }
+    nk = 1; sp = 1;
+    __syncwarp();
+    while (sp > 0 && !bad) {
+      const int f = S.stack[--sp];
+      for (int e = 0; e < 3 && !bad; ++e) {
+        const short a = S.fv[f][e], b = S.fv[f][(e + 1) % 3];
+        int gn = -1;
+        for (int base = 0; base < nf && gn < 0; base += 32) {
+          const int i = base + lane;
+          bool hit = false;
+          if (i < nf) {
+            const short v0 = S.fv[i][0], v1 = S.fv[i][1], v2 = S.fv[i][2];
+            hit = (v0 == b && v1 == a) || (v1 == b && v2 == a) || (v2 == b && v0 == a);
+          }
+          const unsigned mk = __ballot_sync(full, hit);
+          if (mk) gn = base + __ffs(mk) - 1;
+        }
+        if (gn < 0) { bad = true; break; }
+        const int mg = S.mark[gn];
+        if (mg == 1) continue;
+        if (mg == 0) {
+          const Vec3 p0 = S.P[S.fv[gn][0]].w;
+          const bool vis = S.fn[gn][0] * (s.w.x - p0.x) + S.fn[gn][1] * (s.w.y - p0.y) + S.fn[gn][2] * (s.w.z - p0.z) > kEpaVisEps;
+          __syncwarp();
+          if (lane == 0) S.mark[gn] = vis ? 1 : 2;
+          if (vis) {
+            if (nk >= kEpaMaxEdge - 2) { bad = true; break; }
+            if (lane == 0) { S.killed[nk] = (short)gn; S.stack[sp] = (short)gn; }
+            ++nk; ++sp;
+            __syncwarp();
+            continue;
+          }
+          __syncwarp();
+        }
+        if (ne >= kEpaMaxEdge) { bad = true; break; }
+        if (lane == 0) { S.edge[ne][0] = a; S.edge[ne][1] = b; }
+        ++ne;
+      }
+    }
+    __syncwarp();
+    if (bad || ne != nk + 2 || nf + 2 > kEpaMaxFace) break;
+    for (int base = 0; base < ne; base += 32) {
+      const int k = base + lane;
+      bool deg = false;
+      if (k < ne) {
+        const Vec3 pa = S.P[S.edge[k][0]].w;
+        deg = norm2(cross(S.P[S.edge[k][1]].w - pa, s.w - pa)) <= kEpaMinArea2;
+      }
+      if (__any_sync(full, deg)) bad = true;
+    }
+    if (bad) break;
+    // commit: the new vertex, then one new face per horizon edge
+    const int idx = np++;
+    if (lane == 0) S.P[idx] = s;
+    __syncwarp();
+    for (int k = lane; k < ne; k += 32) epa_make_face(S, k < nk ? (int)S.killed[k] : nf + (k - nk), S.edge[k][0], S.edge[k][1], idx);
+    nf += 2;
+    __syncwarp();
+  }
+  if (bestf < 0) return;
+  epa_witness(S.P[S.fv[bestf][0]], S.P[S.fv[bestf][1]], S.P[S.fv[bestf][2]], v3(S.fn[bestf][0], S.fn[bestf][1], S.fn[bestf][2]),
+              S.fd[bestf], out);
+  __syncwarp();
+}
+
+constexpr int kEpaWarps = 2;
+template <int NV, bool CHAIN>
+__global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+                                                                   const __grid_constant__ CollisionIO io) {
+  __shared__ EpaWarpSmem sm[kEpaWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  EpaWarpSmem& S = sm[warp];
+  const int count = *io.epa_count;
+  for (int i = blockIdx.x * kEpaWarps + warp; i < count; i += gridDim.x * kEpaWarps) {
+    const int b = io.epa_list[i];
+    unsigned long long deferred = io.cand_mask[b];
+    BestPair best;
+    best.d = io.dist[b]; best.id = io.pair_out[b];
+    best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
+    best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
+    best.ja = -1; best.jb = -1;
+    for (int k = 0; k < m.npair; ++k)
+      if (m.geom.pair_id[k] == best.id) { best.ja = m.geom.parent[m.geom.pair_a[k]]; best.jb = m.geom.parent[m.geom.pair_b[k]]; }
+    while (deferred) {
+      const int bit = __ffsll((long long)deferred) - 1;
+      deferred &= deferred - 1ull;
+      const int k = m.gjk_pair[bit];
+      const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
+      const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
+      const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+      const Mat3 Rab = tmul(FA.R, FB.R);
+      const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+      const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
+      GjkOut g;
+      gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+      PairResult r;
+      r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+      if (g.intersect) epa_warp(S, A, Bp, g, prm.epa_tol, prm.epa_max_iter, r, lane);
+      consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
+    }
+    __syncwarp();
+    if (lane == 0) collision_finish<NV, CHAIN>(m, prm, io, b, best);
+    __syncwarp();
+  }
+}
+
+constexpr int kAdmmWarps = 1;  // one warp per block: a finished warp frees its slot without waiting for block-mates
+template <class Cfg, bool ID, int MINB>
+__global__ void __launch_bounds__(kAdmmWarps * 32, 4 * MINB) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
+  extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
+  GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = (blockIdx.x * kAdmmWarps + warp) * Cfg::NG;
+  if (first >= io.B) return;  // no block-level barrier below: idle warps may leave
+  int robots[Cfg::NG];
+#pragma unroll
+  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < io.B ? first + g : -1;
+  WarpExec<Cfg> w;
+  w.sh = sh + warp * Cfg::NG;
+  w.lane = lane;
+  lane_assign<Cfg>(w.L, lane);
+  solve_and_emit<Cfg, ID>(w, robots, io, o);
+}
+
+// DyrosMath::getTaskSpaceCubic (math_type_define.h:62-144,235-281,647-685); rotation log/exp by Rodrigues
+struct CubicIO {
+  int B;
+  const double *x_target, *xdot_target, *x_init, *xdot_init;
+  Strided s12, s6;
+  double t, t0, dur;
+  double *x_des, *xdot_des;
+};
+static __device__ __forceinline__ double cubic_pos(double t, double t0, double tf, double x0, double xf, double v0, double vf) {
+  if (t < t0) return x0;
+  if (t > tf) return xf;
+  const double e = t - t0, T = tf - t0, T2 = T * T, T3 = T2 * T, dx = xf - x0;
+  return x0 + v0 * e + (3 * dx / T2 - 2 * v0 / T - vf / T) * e * e + (-2 * dx / T3 + (v0 + vf) / T2) * e * e * e;
+}
+static __device__ __forceinline__ double cubic_vel(double t, double t0, double tf, double x0, double xf, double v0, double vf) {
+  if (t < t0) return v0;
+  if (t > tf) return vf;
+  const double e = t - t0, T = tf - t0, T2 = T * T, T3 = T2 * T, dx = xf - x0;
+  return v0 + 2 * (3 * dx / T2 - 2 * v0 / T - vf / T) * e + 3 * (-2 * dx / T3 + (v0 + vf) / T2) * e * e;
+}
+static __device__ Vec3 so3_log(const Mat3& R) {
+  const double tr = R.m[0] + R.m[4] + R.m[8];
+  const double c = dmin(dmax(0.5 * (tr - 1.0), -1.0), 1.0);
+  const double th = acos(c);
+  const Vec3 w = v3(R.m[7] - R.m[5], R.m[2] - R.m[6], R.m[3] - R.m[1]);
+  if (th < 1e-8) return 0.5 * w;
+  if (3.14159265358979323846 - th < 1e-6) {
+    int k = 0;
+    if (R.m[4] > R.m[0]) k = 1;
+    if (R.m[8] > R.m[4 * k]) k = 2;
+    Vec3 cl = v3(R.m[k], R.m[3 + k], R.m[6 + k]);
+    if (k == 0) cl.x += 1.0; else if (k == 1) cl.y += 1.0; else cl.z += 1.0;
+    Vec3 ax = (1.0 / norm(cl)) * cl;
+    if (dot(ax, w) < 0) ax = -ax;
+    return th * ax;
+  }
+  return (th / (2.0 * sin(th))) * w;
+}
+static __device__ Mat3 so3_exp(Vec3 w) {
+  const double th = norm(w);
+  if (th < 1e-12) { Mat3 R = {{1, -w.z, w.y, w.z, 1, -w.x, -w.y, w.x, 1}}; return R; }
+  double s, c;
+  sincos(th, &s, &c);
+  return rot_axis((1.0 / th) * w, s, c);
+}
+static __global__ void k_task_cubic(const __grid_constant__ CubicIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  auto ld12 = [&](const double* p, int k) { return p[b * io.s12.sb + k * io.s12.sk]; };
+  auto ld6 = [&](const double* p, int k) { return p[b * io.s6.sb + k * io.s6.sk]; };
+  const double tf = io.t0 + io.dur;
+  Mat3 R0, Rf;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { R0.m[3 * r + c] = ld12(io.x_init, 4 * r + c); Rf.m[3 * r + c] = ld12(io.x_target, 4 * r + c); }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double p0 = ld12(io.x_init, 4 * i + 3), pf = ld12(io.x_target, 4 * i + 3), v0 = ld6(io.xdot_init, i), vf = ld6(io.xdot_target, i);
+    io.x_des[b * io.s12.sb + (4 * i + 3) * io.s12.sk] = cubic_pos(io.t, io.t0, tf, p0, pf, v0, vf);
+    io.xdot_des[b * io.s6.sb + i * io.s6.sk] = cubic_vel(io.t, io.t0, tf, p0, pf, v0, vf);
+  }
+  const Vec3 r = so3_log(tmul(R0, Rf));
+  Mat3 Rd;
+  if (io.t >= tf) Rd = Rf;
+  else if (io.t < io.t0) Rd = R0;
+  else Rd = mul(R0, so3_exp(cubic_pos(io.t, io.t0, tf, 0, 1, 0, 0) * r));
+#pragma unroll
+  for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) io.x_des[b * io.s12.sb + (4 * rr + c) * io.s12.sk] = Rd.m[3 * rr + c];
+  Vec3 rd = v3(cubic_vel(io.t, io.t0, tf, 0, r.x, 0, 0), cubic_vel(io.t, io.t0, tf, 0, r.y, 0, 0), cubic_vel(io.t, io.t0, tf, 0, r.z, 0, 0));
+  rd = mul(R0, rd);
+  const double tau = (io.t - io.t0) / (tf - io.t0);
+  if (tau < 0 || tau > 1) rd = v3(0, 0, 0);
+  io.xdot_des[b * io.s6.sb + 3 * io.s6.sk] = rd.x;
+  io.xdot_des[b * io.s6.sb + 4 * io.s6.sk] = rd.y;
+  io.xdot_des[b * io.s6.sb + 5 * io.s6.sk] = rd.z;
+}
+
+// cache (SoA [K][Bc]) -> user array; `sub` != null writes src - sub (coriolis = nle - g)
+static __global__ void k_copy_cache(const double* src, const double* sub, long long Bc, int K, int B, double* dst, Strided s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)K * B) return;
+  const int k = (int)(i / B), b = (int)(i % B);
+  double v = src[(long long)k * Bc + b];
+  if (sub) v -= sub[(long long)k * Bc + b];
+  dst[b * s.sb + k * s.sk] = v;
+}
+
+// FP64 FMA peak: 8 independent chains per thread
+static __global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double x = 1.0000001, y = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+    a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+
+}  // namespace drc_kernels

@@ -633,12 +633,8 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
       Cold& C = S.cold[L.gl];
-      // accumulate straight into this lane's shared-memory slots (keeps the register peak of the kernel low)
-      struct Acc {
-        double* base;
-        DRC_HD double& operator[](int i) const { return base[i * Cfg::GL]; }
-      };
-      const Acc m = {S.red + L.gl};
+      // per-lane partial reductions in registers (the hot-loop temporaries are dead here), published once at the end
+      double m[kNumRed];
 #pragma unroll
       for (int i = 0; i < kNumRed; ++i) m[i] = 0.0;
       m[20] = -1e300; m[21] = 1e300;
@@ -711,6 +707,8 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         for (int i = 0; i < NC; ++i) { ax += S.A[r * NC + i] * S.u[i]; adx += S.A[r * NC + i] * S.v[i]; }
         bundle_acc(0, ax, adx, y, pdy);
       }
+#pragma unroll
+      for (int i = 0; i < kNumRed; ++i) S.red[i * GL + L.gl] = m[i];
     });
     // C2a: the lanes share the kNumRed group reductions
     w.each([&](LaneT& L, GS& S) {

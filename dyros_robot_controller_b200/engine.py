@@ -65,6 +65,35 @@ class Model:
     def frame_id(self, link_name: str) -> int:
         return lib().drc_model_frame_id(self._h, link_name.encode())
 
+    # ---- mobile base (reference Mobile::KinematicParam, JointIndex, ActuatorIndex: type_define.h:13-72)
+    DRIVE_TYPES = dict(Differential=0, Mecanum=1, Caster=2)
+
+    def attach_mobile_base(self, kin: dict, joint_idx: dict, actuator_idx: dict):
+        """kin: type ("Differential" | "Mecanum" | "Caster" or 0/1/2), wheel_radius, base_width, wheel_offset,
+        roller_angles, base2wheel_positions [(x, y)...], base2wheel_angles.  Call before creating contexts."""
+        t = kin["type"] if isinstance(kin["type"], (int, np.integer)) else self.DRIVE_TYPES[kin["type"]]
+        pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+        w = 2 if t == 0 else (len(kin["roller_angles"]) if t == 1 else 2 * len(pos))
+        arr = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+        ra = arr(kin.get("roller_angles", np.zeros(w)))
+        ba = arr(kin.get("base2wheel_angles", np.zeros(w)))
+        bx, by = arr(pos[:, 0]) if len(pos) else np.zeros(w), arr(pos[:, 1]) if len(pos) else np.zeros(w)
+        check(lib().drc_model_attach_mobile_base(
+            self._h, int(t), C.c_double(kin.get("wheel_radius", 0.0)), C.c_double(kin.get("base_width", 0.0)),
+            C.c_double(kin.get("wheel_offset", 0.0)), int(w), ra.ctypes.data_as(_D), bx.ctypes.data_as(_D), by.ctypes.data_as(_D),
+            ba.ctypes.data_as(_D), int(joint_idx["virtual_start"]), int(joint_idx["mani_start"]), int(joint_idx["mobi_start"]),
+            int(actuator_idx["mani_start"]), int(actuator_idx["mobi_start"])), "drc_model_attach_mobile_base")
+        s = (C.c_int * 4)()
+        check(lib().drc_model_moma_info(self._h, s), "drc_model_moma_info")
+        self.drive_type, self.wheel_num, self.mani_dof, self.actuated_dof = s[0], s[1], s[2], s[3]
+        self.joint_idx, self.actuator_idx = dict(joint_idx), dict(actuator_idx)
+        return self
+
+    def base_jacobian(self) -> np.ndarray:
+        J = np.zeros((3, self.wheel_num))
+        check(lib().drc_model_base_jacobian(self._h, J.ctypes.data_as(_D)), "drc_model_base_jacobian")
+        return J
+
     def verbose(self) -> str:
         return lib().drc_model_verbose(self._h).decode()
 
@@ -350,6 +379,104 @@ class Context:
                                              self._pi(status), self._pi(iters)), "drc_host_cycle_qpid_step")
         self._B = B
         return dict(out=out, status=status, iters=iters)
+
+
+    # ------------------------------------------------------------------ mobile manipulator (whole-body)
+    def moma_update_state(self, q, qdot):
+        """q, qdot: (B, dof) joint-ordered vectors (getJointVector of the reference)."""
+        if _is_torch(q):
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            check(lib().drc_batch_moma_update_state(self._h, B, self._tp(q), self._tp(qd), _capi.LAYOUT_AOS, self._stream()),
+                  "drc_batch_moma_update_state")
+        else:
+            q, B = self._np_in(q, self.n)
+            qd, _ = self._np_in(qdot, self.n, B)
+            check(lib().drc_host_moma_update_state(self._h, B, self._p(q), self._p(qd)), "drc_host_moma_update_state")
+        self._B = B
+        return True
+
+    def moma_get_state(self, link, want=("pose", "J", "Jdot", "vel", "M", "Minv", "g", "nle", "mani", "mani_grad", "mani_graddot")):
+        B, a, k, f = self._B, self.model.actuated_dof, self.model.mani_dof, self._frame(link)
+        shp = dict(pose=(B, 12), J=(B, 6, a), Jdot=(B, 6, a), vel=(B, 6), M=(B, a, a), Minv=(B, a, a), g=(B, a), nle=(B, a),
+                   mani=(B,), mani_grad=(B, k), mani_graddot=(B, k))
+        o = {key: (np.zeros(shp[key]) if key in want else None) for key in shp}
+        if o["mani"] is None and (o["mani_grad"] is not None or o["mani_graddot"] is not None):
+            o["mani"] = np.zeros(B)
+        check(lib().drc_host_moma_get_state(self._h, B, f, *(self._p(o[key]) for key in ("pose", "J", "Jdot", "vel", "M", "Minv", "g",
+                                                                                          "nle", "mani", "mani_grad", "mani_graddot"))),
+              "drc_host_moma_get_state")
+        return {key: v for key, v in o.items() if v is not None}
+
+    def _moma_qp(self, name, B, args, two):
+        a = self.model.actuated_dof
+        out, st, it = np.zeros((B, a)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        fn = getattr(lib(), name)
+        if two:
+            out2 = np.zeros((B, a))
+            check(fn(self._h, B, *args, self._p(out), self._p(out2), self._pi(st), self._pi(it)), name)
+            return dict(out=out, etadot=out2, status=st, iters=it)
+        check(fn(self._h, B, *args, self._p(out), self._pi(st), self._pi(it)), name)
+        return dict(out=out, status=st, iters=it)
+
+    def moma_qpik(self, xdot_des, link):
+        x, B = self._np_in(xdot_des, 6, self._B)
+        return self._moma_qp("drc_host_moma_qpik", B, (self._p(x), self._frame(link)), False)
+
+    def moma_qpik_step(self, x_target, xdot_target, link):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        return self._moma_qp("drc_host_moma_qpik_step", B, (self._p(xt), self._p(xd), self._frame(link)), False)
+
+    def moma_qpid(self, xddot_des, link):
+        x, B = self._np_in(xddot_des, 6, self._B)
+        return self._moma_qp("drc_host_moma_qpid", B, (self._p(x), self._frame(link)), True)
+
+    def moma_qpid_step(self, x_target, xdot_target, link):
+        xt, B = self._np_in(pose12(x_target), 12, self._B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        return self._moma_qp("drc_host_moma_qpid_step", B, (self._p(xt), self._p(xd), self._frame(link)), True)
+
+    def moma_cycle(self, kind, q, qdot, x_target, xdot_target, link, out=None, out2=None, status=None, iters=None):
+        """Fused updateState + whole-body QPIKStep (kind "ik") / QPIDStep (kind "id").  numpy in -> numpy out (host path);
+        torch CUDA tensors in -> torch out (device path, asynchronous)."""
+        f, a, ident = self._frame(link), self.model.actuated_dof, kind == "id"
+        if _is_torch(q):
+            import torch
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            xt, _ = self._t_in(x_target, 12, B)
+            xd, _ = self._t_in(xdot_target, 6, B)
+            out = torch.empty((B, a), dtype=torch.float64, device=q.device) if out is None else out
+            status = torch.empty(B, dtype=torch.int32, device=q.device) if status is None else status
+            iters = torch.empty(B, dtype=torch.int32, device=q.device) if iters is None else iters
+            if ident:
+                out2 = torch.empty((B, a), dtype=torch.float64, device=q.device) if out2 is None else out2
+                check(lib().drc_batch_moma_cycle_qpid_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
+                                                           self._tp(out), self._tp(out2), self._tp(status), self._tp(iters),
+                                                           _capi.LAYOUT_AOS, self._stream()), "drc_batch_moma_cycle_qpid_step")
+            else:
+                check(lib().drc_batch_moma_cycle_qpik_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
+                                                           self._tp(out), self._tp(status), self._tp(iters), _capi.LAYOUT_AOS,
+                                                           self._stream()), "drc_batch_moma_cycle_qpik_step")
+            self._B = B
+            return dict(out=out, etadot=out2, status=status, iters=iters)
+        q, B = self._np_in(q, self.n)
+        qd, _ = self._np_in(qdot, self.n, B)
+        xt, _ = self._np_in(pose12(x_target), 12, B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        out = np.zeros((B, a)) if out is None else out
+        status = np.zeros(B, np.int32) if status is None else status
+        iters = np.zeros(B, np.int32) if iters is None else iters
+        if ident:
+            out2 = np.zeros((B, a)) if out2 is None else out2
+            check(lib().drc_host_moma_cycle_qpid_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
+                                                      self._p(out2), self._pi(status), self._pi(iters)), "drc_host_moma_cycle_qpid_step")
+        else:
+            check(lib().drc_host_moma_cycle_qpik_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
+                                                      self._pi(status), self._pi(iters)), "drc_host_moma_cycle_qpik_step")
+        self._B = B
+        return dict(out=out, etadot=out2, status=status, iters=iters)
 
 
 def fp64_peak_tflops(device: int = 0) -> float:

@@ -164,6 +164,66 @@ int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double*
 int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
                              const double* xdot_target, int frame, double* tau_out, int* status, int* iters);
 
+/* ---- mobile base + mobile manipulator (reference src/mobile/robot_data.cpp, src/mobile_manipulator/*.cpp).
+ * Attach the base to a compiled URDF model BEFORE creating contexts: replaces the Mobile::RobotData(KinematicParam) and
+ * MobileManipulator::RobotData(KinematicParam, JointIndex, ActuatorIndex, urdf...) constructors
+ * (mobile/robot_data.cpp:7-32, mobile_manipulator/robot_data.cpp:7-44).  The URDF must hold three virtual joints
+ * (prismatic x, prismatic y, revolute z at virtual_start..+2), n_wheels wheel joints at mobi_start and the manipulator
+ * joints at mani_start (dof - 3 - n_wheels of them, :19).  Arrays follow KinematicParam (type_define.h:58-72):
+ * roller_angles / b2w_angles (n_wheels, mecanum), b2w_x / b2w_y (n_wheels for mecanum, n_wheels/2 for caster). */
+int drc_model_attach_mobile_base(drc_model_t* m, int drive_type, double wheel_radius, double base_width, double wheel_offset,
+                                 int n_wheels, const double* roller_angles, const double* b2w_x, const double* b2w_y,
+                                 const double* b2w_angles, int virtual_start, int mani_start, int mobi_start,
+                                 int act_mani_start, int act_mobi_start);
+/* sizes: [0] drive type (-1 none) [1] wheels [2] manipulator dof [3] actuated dof */
+int drc_model_moma_info(const drc_model_t* m, int* sizes4);
+/* Mobile::RobotData::getFKJacobian (mobile/robot_data.cpp:122-177), 3 x n_wheels row-major; differential / mecanum */
+int drc_model_base_jacobian(const drc_model_t* m, double* J);
+/* MobileManipulator::RobotData::updateState (mobile_manipulator/robot_data.cpp:83-144) on the joint-ordered vectors
+ * q = getJointVector(q_virtual, q_mobile, q_mani), qdot likewise (dof each, :417-427). */
+int drc_batch_moma_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot, int layout, void* stream);
+/* getPose / getJacobianActuated / getJacobianActuatedTimeVariation / getVelocity (:407-415), getMassMatrixActuated,
+ * getMassMatrixActuatedInv, getGravityActuated, getNonlinearEffectsActuated (:138-142), getManipulability (manipulator
+ * columns, :439-496).  J: 6 x act, M: act x act, mani_grad: manipulator dof.  NULL = skip. */
+int drc_batch_moma_get_state(drc_ctx_t* c, int B, int frame, double* pose12, double* J_act, double* Jdot_act, double* vel,
+                             double* M_act, double* Minv_act, double* g_act, double* nle_act, double* mani, double* mani_grad,
+                             double* mani_graddot, int layout, void* stream);
+/* MobileManipulator::RobotController::QPIK / QPIKStep / QPID / QPIDStep (mobile_manipulator/robot_controller.cpp:147-231).
+ * eta_out / tau_out / etadot_out hold the ACTUATED vector (act per robot); the reference's (mobile, manipulator) pair is
+ * its ActuatorIndex split.  Failures: zeros (QPIK), actuated gravity + zero eta_dot (QPID; the reference slices the
+ * full-dof gravity with actuator indices, :208-218, a latent bug that is not reproduced). */
+int drc_batch_moma_qpik(drc_ctx_t* c, int B, const double* xdot_des, int frame, double* eta_out, int* status, int* iters,
+                        int layout, void* stream);
+int drc_batch_moma_qpik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                             double* eta_out, int* status, int* iters, int layout, void* stream);
+int drc_batch_moma_qpid(drc_ctx_t* c, int B, const double* xddot_des, int frame, double* tau_out, double* etadot_out,
+                        int* status, int* iters, int layout, void* stream);
+int drc_batch_moma_qpid_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                             double* tau_out, double* etadot_out, int* status, int* iters, int layout, void* stream);
+/* fused updateState + QPIKStep / QPIDStep (BASELINE configs 4-5) */
+int drc_batch_moma_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                   const double* xdot_target, int frame, double* eta_out, int* status, int* iters,
+                                   int layout, void* stream);
+int drc_batch_moma_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                   const double* xdot_target, int frame, double* tau_out, double* etadot_out, int* status,
+                                   int* iters, int layout, void* stream);
+int drc_host_moma_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot);
+int drc_host_moma_get_state(drc_ctx_t* c, int B, int frame, double* pose12, double* J_act, double* Jdot_act, double* vel,
+                            double* M_act, double* Minv_act, double* g_act, double* nle_act, double* mani, double* mani_grad,
+                            double* mani_graddot);
+int drc_host_moma_qpik(drc_ctx_t* c, int B, const double* xdot_des, int frame, double* eta_out, int* status, int* iters);
+int drc_host_moma_qpik_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                            double* eta_out, int* status, int* iters);
+int drc_host_moma_qpid(drc_ctx_t* c, int B, const double* xddot_des, int frame, double* tau_out, double* etadot_out,
+                       int* status, int* iters);
+int drc_host_moma_qpid_step(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, int frame,
+                            double* tau_out, double* etadot_out, int* status, int* iters);
+int drc_host_moma_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                  const double* xdot_target, int frame, double* eta_out, int* status, int* iters);
+int drc_host_moma_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                  const double* xdot_target, int frame, double* tau_out, double* etadot_out, int* status,
+                                  int* iters);
+
 /* ---- instrumentation (replaces QP::TimeDuration / SuhanBenchmark, QP_base.h:19-43) */
 /* device time in ms of the stages of the LAST cycle/QP call on this context (CUDA events on its stream):
  * [0] state/QP build  [1] self-collision  [2] ADMM solve  [3] total; requires drc_ctx_enable_timing(c,1) */

@@ -1,0 +1,141 @@
+"""GPU parity tests of the mobile-manipulator path through the C ABI against the oracle."""
+import numpy as np
+import pytest
+
+from tests.conftest import MOMA, moma_workload
+
+pytestmark = pytest.mark.gpu
+LINK = "fr3_link8"
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module", params=["husky_fr3", "xls_fr3"])
+def rig(request):
+    import dyros_robot_controller_b200 as drc
+    from oracle.c_oracle import MomaOracle
+    if drc.device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device; the product path has no CPU fallback")
+    d = MOMA[request.param]
+    o = MomaOracle(d["urdf"], d["srdf"], d["kin"], d["joint_idx"], d["actuator_idx"], threads=8)
+    model = drc.Model(d["urdf"], d["srdf"]).attach_mobile_base(d["kin"], d["joint_idx"], d["actuator_idx"])
+    ctx = drc.Context(model, 8192, device=0)
+    return request.param, d, o, model, ctx
+
+
+def consistent(o, q, qd):
+    J, bv = o.mobile_state(q[:, 3:3 + o.w], qd[:, 3:3 + o.w])
+    c, s = np.cos(q[:, 2]), np.sin(q[:, 2])
+    qd = qd.copy()
+    qd[:, 0], qd[:, 1], qd[:, 2] = c * bv[:, 0] - s * bv[:, 1], s * bv[:, 0] + c * bv[:, 1], bv[:, 2]
+    return qd
+
+
+def test_moma_model_and_state(rig):
+    name, d, o, model, ctx = rig
+    assert model.actuated_dof == o.act and model.mani_dof == 7 and model.wheel_num == o.w
+    assert np.abs(model.base_jacobian() - o.mobile_state(np.zeros((1, o.w)), np.zeros((1, o.w)))[0][0]).max() < 1e-12
+    f = o.frame_id(LINK)
+    q, qd, _, _ = moma_workload(o.model, o.w, 1000, 31)
+    ref, full = o.moma_update_state(q, qd, f), o.update_state(q, qd, f)
+    ctx.moma_update_state(q, qd)
+    r = ctx.moma_get_state(LINK)
+    assert rel(r["pose"], full["pose"]) < 1e-12
+    assert rel(r["J"], ref["J"]) < 1e-12 and rel(r["Jdot"], ref["Jdot"]) < 1e-11
+    assert rel(r["vel"], np.einsum("bij,bj->bi", full["J"], qd)) < 1e-11
+    assert rel(r["M"], ref["M"]) < 1e-9 and rel(r["g"], ref["g"]) < 1e-9 and rel(r["nle"], ref["nle"]) < 1e-9
+    assert rel(r["Minv"], ref["Minv"]) < 1e-7
+    assert np.abs(r["mani"] - ref["mani"]).max() < 1e-11
+    assert np.abs(r["mani_grad"] - ref["mani_grad"]).max() < 1e-9 * max(1.0, np.abs(ref["mani_grad"]).max())
+    assert np.abs(r["mani_graddot"] - ref["mani_graddot"]).max() < 1e-8 * max(1.0, np.abs(ref["mani_graddot"]).max())
+
+
+@pytest.mark.parametrize("mode,B", [(1, 2000), (3, 1000), (0, 500), (2, 500)])
+def test_moma_control_cycle_matches_oracle(rig, mode, B):
+    name, d, o, model, ctx = rig
+    f = o.frame_id(LINK)
+    q, qd, q_t, xd = moma_workload(o.model, o.w, B, 40 + mode)
+    qd = consistent(o, q, qd)
+    x_t = o.update_state(q_t, qd, f)["pose"] if mode in (1, 3) else None
+    des = xd if mode in (1, 3) else 3.0 * xd
+    ref = o.moma_cycle(mode, q, qd, x_t, des, f)
+    if mode == 1:
+        r = ctx.moma_cycle("ik", q, qd, x_t, des, LINK)
+    elif mode == 3:
+        r = ctx.moma_cycle("id", q, qd, x_t, des, LINK)
+    else:
+        ctx.moma_update_state(q, qd)
+        r = ctx.moma_qpik(des, LINK) if mode == 0 else ctx.moma_qpid(des, LINK)
+    assert (r["status"] == ref["status"]).mean() > 0.98
+    same = (r["iters"] == ref["iters"]) & (r["status"] == ref["status"])
+    assert same.mean() > 0.97
+    scale = max(1.0, np.abs(ref["out"]).max())
+    err = np.abs(r["out"] - ref["out"]).max(axis=1)[same]
+    # hard-constraint whole-body QPs amplify the GJK witness noise of an ACTIVE self-collision row more than the slack
+    # formulations do: a handful of robots per thousand may differ by a few per cent of the torque scale
+    assert (err < 1e-4 * scale).mean() > 0.99 and err.max() < (1e-2 if mode <= 1 else 5e-2) * scale
+    if mode >= 2:
+        e2 = np.abs(r["etadot"] - ref["out2"]).max(axis=1)[same]
+        assert (e2 < 1e-4 * max(1.0, np.abs(ref["out2"]).max())).mean() > 0.99
+    # fallbacks: zeros (QPIK) / actuated gravity with zero eta_dot (QPID)
+    bad = r["status"] != 1
+    if bad.any():
+        if mode <= 1:
+            assert np.abs(r["out"][bad]).max() == 0.0
+        else:
+            assert np.abs(r["etadot"][bad]).max() == 0.0
+
+
+def test_moma_reference_api_mirror(rig):
+    """dyros_robot_controller_b200.drc.mobile_manipulator mirrors the reference classes: six state vectors in,
+    (mobile, manipulator) pairs out (mobile_manipulator/robot_controller.cpp:147-231)."""
+    from dyros_robot_controller_b200.drc.mobile_manipulator import RobotController, RobotData
+    from oracle import c_oracle
+    name, d, o, model, ctx = rig
+    rd = RobotData(d["kin"], d["joint_idx"], d["actuator_idx"], d["urdf"], d["srdf"], max_batch=32)
+    rc = RobotController(0.001, rd)
+    f = o.frame_id(LINK)
+    q, qd, q_t, xd = moma_workload(o.model, o.w, 32, 50)
+    qd = consistent(o, q, qd)
+    w = o.w
+    x_t = o.update_state(q_t, qd, f)["pose"]
+    ref = o.moma_cycle(1, q, qd, x_t, xd, f)
+    # one robot, reference shapes
+    assert rd.update_state(q[0, :3], q[0, 3:3 + w], q[0, 3 + w:], qd[0, :3], qd[0, 3:3 + w], qd[0, 3 + w:]) is True
+    assert rd.get_pose(LINK).shape == (4, 4) and rd.get_jacobian_actuated(LINK).shape == (6, o.act)
+    assert rd.get_mass_matrix_actuated().shape == (o.act, o.act) and rd.get_gravity_actuated().shape == (o.act,)
+    assert np.abs(rd.get_base_vel() - rd.get_FK_jacobian() @ qd[0, 3:3 + w]).max() < 1e-14
+    mob, mani = rc.QPIK_step(c_oracle.pose44(x_t[0]), xd[0], LINK)
+    assert mob.shape == (w,) and mani.shape == (7,)
+    assert np.abs(np.concatenate([mob, mani]) - ref["out"][0]).max() < 1e-4
+    # batch
+    rd.update_state(q[:, :3], q[:, 3:3 + w], q[:, 3 + w:], qd[:, :3], qd[:, 3:3 + w], qd[:, 3 + w:])
+    mob, mani = rc.QPIK_step(c_oracle.pose44(x_t), xd, LINK)
+    same = rc.last_iters == ref["iters"]
+    assert same.mean() > 0.9 and np.abs(np.concatenate([mob, mani], axis=1) - ref["out"])[same].max() < 1e-4
+    ref3 = o.moma_cycle(3, q, qd, x_t, xd, f)
+    acc, tau = rc.QPID_step(c_oracle.pose44(x_t), xd, LINK)
+    same = rc.last_iters == ref3["iters"]
+    assert acc.shape == (32, w) and tau.shape == (32, 7)
+    assert np.abs(tau - ref3["out"][:, w:])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out"]).max())
+    assert np.abs(acc - ref3["out2"][:, :w])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out2"]).max())
+
+
+def test_moma_full_size_properties(rig):
+    """BASELINE config 4/5 batch on one GPU shard (8192 here): determinism, permutation equivariance, fallbacks."""
+    name, d, o, model, ctx = rig
+    B = 8192
+    q, qd, q_t, xd = moma_workload(o.model, o.w, B, 60)
+    qd = consistent(o, q, qd)
+    ctx.moma_update_state(q_t, qd)
+    x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
+    r = ctx.moma_cycle("ik", q, qd, x_t, xd, LINK)
+    assert (r["status"] == 1).mean() > 0.9
+    assert (r["iters"] % 25 == 0).all()
+    r2 = ctx.moma_cycle("ik", q, qd, x_t, xd, LINK)
+    assert np.array_equal(r2["out"], r["out"]) and (r2["iters"] == r["iters"]).all()
+    perm = np.random.default_rng(0).permutation(B)
+    r3 = ctx.moma_cycle("ik", q[perm], qd[perm], x_t[perm], xd[perm], LINK)
+    assert np.array_equal(r3["out"], r["out"][perm])
