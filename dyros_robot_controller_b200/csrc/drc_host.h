@@ -69,9 +69,11 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
   io.c_Mact = c->c_Mact; io.c_Minvact = c->c_Minvact; io.c_gact = c->c_gact; io.c_nleact = c->c_nleact;
 }
 
-// dispatch on the compile-time robot shape; extend the list to add robots
+// dispatch on the compile-time robot shape; extend the list to add robots (serial chains of 7 / 6 revolute joints:
+// FR3 class, UR5e class)
 #define DRC_DISPATCH_NV(nv, chain, CALL)                                         \
   if ((nv) == 7 && (chain)) { constexpr int NV = 7; constexpr bool CHAIN = true; CALL; } \
+  else if ((nv) == 6 && (chain)) { constexpr int NV = 6; constexpr bool CHAIN = true; CALL; } \
   else return fail(DRC_E_UNSUPPORTED, "no kernel instantiation for this robot (dof / topology)");
 
 template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>

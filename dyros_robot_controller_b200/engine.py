@@ -354,7 +354,8 @@ class Context:
         self._B = B
         return dict(out=out, status=status, iters=iters)
 
-    def cycle_qpid_step(self, q, qdot, x_target, xdot_target, link):
+    def cycle_qpid_step(self, q, qdot, x_target, xdot_target, link, out=None, status=None, iters=None):
+        """updateState + QPIDStep -> torque.  numpy in -> numpy out (host path); torch CUDA in -> torch out (async)."""
         f = self._frame(link)
         if _is_torch(q):
             import torch
@@ -362,9 +363,9 @@ class Context:
             qd, _ = self._t_in(qdot, self.n, B)
             xt, _ = self._t_in(x_target, 12, B)
             xd, _ = self._t_in(xdot_target, 6, B)
-            out = torch.empty((B, self.n), dtype=torch.float64, device=q.device)
-            status = torch.empty(B, dtype=torch.int32, device=q.device)
-            iters = torch.empty(B, dtype=torch.int32, device=q.device)
+            out = torch.empty((B, self.n), dtype=torch.float64, device=q.device) if out is None else out
+            status = torch.empty(B, dtype=torch.int32, device=q.device) if status is None else status
+            iters = torch.empty(B, dtype=torch.int32, device=q.device) if iters is None else iters
             check(lib().drc_batch_cycle_qpid_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
                                                   self._tp(out), self._tp(status), self._tp(iters), _capi.LAYOUT_AOS,
                                                   self._stream()), "drc_batch_cycle_qpid_step")
@@ -374,12 +375,13 @@ class Context:
         qd, _ = self._np_in(qdot, self.n, B)
         xt, _ = self._np_in(pose12(x_target), 12, B)
         xd, _ = self._np_in(xdot_target, 6, B)
-        out, status, iters = np.zeros((B, self.n)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        out = np.zeros((B, self.n)) if out is None else out
+        status = np.zeros(B, np.int32) if status is None else status
+        iters = np.zeros(B, np.int32) if iters is None else iters
         check(lib().drc_host_cycle_qpid_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
                                              self._pi(status), self._pi(iters)), "drc_host_cycle_qpid_step")
         self._B = B
         return dict(out=out, status=status, iters=iters)
-
 
     # ------------------------------------------------------------------ mobile manipulator (whole-body)
     def moma_update_state(self, q, qdot):

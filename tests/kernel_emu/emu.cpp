@@ -124,11 +124,12 @@ void emu_set_params(EmuHandle* h, const double* kp_task, const double* kv_task, 
 }
 
 // ---- stage: updateState + frame getters + manipulability (all arrays batch-major / AoS)
-int emu_update_and_get(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* J,
+}  // extern "C"
+template <int NV>
+static int emu_update_and_get_t(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* J,
                        double* Jdot, double* vel, double* M, double* Minv, double* g, double* nle, double* oMi,
                        double* mani, double* mgrad, double* mgraddot) {
   const int n = h->hm.dev.nv;
-  if (n != 7 || !h->hm.chain) return -1;
   const DrcFrame fr = make_frame(h->hm, frame_id);
   Cache c(n, B);
   JobIO io;
@@ -137,7 +138,7 @@ int emu_update_and_get(EmuHandle* h, int frame_id, int B, const double* q, const
   c.bind(io);
   io.pose = pose; io.spose = aos(12); io.J = J; io.sJ = aos(6 * n); io.Jdot = Jdot; io.sJd = aos(6 * n); io.vel = vel; io.svel = aos(6);
   io.mani = mani; io.mani_grad = mgrad; io.smg = aos(n); io.mani_graddot = mgraddot; io.smgd = aos(n);
-  run_job<7, true, F_DYN | F_STORE | F_FRAME_OUT | F_MANIP_OUT | F_GRADDOT>(h, fr, io);
+  run_job<NV, true, F_DYN | F_STORE | F_FRAME_OUT | F_MANIP_OUT | F_GRADDOT>(h, fr, io);
   for (int b = 0; b < B; ++b) {
     for (int i = 0; i < n * n; ++i) { if (M) M[b * n * n + i] = c.M[i * B + b]; if (Minv) Minv[b * n * n + i] = c.Minv[i * B + b]; }
     for (int i = 0; i < n; ++i) { if (g) g[b * n + i] = c.g[i * B + b]; if (nle) nle[b * n + i] = c.nle[i * B + b]; }
@@ -145,36 +146,55 @@ int emu_update_and_get(EmuHandle* h, int frame_id, int B, const double* q, const
   }
   return 0;
 }
+extern "C" {
+int emu_update_and_get(EmuHandle* h, int frame_id, int B, const double* q, const double* qd, double* pose, double* J,
+                       double* Jdot, double* vel, double* M, double* Minv, double* g, double* nle, double* oMi,
+                       double* mani, double* mgrad, double* mgraddot) {
+  if (!h->hm.chain) return -1;
+  if (h->hm.dev.nv == 7) return emu_update_and_get_t<7>(h, frame_id, B, q, qd, pose, J, Jdot, vel, M, Minv, g, nle, oMi, mani, mgrad, mgraddot);
+  if (h->hm.dev.nv == 6) return emu_update_and_get_t<6>(h, frame_id, B, q, qd, pose, J, Jdot, vel, M, Minv, g, nle, oMi, mani, mgrad, mgraddot);
+  return -1;
+}
 
 // ---- stage: min self-distance with gradients
-int emu_min_distance(EmuHandle* h, int B, const double* q, const double* qd, double* dist, double* grad, double* grad_dot,
+}  // extern "C"
+template <int NV>
+static int emu_min_distance_t(EmuHandle* h, int B, const double* q, const double* qd, double* dist, double* grad, double* grad_dot,
                      int* pair, double* witness) {
   const int n = h->hm.dev.nv;
-  if (n != 7 || !h->hm.chain) return -1;
   Cache c(n, B);
   JobIO io;
   std::memset(&io, 0, sizeof io);
   io.B = B; io.q = q; io.sq = aos(n); io.qd = qd; io.sqd = aos(n);
   c.bind(io);
   DrcFrame fr = make_frame(h->hm, 0);
-  run_job<7, true, F_STORE>(h, fr, io);
+  run_job<NV, true, F_STORE>(h, fr, io);
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.c_q = c.q.data(); cio.c_qd = c.qd.data(); cio.c_oMi = c.oMi.data(); cio.Bc = B; cio.mode = 0;
   cio.dist = dist; cio.grad = grad; cio.sgrad = aos(n); cio.grad_dot = grad_dot; cio.sgd = aos(n); cio.pair_out = pair; cio.witness = witness;
   std::vector<int> flag, pr; std::vector<unsigned long long> mask; std::vector<double> ds, wt;
-  run_collision<7, true>(h, cio, flag, mask, ds, pr, wt);
+  run_collision<NV, true>(h, cio, flag, mask, ds, pr, wt);
   int nepa = 0;
   for (int b = 0; b < B; ++b) nepa += flag[b];
   return nepa;
 }
+extern "C" {
+int emu_min_distance(EmuHandle* h, int B, const double* q, const double* qd, double* dist, double* grad, double* grad_dot,
+                     int* pair, double* witness) {
+  if (!h->hm.chain) return -1;
+  if (h->hm.dev.nv == 7) return emu_min_distance_t<7>(h, B, q, qd, dist, grad, grad_dot, pair, witness);
+  if (h->hm.dev.nv == 6) return emu_min_distance_t<6>(h, B, q, qd, dist, grad, grad_dot, pair, witness);
+  return -1;
+}
 
 // ---- full control cycle: updateState + QPIKStep / QPIDStep (mode 1 / 3) or QPIK / QPID with the
 //      desired task signal given in xdot_target (mode 0 / 2)
-int emu_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+}  // extern "C"
+template <int NV>
+static int emu_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
               const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records) {
   const int n = h->hm.dev.nv;
-  if (n != 7 || !h->hm.chain) return -1;
   const DrcFrame fr = make_frame(h->hm, frame_id);
   Cache c(n, B);
   JobIO io;
@@ -183,36 +203,45 @@ int emu_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, cons
   io.x_target = x_target; io.sxt = aos(12); io.xdot_target = xdot_target; io.sxd = aos(6);
   c.bind(io);
   const bool ID = mode >= 2;
-  const int stride = ID ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE;
+  const int stride = ID ? QpidCfg<NV>::STRIDE : QpikCfg<NV>::STRIDE;
   std::vector<double> rec((size_t)stride * B, 0.0);
   io.qp = rec.data();
-  if (mode == 0) run_job<7, true, F_DYN | F_STORE | F_QPIK>(h, fr, io);
-  else if (mode == 1) run_job<7, true, F_DYN | F_STORE | F_QPIK | F_STEP>(h, fr, io);
-  else if (mode == 2) run_job<7, true, F_DYN | F_STORE | F_QPID>(h, fr, io);
-  else run_job<7, true, F_DYN | F_STORE | F_QPID | F_STEP>(h, fr, io);
+  if (mode == 0) run_job<NV, true, F_DYN | F_STORE | F_QPIK>(h, fr, io);
+  else if (mode == 1) run_job<NV, true, F_DYN | F_STORE | F_QPIK | F_STEP>(h, fr, io);
+  else if (mode == 2) run_job<NV, true, F_DYN | F_STORE | F_QPID>(h, fr, io);
+  else run_job<NV, true, F_DYN | F_STORE | F_QPID | F_STEP>(h, fr, io);
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.c_q = c.q.data(); cio.c_qd = c.qd.data(); cio.c_oMi = c.oMi.data(); cio.Bc = B;
   cio.mode = ID ? 2 : 1; cio.qp = rec.data(); cio.qp_stride = stride;
-  cio.qp_row_off = (ID ? QpidCfg<7>::OFF_ROW : QpikCfg<7>::OFF_ROW) + (n + 1);
+  cio.qp_row_off = (ID ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (n + 1);
   std::vector<int> flag, pr; std::vector<unsigned long long> mask; std::vector<double> ds, wt;
-  run_collision<7, true>(h, cio, flag, mask, ds, pr, wt);
+  run_collision<NV, true>(h, cio, flag, mask, ds, pr, wt);
   if (qp_records) std::memcpy(qp_records, rec.data(), rec.size() * sizeof(double));
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.qp = rec.data(); sio.out = out; sio.sout = aos(n); sio.status = status; sio.iters = iters;
   sio.c_g = c.g.data(); sio.Bc = B; sio.qp_x = qp_x;
-  if (ID) run_solve<QpidCfg<7>, true>(h, sio, 0x7f);
-  else run_solve<QpikCfg<7>, false>(h, sio, 0x7f);
+  if (ID) run_solve<QpidCfg<NV>, true>(h, sio, (1u << NV) - 1u);
+  else run_solve<QpikCfg<NV>, false>(h, sio, (1u << NV) - 1u);
   return 0;
 }
-int emu_qp_stride(int mode) { return mode >= 2 ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE; }
+extern "C" {
+int emu_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records) {
+  if (!h->hm.chain) return -1;
+  if (h->hm.dev.nv == 7) return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records);
+  if (h->hm.dev.nv == 6) return emu_cycle_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records);
+  return -1;
+}
+int emu_qp_stride(int mode) { return mode >= 2 ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE; }  // FR3 records
 
 // ---- CLIKStep (mode 0) / OSFStep (mode 1) / OSF (mode 2) / joint PD torque (mode 3: aux=q_t, aux2=qd_t)
-int emu_taskspace(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+}  // extern "C"
+template <int NV>
+static int emu_taskspace_t(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
                   const double* xdot_target, const double* aux, const double* aux2, double* out) {
   const int n = h->hm.dev.nv;
-  if (n != 7 || !h->hm.chain) return -1;
   const DrcFrame fr = make_frame(h->hm, frame_id);
   Cache c(n, B);
   JobIO io;
@@ -221,11 +250,19 @@ int emu_taskspace(EmuHandle* h, int mode, int frame_id, int B, const double* q, 
   io.x_target = x_target; io.sxt = aos(12); io.xdot_target = xdot_target; io.sxd = aos(6);
   io.aux = aux; io.saux = aos(n); io.aux2 = aux2; io.saux2 = aos(n); io.out = out; io.sout = aos(n);
   c.bind(io);
-  if (mode == 0) run_job<7, true, F_CLIK | F_STEP>(h, fr, io);
-  else if (mode == 1) run_job<7, true, F_DYN | F_OSF | F_STEP>(h, fr, io);
-  else if (mode == 2) run_job<7, true, F_DYN | F_OSF>(h, fr, io);
-  else run_job<7, true, F_DYN | F_TORQUE>(h, fr, io);
+  if (mode == 0) run_job<NV, true, F_CLIK | F_STEP>(h, fr, io);
+  else if (mode == 1) run_job<NV, true, F_DYN | F_OSF | F_STEP>(h, fr, io);
+  else if (mode == 2) run_job<NV, true, F_DYN | F_OSF>(h, fr, io);
+  else run_job<NV, true, F_DYN | F_TORQUE>(h, fr, io);
   return 0;
+}
+extern "C" {
+int emu_taskspace(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                  const double* xdot_target, const double* aux, const double* aux2, double* out) {
+  if (!h->hm.chain) return -1;
+  if (h->hm.dev.nv == 7) return emu_taskspace_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, aux, aux2, out);
+  if (h->hm.dev.nv == 6) return emu_taskspace_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, aux, aux2, out);
+  return -1;
 }
 
 // ---- narrow phase of the product on one shape pair (type, prm[3], pose12), world frame
