@@ -46,6 +46,8 @@ struct DrcParams {
   double gjk_tol = 1e-10, epa_tol = 1e-6;  // EPA: hpp-fcl's default; curved pairs converge like 1/k^2
   int gjk_max_iter = 128, epa_max_iter = 96;
   double pinv_threshold = 1e-6;  // COD rank threshold (math_type_define.h:7)
+  // scheduling only (no effect on results): order the ADMM launch by the previous tick's iteration counts
+  int schedule_hint = 1;
 };
 
 // Collision primitives (kept as one block so a kernel can stage it into shared memory).

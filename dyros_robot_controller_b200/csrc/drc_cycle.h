@@ -723,6 +723,8 @@ struct SolveIO {
   int* status; int* iters;      // per robot (optional)
   const double* c_g; long long Bc;  // gravity cache for the QPID fallback
   double* qp_x;                 // optional debug: [core x (NC) | unit slacks (KU*NC) | row singletons (NR)] per robot
+  const int* order;             // optional schedule: the i-th solver group takes robot order[i] (null = identity)
+  int* iters_hint;              // optional: iteration count of every robot, kept by the context for the next tick's schedule
 };
 
 template <class Cfg, bool ID, class W>
@@ -735,6 +737,7 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
     if (L.gl == 0) {
       if (io.status) io.status[b] = S.status;
       if (io.iters) io.iters[b] = S.iters;
+      if (io.iters_hint) io.iters_hint[b] = S.iters;
     }
     const ColdLane<Cfg>& C = S.cold[L.gl];
     if (L.is_core) {

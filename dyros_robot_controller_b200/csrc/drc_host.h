@@ -43,6 +43,7 @@ struct drc_ctx {
   int qp_stride_max;
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
+  int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
   int sm_count;
   // device staging for host entry points
   double* stage; size_t stage_doubles;
@@ -109,6 +110,19 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   io.qp = c->qp; io.c_g = gravity ? gravity : c->c_g; io.Bc = c->cap;
   const QpOptions o = qp_options(c->prm, unit_mask);
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
+  // schedule from the previous tick's iteration counts (see k_sched_* in drc_kernels.cuh); results do not depend on it
+  io.iters_hint = c->prev_iters;
+  io.order = nullptr;
+  if (c->prm.schedule_hint && io.B >= 4 * per_block) {
+    CU(cudaMemsetAsync(c->sched_hist, 0, kSchedBuckets * sizeof(int), s));
+    const int tb = 256, nb = (io.B + tb - 1) / tb;
+    k_sched_hist<<<nb < 1024 ? nb : 1024, tb, 0, s>>>(c->prev_iters, io.B, c->sched_hist);
+    k_sched_scan<<<1, kSchedBuckets, 0, s>>>(c->sched_hist);
+    k_sched_scatter<<<nb, tb, 0, s>>>(c->prev_iters, io.B, c->sched_hist, c->order);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    io.order = c->order;
+  }
   // blocks/SM the kernel is compiled for (register cap 65536 / (128 * MINB)); tunable for experiments
   static const int minb = [] { const char* e = getenv("DRC_ADMM_MINB"); return e ? atoi(e) : 3; }();
   constexpr size_t smem = sizeof(GroupShared<Cfg>) * kAdmmWarps * Cfg::NG;

@@ -218,12 +218,49 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, 4 * MINB) k_admm(const __grid
   if (first >= io.B) return;  // no block-level barrier below: idle warps may leave
   int robots[Cfg::NG];
 #pragma unroll
-  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < io.B ? first + g : -1;
+  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < io.B ? (io.order ? io.order[first + g] : first + g) : -1;
   WarpExec<Cfg> w;
   w.sh = sh + warp * Cfg::NG;
   w.lane = lane;
   lane_assign<Cfg>(w.L, lane);
   solve_and_emit<Cfg, ID>(w, robots, io, o);
+}
+
+// ---- ADMM schedule.  The iteration count of a QP is not known in advance and spreads from 50 to max_iter (4000):
+// one late-starting slow robot keeps a single warp busy long after the rest of the grid has drained (measured: 41 %
+// of the kernel), and the robots sharing a warp wait for its slowest member.  In a control loop consecutive ticks
+// solve nearly the same QP, so the PREVIOUS tick's iteration count is an excellent predictor: robots are ordered by
+// descending previous count (counting sort over count/25), i.e. longest first and warps of similar length.  Only the
+// robot -> warp assignment changes; every robot's arithmetic, and therefore its result, is unaffected.
+constexpr int kSchedBuckets = 256;
+static __device__ __forceinline__ int sched_bucket(int iters) {
+  const int k = iters / 25;
+  return kSchedBuckets - 1 - (k < kSchedBuckets ? k : kSchedBuckets - 1);  // descending: slow robots get the small buckets
+}
+static __global__ void k_sched_hist(const int* prev, int B, int* hist) {
+  __shared__ int h[kSchedBuckets];
+  for (int i = threadIdx.x; i < kSchedBuckets; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) atomicAdd(&h[sched_bucket(prev[b])], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSchedBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+static __global__ void k_sched_scan(int* hist) {  // one block of kSchedBuckets threads: exclusive prefix sum in place
+  __shared__ int a[kSchedBuckets];
+  const int t = threadIdx.x;
+  a[t] = hist[t];
+  __syncthreads();
+  for (int off = 1; off < kSchedBuckets; off <<= 1) {
+    const int v = t >= off ? a[t - off] : 0;
+    __syncthreads();
+    a[t] += v;
+    __syncthreads();
+  }
+  hist[t] = a[t] - hist[t];
+}
+static __global__ void k_sched_scatter(const int* prev, int B, int* offs, int* order) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) order[atomicAdd(&offs[sched_bucket(prev[b])], 1)] = b;
 }
 
 // DyrosMath::getTaskSpaceCubic (math_type_define.h:62-144,235-281,647-685); rotation log/exp by Rodrigues

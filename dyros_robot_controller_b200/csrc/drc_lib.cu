@@ -167,6 +167,10 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   CU(dalloc(&c->col_wit, 6 * B));
   CU(cudaMalloc((void**)&c->epa_list, B * sizeof(int)));
   CU(cudaMalloc((void**)&c->epa_count, sizeof(int)));
+  CU(cudaMalloc((void**)&c->prev_iters, B * sizeof(int)));
+  CU(cudaMemset(c->prev_iters, 0, B * sizeof(int)));
+  CU(cudaMalloc((void**)&c->order, B * sizeof(int)));
+  CU(cudaMalloc((void**)&c->sched_hist, kSchedBuckets * sizeof(int)));
   {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -193,6 +197,9 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->col_pair) cudaFree(c->col_pair);
   if (c->epa_list) cudaFree(c->epa_list);
   if (c->epa_count) cudaFree(c->epa_count);
+  if (c->prev_iters) cudaFree(c->prev_iters);
+  if (c->order) cudaFree(c->order);
+  if (c->sched_hist) cudaFree(c->sched_hist);
   if (c->stage_i) cudaFree(c->stage_i);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
@@ -210,7 +217,7 @@ int drc_ctx_get_params(const drc_ctx_t* c, drc_params_t* p) {
   p->check_termination = s.check_termination; p->scaling = s.scaling; p->adaptive_rho = s.adaptive_rho;
   p->adaptive_rho_interval = s.adaptive_rho_interval; p->adaptive_rho_tolerance = s.adaptive_rho_tolerance;
   p->gjk_tol = s.gjk_tol; p->epa_tol = s.epa_tol; p->gjk_max_iter = s.gjk_max_iter; p->epa_max_iter = s.epa_max_iter;
-  p->pinv_threshold = s.pinv_threshold;
+  p->pinv_threshold = s.pinv_threshold; p->schedule_hint = s.schedule_hint;
   return DRC_OK;
 }
 int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
@@ -228,7 +235,7 @@ int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
   s.check_termination = p->check_termination; s.scaling = p->scaling; s.adaptive_rho = p->adaptive_rho;
   s.adaptive_rho_interval = p->adaptive_rho_interval; s.adaptive_rho_tolerance = p->adaptive_rho_tolerance;
   s.gjk_tol = p->gjk_tol; s.epa_tol = p->epa_tol; s.gjk_max_iter = p->gjk_max_iter; s.epa_max_iter = p->epa_max_iter;
-  s.pinv_threshold = p->pinv_threshold;
+  s.pinv_threshold = p->pinv_threshold; s.schedule_hint = p->schedule_hint;
   return DRC_OK;
 }
 int drc_ctx_max_batch(const drc_ctx_t* c) { return c ? c->cap : DRC_E_INVALID; }

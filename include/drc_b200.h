@@ -48,6 +48,9 @@ typedef struct drc_params {
   double gjk_tol, epa_tol;
   int gjk_max_iter, epa_max_iter;
   double pinv_threshold;
+  /* scheduling only, results unaffected: order the ADMM launch by each robot's iteration count of the previous call on
+   * this context (longest first, similar counts share a warp) -- consecutive control ticks solve nearly the same QP */
+  int schedule_hint;
 } drc_params_t;
 
 const char* drc_last_error(void);

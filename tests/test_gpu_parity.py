@@ -257,3 +257,22 @@ def test_reference_api_mirror(oracle):
     assert same.mean() > 0.95 and np.abs(out2 - ref4["out"])[same].max() < 1e-4
     with pytest.raises(RuntimeError):
         rc.set_task_gain(np.ones(5), np.ones(6))
+
+
+def test_schedule_hint_changes_nothing_but_the_order(gpu_ctx, oracle):
+    """The ADMM launch is ordered by the previous call's iteration counts (longest first); with the hint off, on, and on
+    again with a stale hint from a different batch, every robot's result is bit-identical."""
+    model, ctx = gpu_ctx
+    B = 20000
+    q, qd, q_t, xdot_t = workload(oracle.model, B, 13, stress=True)
+    x_t = oracle.update_state(q_t, qd, oracle.frame_id(LINK))["pose"]
+    ctx.set_params(schedule_hint=0)
+    a = ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)
+    ctx.set_params(schedule_hint=1)
+    b = ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)            # hint = the counts of call a (exact)
+    perm = np.random.default_rng(3).permutation(B)
+    ctx.cycle_qpik_step(q[perm], qd[perm], x_t[perm], xdot_t[perm], LINK)
+    c = ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)            # hint from the permuted batch (wrong for every robot)
+    for r in (b, c):
+        assert np.array_equal(r["out"], a["out"]) and np.array_equal(r["iters"], a["iters"]) and np.array_equal(r["status"], a["status"])
+    assert ctx.get_params().schedule_hint == 1
