@@ -35,6 +35,8 @@ struct drc_ctx {
   int device, cap;
   DrcParams prm;
   cudaStream_t stream;
+  cudaStream_t side;      // EPA pass of the self-collision stage runs here, next to the state / QP-build kernel
+  cudaEvent_t ev_col, ev_epa;
   // state cache (SoA, stride cap)
   double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
   double *c_Mact, *c_Minvact, *c_gact, *c_nleact;  // mobile manipulator only (actuated-space dynamics)
@@ -88,7 +90,7 @@ static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStrea
 }
 
 template <int NV, bool CHAIN>
-static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s) {
+static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa_on_side_stream = false) {
   io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.Bc = c->cap;
   io.epa_flag = c->epa_flag; io.cand_mask = c->cand_mask; io.epa_list = c->epa_list; io.epa_count = c->epa_count;
   CU(cudaMemsetAsync(c->epa_count, 0, sizeof(int), s));
@@ -97,11 +99,30 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s) {
   if (!io.witness) io.witness = c->col_wit;
   static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 128; return t >= 32 && t <= 128 ? t : 128; }();
   const int blocks = (io.B + threads - 1) / threads;
-  k_collision<NV, CHAIN><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  // resident blocks/SM the kernel is compiled for (register cap); tunable for experiments on the FR3 shape
+  static const int minb = [] { const char* e = getenv("DRC_COL_MINB"); return e ? atoi(e) : 2; }();
+  if (NV == 7 && minb == 3) k_collision<NV, CHAIN, (NV == 7 ? 3 : 2)><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  else if (NV == 7 && minb >= 4) k_collision<NV, CHAIN, (NV == 7 ? 4 : 2)><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  else k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
-  k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, s>>>(c->model->hm.dev, c->prm, io);
+  // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it
+  // on the side stream, concurrently with the state / QP-build kernel (disjoint parts of the QP record), and join
+  // before the ADMM launch (join_epa).
+  cudaStream_t es = s;
+  if (epa_on_side_stream) {
+    CU(cudaEventRecord(c->ev_col, s));
+    CU(cudaStreamWaitEvent(c->side, c->ev_col, 0));
+    es = c->side;
+  }
+  k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, es>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
+  if (epa_on_side_stream) CU(cudaEventRecord(c->ev_epa, c->side));
   c->launches += 2;
+  return DRC_OK;
+}
+
+static int join_epa(drc_ctx* c, cudaStream_t s) {
+  CU(cudaStreamWaitEvent(s, c->ev_epa, 0));
   return DRC_OK;
 }
 

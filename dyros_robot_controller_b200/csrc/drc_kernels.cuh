@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcMo
   if (b < io.B) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
 }
 
-template <int NV, bool CHAIN>
-__global__ void __launch_bounds__(128) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+template <int NV, bool CHAIN, int MINB = 2>
+__global__ void __launch_bounds__(128, MINB) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ CollisionIO io) {
   // stage the geometry table in shared memory: the GJK pass indexes it with per-thread pair ids
   __shared__ GeomTable G;

@@ -27,6 +27,17 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (c->timing) cudaEventRecord(c->ev[0], s);
   int rc;
   const bool fused = q != nullptr;
+  // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; its EPA pass goes to the side stream
+  if (fused) { rc = launch_job<NV, CHAIN, F_STORE>(c, fr, io, s); if (rc) return rc; }
+  CollisionIO cio;
+  std::memset(&cio, 0, sizeof cio);
+  cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp;
+  cio.qp_stride = id ? QpidCfg<NV>::STRIDE : QpikCfg<NV>::STRIDE;
+  cio.qp_row_off = (id ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (NV + 1);
+  rc = launch_collision<NV, CHAIN>(c, cio, s, true);
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[1], s);
+  // stage 2 (next to the EPA pass): state update, manipulability, QP record except the self-collision row
 #define J(FL) launch_job<NV, CHAIN, FL>(c, fr, io, s)
   if (!id) {
     if (fused) rc = step ? J(F_DYN | F_STORE | F_QPIK | F_STEP) : J(F_DYN | F_STORE | F_QPIK);
@@ -37,13 +48,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   }
 #undef J
   if (rc) return rc;
-  if (c->timing) cudaEventRecord(c->ev[1], s);
-  CollisionIO cio;
-  std::memset(&cio, 0, sizeof cio);
-  cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp;
-  cio.qp_stride = id ? QpidCfg<NV>::STRIDE : QpikCfg<NV>::STRIDE;
-  cio.qp_row_off = (id ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (NV + 1);
-  rc = launch_collision<NV, CHAIN>(c, cio, s);
+  rc = join_epa(c, s);
   if (rc) return rc;
   if (c->timing) cudaEventRecord(c->ev[2], s);
   SolveIO sio;
@@ -148,6 +153,9 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   const int n = m->hm.dev.nv;
   const size_t B = (size_t)max_batch;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming));
   auto dalloc = [&](double** p, size_t cnt) { return cudaMalloc((void**)p, cnt * sizeof(double)); };
   CU(dalloc(&c->c_q, n * B)); CU(dalloc(&c->c_qd, n * B)); CU(dalloc(&c->c_oMi, 12 * n * B));
   CU(dalloc(&c->c_M, n * n * B)); CU(dalloc(&c->c_Minv, n * n * B)); CU(dalloc(&c->c_g, n * B)); CU(dalloc(&c->c_nle, n * B));
@@ -202,6 +210,9 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->sched_hist) cudaFree(c->sched_hist);
   if (c->stage_i) cudaFree(c->stage_i);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->ev_col) cudaEventDestroy(c->ev_col);
+  if (c->ev_epa) cudaEventDestroy(c->ev_epa);
+  if (c->side) cudaStreamDestroy(c->side);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -243,6 +254,7 @@ int drc_ctx_synchronize(drc_ctx_t* c) {
   if (!c) return fail(DRC_E_INVALID, "null context");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->side));
   return DRC_OK;
 }
 void* drc_ctx_stream(drc_ctx_t* c) { return c ? (void*)c->stream : nullptr; }

@@ -53,16 +53,22 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   bind_cache(c, io);
   const DrcFrame fr = frame_of(c->model, frame);
   if (c->timing) cudaEventRecord(c->ev[0], s);
-  int rc = id ? launch_job<NV, false, K_ID, W>(c, fr, io, s) : launch_job<NV, false, K_IK, W>(c, fr, io, s);
-  if (rc) return rc;
-  if (c->timing) cudaEventRecord(c->ev[1], s);
+  // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; EPA pass on the side stream
+  int rc = DRC_OK;
+  if (q) { rc = launch_job<NV, false, F_STORE>(c, fr, io, s); if (rc) return rc; }
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp;
   cio.qp_stride = id ? MomaIdCfg<ACT>::STRIDE : MomaIkCfg<ACT>::STRIDE;
   cio.qp_row_off = (id ? MomaIdCfg<ACT>::OFF_ROW : MomaIkCfg<ACT>::OFF_ROW) + (ACT + 1);
   cio.row_n = ACT; cio.row_col0 = d.act_mani_start; cio.src0 = d.mani_start; cio.nsrc = MANI;
-  rc = launch_collision<NV, false>(c, cio, s);
+  rc = launch_collision<NV, false>(c, cio, s, true);
+  if (rc) return rc;
+  if (c->timing) cudaEventRecord(c->ev[1], s);
+  // stage 2 (next to the EPA pass): whole-body state update and QP record except the self-collision row
+  rc = id ? launch_job<NV, false, K_ID, W>(c, fr, io, s) : launch_job<NV, false, K_IK, W>(c, fr, io, s);
+  if (rc) return rc;
+  rc = join_epa(c, s);
   if (rc) return rc;
   if (c->timing) cudaEventRecord(c->ev[2], s);
   SolveIO sio;

@@ -153,7 +153,7 @@ class Context:
     def last_timing(self):
         ms = (C.c_float * 4)()
         check(lib().drc_ctx_last_timing(self._h, ms), "drc_ctx_last_timing")
-        return dict(build_ms=ms[0], collision_ms=ms[1], admm_ms=ms[2], total_ms=ms[3])
+        return dict(collision_ms=ms[0], build_ms=ms[1], admm_ms=ms[2], total_ms=ms[3])
 
     @property
     def launch_count(self) -> int:

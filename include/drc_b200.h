@@ -229,7 +229,8 @@ int drc_host_moma_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const do
 
 /* ---- instrumentation (replaces QP::TimeDuration / SuhanBenchmark, QP_base.h:19-43) */
 /* device time in ms of the stages of the LAST cycle/QP call on this context (CUDA events on its stream):
- * [0] state/QP build  [1] self-collision  [2] ADMM solve  [3] total; requires drc_ctx_enable_timing(c,1) */
+ * [0] joint placements + self-collision narrow phase  [1] state / QP build (EPA pass of the collision stage runs next to
+ * it on a side stream)  [2] ADMM solve  [3] total; requires drc_ctx_enable_timing(c,1) */
 int drc_ctx_enable_timing(drc_ctx_t* c, int on);
 int drc_ctx_last_timing(drc_ctx_t* c, float* ms4);
 /* number of kernels this library launched on the context since creation */

@@ -10,8 +10,11 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_bench.log 2>&1
 for k in k_admm k_collision k_robot_job; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" -c 1 -f -o gpurun_out/${tag}_${k} \
-    python tools/prof_cycle.py 65536 1 > gpurun_out/${tag}_ncu_${k}.log 2>&1
+  # second control tick: the ADMM schedule then has the previous tick's iteration counts (k_robot_job: skip the two
+  # state-update launches of the set-up and the first tick)
+  skip=1; [ "$k" = "k_robot_job" ] && skip=3
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip -c 1 -f -o gpurun_out/${tag}_${k} \
+    python tools/prof_cycle.py 65536 2 > gpurun_out/${tag}_ncu_${k}.log 2>&1
   # gpurun_out/ is capped at 64 MiB: keep the CSV pages, drop the report
   ncu -i gpurun_out/${tag}_${k}.ncu-rep --page raw --csv > gpurun_out/${tag}_${k}_raw.csv 2>/dev/null
   ncu -i gpurun_out/${tag}_${k}.ncu-rep --page source --csv > gpurun_out/${tag}_${k}_src.csv 2>/dev/null
