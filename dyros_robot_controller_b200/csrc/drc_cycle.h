@@ -52,6 +52,9 @@ struct JobIO {
   double* out; Strided sout;                // n per robot (CLIK qdot / OSF torque / PD torque)
   double* out2;                             // OSF torque when CLIK and OSF run in one launch (same layout)
   double* qp;                               // QP records (AoS, Cfg::STRIDE doubles per robot)
+  // priority sub-batch (robots predicted to need many ADMM iterations, see run_qp): slot b of the cache / QP scratch
+  // holds robot ids[b] of the INPUT arrays; *count slots are in use (null = identity / io.B)
+  const int* ids; const int* count;
 };
 
 template <int NV>
@@ -91,11 +94,12 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   // mobile-manipulator jobs pick the state source and the task signal at run time (fewer heavy instantiations)
   const bool from_cache = (FLAGS & F_FROM_CACHE) || (MOMA && io.q == nullptr);
   const bool step = (FLAGS & F_STEP) || (MOMA && io.x_target != nullptr);
+  const long long bi = io.ids ? io.ids[b] : b;  // robot index in the input arrays (b indexes cache / QP scratch)
   double q[NV], qd[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (from_cache) { q[i] = io.c_q[i * io.Bc + b]; qd[i] = io.c_qd[i * io.Bc + b]; }
-    else { q[i] = io.q[b * io.sq.sb + i * io.sq.sk]; qd[i] = io.qd[b * io.sqd.sb + i * io.sqd.sk]; }
+    else { q[i] = io.q[bi * io.sq.sb + i * io.sq.sk]; qd[i] = io.qd[bi * io.sqd.sb + i * io.sqd.sk]; }
   }
   KinState<NV> k;
   k.origin = v3(0, 0, 0);
@@ -272,17 +276,17 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   if (FLAGS & (F_QPIK | F_QPID | F_CLIK | F_OSF)) {
     double xd_t[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) xd_t[r] = io.xdot_target[b * io.sxd.sb + r * io.sxd.sk];
+    for (int r = 0; r < 6; ++r) xd_t[r] = io.xdot_target[bi * io.sxd.sb + r * io.sxd.sk];
     if (step) {
       Mat3 Rt;
       Vec3 pt;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) Rt.m[3 * r + c] = io.x_target[b * io.sxt.sb + (4 * r + c) * io.sxt.sk];
+        for (int c = 0; c < 3; ++c) Rt.m[3 * r + c] = io.x_target[bi * io.sxt.sb + (4 * r + c) * io.sxt.sk];
       }
-      pt = v3(io.x_target[b * io.sxt.sb + 3 * io.sxt.sk], io.x_target[b * io.sxt.sb + 7 * io.sxt.sk],
-              io.x_target[b * io.sxt.sb + 11 * io.sxt.sk]);
+      pt = v3(io.x_target[bi * io.sxt.sb + 3 * io.sxt.sk], io.x_target[bi * io.sxt.sb + 7 * io.sxt.sk],
+              io.x_target[bi * io.sxt.sb + 11 * io.sxt.sk]);
       const Vec3 ep = pt - pf, eo = orientation_error(Rt, Rf);
       const double xe[6] = {ep.x, ep.y, ep.z, eo.x, eo.y, eo.z};
 #pragma unroll
@@ -468,6 +472,7 @@ struct CollisionIO {
   int* epa_flag;                     // per robot: number of overlapping GJK pairs still to resolve
   unsigned long long* cand_mask;     // per robot: bit i = GJK-type pair i must be resolved by EPA
   int* epa_list; int* epa_count;     // compacted list of flagged robots (device: atomic append), may be null
+  const int* count;                  // number of slots in use (device memory; null = B)
 };
 
 struct JointFrame {
@@ -725,14 +730,18 @@ struct SolveIO {
   double* qp_x;                 // optional debug: [core x (NC) | unit slacks (KU*NC) | row singletons (NR)] per robot
   const int* order;             // optional schedule: the i-th solver group takes robot order[i] (null = identity)
   int* iters_hint;              // optional: iteration count of every robot, kept by the context for the next tick's schedule
+  const int* order_off;         // optional (device): skip the first *order_off entries of `order` (they run in the priority launch)
+  const int* out_ids;           // optional: outputs / hints of QP slot i go to robot out_ids[i] (priority launch: records are compact)
+  const int* count;             // optional (device): number of slots (null = B)
 };
 
 template <class Cfg, bool ID, class W>
 DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpOptions& o) {
   admm_solve<Cfg>(w, io.qp, robots, o);
   w.each([&](Lane<Cfg>& L, GroupShared<Cfg>& S) {
-    const int b = S.robot;
-    if (b < 0) return;
+    const int slot = S.robot;  // index of the QP record / state-cache entry
+    if (slot < 0) return;
+    const long long b = io.out_ids ? io.out_ids[slot] : slot;  // robot index in the output arrays
     const bool ok = S.status == kQpSolved;
     if (L.gl == 0) {
       if (io.status) io.status[b] = S.status;
@@ -755,7 +764,7 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
       const int r = L.gl - Cfg::NC;
       if (ID && r >= Cfg::ND) {
         const int j = r - Cfg::ND;
-        io.out[b * io.sout.sb + j * io.sout.sk] = ok ? C.Dd[0] * L.b[0].xd : io.c_g[j * io.Bc + b];
+        io.out[b * io.sout.sb + j * io.sout.sk] = ok ? C.Dd[0] * L.b[0].xd : io.c_g[j * io.Bc + slot];
       }
       if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = C.has_sing[0] ? C.Dd[0] * L.b[0].xd : 0.0;
     }

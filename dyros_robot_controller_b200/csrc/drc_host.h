@@ -30,6 +30,19 @@ struct drc_model {
   std::string verbose;
 };
 
+// State cache + QP / collision scratch of one pipeline.  The context owns two: the full batch and a small compact one
+// for the priority sub-batch (robots predicted to need many ADMM iterations; run_qp in drc_lib.cu).
+struct Scratch {
+  double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
+  long long Bc;
+  double* qp;
+  int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
+  int* epa_list; int* epa_count;
+};
+constexpr int kPrioSlots = 2048;        // capacity of the priority sub-batch
+constexpr int kPrioMinBatch = 8192;     // batches below this run as one pipeline
+constexpr int kPrioIters = 300;         // previous-tick iteration count from which a robot is "slow"
+
 struct drc_ctx {
   const drc_model* model;
   int device, cap;
@@ -46,6 +59,10 @@ struct drc_ctx {
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
+  int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
+  Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
+  cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
+  cudaEvent_t ev_sched, ev_prio;
   int sm_count;
   // device staging for host entry points
   double* stage; size_t stage_doubles;
@@ -66,6 +83,17 @@ static DrcFrame frame_of(const drc_model* m, int fid) {
 }
 static Strided lay(int layout, int K, int B) { return layout == DRC_LAYOUT_SOA ? soa(B) : aos(K); }
 
+static Scratch main_scratch(const drc_ctx* c) {
+  Scratch sc;
+  sc.c_q = c->c_q; sc.c_qd = c->c_qd; sc.c_oMi = c->c_oMi; sc.c_M = c->c_M; sc.c_Minv = c->c_Minv; sc.c_g = c->c_g; sc.c_nle = c->c_nle;
+  sc.Bc = c->cap; sc.qp = c->qp; sc.epa_flag = c->epa_flag; sc.cand_mask = c->cand_mask; sc.col_dist = c->col_dist;
+  sc.col_pair = c->col_pair; sc.col_wit = c->col_wit; sc.epa_list = c->epa_list; sc.epa_count = c->epa_count;
+  return sc;
+}
+static void bind_scratch(const Scratch& sc, JobIO& io) {
+  io.c_q = sc.c_q; io.c_qd = sc.c_qd; io.c_oMi = sc.c_oMi; io.c_M = sc.c_M; io.c_Minv = sc.c_Minv; io.c_g = sc.c_g;
+  io.c_nle = sc.c_nle; io.Bc = sc.Bc; io.qp = sc.qp;
+}
 static void bind_cache(const drc_ctx* c, JobIO& io) {
   io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.c_M = c->c_M; io.c_Minv = c->c_Minv; io.c_g = c->c_g;
   io.c_nle = c->c_nle; io.Bc = c->cap;
@@ -90,13 +118,14 @@ static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStrea
 }
 
 template <int NV, bool CHAIN>
-static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa_on_side_stream = false) {
-  io.c_q = c->c_q; io.c_qd = c->c_qd; io.c_oMi = c->c_oMi; io.Bc = c->cap;
-  io.epa_flag = c->epa_flag; io.cand_mask = c->cand_mask; io.epa_list = c->epa_list; io.epa_count = c->epa_count;
-  CU(cudaMemsetAsync(c->epa_count, 0, sizeof(int), s));
-  if (!io.dist) io.dist = c->col_dist;
-  if (!io.pair_out) io.pair_out = c->col_pair;
-  if (!io.witness) io.witness = c->col_wit;
+static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa_on_side_stream = false, const Scratch* scp = nullptr) {
+  const Scratch sc = scp ? *scp : main_scratch(c);
+  io.c_q = sc.c_q; io.c_qd = sc.c_qd; io.c_oMi = sc.c_oMi; io.Bc = sc.Bc;
+  io.epa_flag = sc.epa_flag; io.cand_mask = sc.cand_mask; io.epa_list = sc.epa_list; io.epa_count = sc.epa_count;
+  CU(cudaMemsetAsync(sc.epa_count, 0, sizeof(int), s));
+  if (!io.dist) io.dist = sc.col_dist;
+  if (!io.pair_out) io.pair_out = sc.col_pair;
+  if (!io.witness) io.witness = sc.col_wit;
   static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 128; return t >= 32 && t <= 128 ? t : 128; }();
   const int blocks = (io.B + threads - 1) / threads;
   // resident blocks/SM the kernel is compiled for (register cap); tunable for experiments on the FR3 shape
@@ -114,7 +143,8 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
     CU(cudaStreamWaitEvent(c->side, c->ev_col, 0));
     es = c->side;
   }
-  k_collision_epa<NV, CHAIN><<<c->sm_count, kEpaWarps * 32, 0, es>>>(c->model->hm.dev, c->prm, io);
+  const int epa_blocks = scp ? 16 : c->sm_count;
+  k_collision_epa<NV, CHAIN><<<epa_blocks, kEpaWarps * 32, 0, es>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
   if (epa_on_side_stream) CU(cudaEventRecord(c->ev_epa, c->side));
   c->launches += 2;
@@ -126,24 +156,30 @@ static int join_epa(drc_ctx* c, cudaStream_t s) {
   return DRC_OK;
 }
 
+// ADMM schedule from the previous tick's iteration counts (k_sched_* in drc_kernels.cuh): c->order = robots by descending
+// count, *c->slow_count = how many of them reached kPrioIters (at most kPrioSlots).  Results do not depend on it.
+static int launch_schedule(drc_ctx* c, int B, cudaStream_t s) {
+  CU(cudaMemsetAsync(c->sched_hist, 0, kSchedBuckets * sizeof(int), s));
+  CU(cudaMemsetAsync(c->slow_count, 0, sizeof(int), s));
+  const int tb = 256, nb = (B + tb - 1) / tb;
+  k_sched_hist<<<nb < 1024 ? nb : 1024, tb, 0, s>>>(c->prev_iters, B, c->sched_hist);
+  k_sched_scan<<<1, kSchedBuckets, 0, s>>>(c->sched_hist, kPrioIters, kPrioSlots, c->slow_count);
+  k_sched_scatter<<<nb, tb, 0, s>>>(c->prev_iters, B, c->sched_hist, c->order);
+  c->launches += 3;
+  CU(cudaGetLastError());
+  return DRC_OK;
+}
+
+// io.B = slots to cover; io.order / order_off / out_ids / count select them (see SolveIO)
 template <class Cfg, bool ID>
-static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask = (1u << Cfg::NC) - 1u, const double* gravity = nullptr) {
-  io.qp = c->qp; io.c_g = gravity ? gravity : c->c_g; io.Bc = c->cap;
+static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask = (1u << Cfg::NC) - 1u, const double* gravity = nullptr,
+                       const Scratch* scp = nullptr) {
+  io.qp = scp ? scp->qp : c->qp;
+  io.c_g = gravity ? gravity : (scp ? scp->c_g : c->c_g);
+  io.Bc = scp ? scp->Bc : c->cap;
   const QpOptions o = qp_options(c->prm, unit_mask);
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
-  // schedule from the previous tick's iteration counts (see k_sched_* in drc_kernels.cuh); results do not depend on it
   io.iters_hint = c->prev_iters;
-  io.order = nullptr;
-  if (c->prm.schedule_hint && io.B >= 4 * per_block) {
-    CU(cudaMemsetAsync(c->sched_hist, 0, kSchedBuckets * sizeof(int), s));
-    const int tb = 256, nb = (io.B + tb - 1) / tb;
-    k_sched_hist<<<nb < 1024 ? nb : 1024, tb, 0, s>>>(c->prev_iters, io.B, c->sched_hist);
-    k_sched_scan<<<1, kSchedBuckets, 0, s>>>(c->sched_hist);
-    k_sched_scatter<<<nb, tb, 0, s>>>(c->prev_iters, io.B, c->sched_hist, c->order);
-    c->launches += 3;
-    CU(cudaGetLastError());
-    io.order = c->order;
-  }
   // blocks/SM the kernel is compiled for (register cap 65536 / (128 * MINB)); tunable for experiments
   static const int minb = [] { const char* e = getenv("DRC_ADMM_MINB"); return e ? atoi(e) : 3; }();
   constexpr size_t smem = sizeof(GroupShared<Cfg>) * kAdmmWarps * Cfg::NG;

@@ -21,7 +21,7 @@ template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 __global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ DrcFrame frame, const __grid_constant__ JobIO io) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
+  if (b < io.B && (!io.count || b < *io.count)) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
 }
 
 template <int NV, bool CHAIN, int MINB = 2>
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128, MINB) k_collision(const __grid_constant__
   }
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) collision_job<NV, CHAIN>(m, G, prm, io, b);
+  if (b < io.B && (!io.count || b < *io.count)) collision_job<NV, CHAIN>(m, G, prm, io, b);
 }
 // ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar
 // epa_penetration (drc_geom.h: flood-fill horizon, uncommitted bad expansions, slot policy); the polytope lives in
@@ -214,11 +214,14 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, 4 * MINB) k_admm(const __grid
   extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
   GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int first = (blockIdx.x * kAdmmWarps + warp) * Cfg::NG;
-  if (first >= io.B) return;  // no block-level barrier below: idle warps may leave
+  // slots of this warp: entries [off + first, off + first + NG) of `order` (or the identity), below the slot count
+  const int off = io.order_off ? *io.order_off : 0;
+  const int nslot = io.count ? (*io.count < io.B ? *io.count : io.B) : io.B;
+  const int first = off + (blockIdx.x * kAdmmWarps + warp) * Cfg::NG;
+  if (first >= nslot) return;  // no block-level barrier below: idle warps may leave
   int robots[Cfg::NG];
 #pragma unroll
-  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < io.B ? (io.order ? io.order[first + g] : first + g) : -1;
+  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < nslot ? (io.order ? io.order[first + g] : first + g) : -1;
   WarpExec<Cfg> w;
   w.sh = sh + warp * Cfg::NG;
   w.lane = lane;
@@ -245,7 +248,7 @@ static __global__ void k_sched_hist(const int* prev, int B, int* hist) {
   __syncthreads();
   for (int i = threadIdx.x; i < kSchedBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
 }
-static __global__ void k_sched_scan(int* hist) {  // one block of kSchedBuckets threads: exclusive prefix sum in place
+static __global__ void k_sched_scan(int* hist, int slow_iters, int slow_max, int* slow_count) {  // one block of kSchedBuckets threads: exclusive prefix sum in place
   __shared__ int a[kSchedBuckets];
   const int t = threadIdx.x;
   a[t] = hist[t];
@@ -257,6 +260,8 @@ static __global__ void k_sched_scan(int* hist) {  // one block of kSchedBuckets 
     __syncthreads();
   }
   hist[t] = a[t] - hist[t];
+  // robots whose previous count reached slow_iters sort in front of bucket(slow_iters - 1)'s first entry: the priority launch
+  if (slow_count && t == sched_bucket(slow_iters - 1)) *slow_count = hist[t] < slow_max ? hist[t] : slow_max;
 }
 static __global__ void k_sched_scatter(const int* prev, int B, int* offs, int* order) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

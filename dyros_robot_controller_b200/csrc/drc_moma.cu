@@ -53,8 +53,10 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   bind_cache(c, io);
   const DrcFrame fr = frame_of(c->model, frame);
   if (c->timing) cudaEventRecord(c->ev[0], s);
-  // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; EPA pass on the side stream
   int rc = DRC_OK;
+  const bool sched = c->prm.schedule_hint != 0 && B >= 64;
+  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; }
+  // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; EPA pass on the side stream
   if (q) { rc = launch_job<NV, false, F_STORE>(c, fr, io, s); if (rc) return rc; }
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
@@ -74,6 +76,7 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.out = out; sio.sout = lay(layout, ACT, B); sio.out2 = out2; sio.sout2 = sio.sout; sio.status = status; sio.iters = iters;
+  if (sched) sio.order = c->order;
   const unsigned mani_mask = ((1u << MANI) - 1u) << d.act_mani_start;   // CBF unit rows exist on manipulator joints only
   rc = id ? launch_admm<MomaIdCfg<ACT>, true>(c, sio, s, mani_mask, c->c_gact) : launch_admm<MomaIkCfg<ACT>, false>(c, sio, s, mani_mask, c->c_gact);
   if (c->timing) cudaEventRecord(c->ev[3], s);
