@@ -262,6 +262,8 @@ def run_ours(args):
     ctx = drc.Context(model, B, device=local)
     if os.environ.get("DRC_DEBUG_MAX_ITER"):  # experiment knob (tail analysis); never set for a reported number
         ctx.set_params(max_iter=int(os.environ["DRC_DEBUG_MAX_ITER"]))
+    if os.environ.get("DRC_DEBUG_EPS"):       # experiment knob: force every robot to max_iter (lone-warp latency measurement)
+        ctx.set_params(eps_abs=float(os.environ["DRC_DEBUG_EPS"]), eps_rel=float(os.environ["DRC_DEBUG_EPS"]))
     # each rank owns an independent shard of the batch (no exchange on the solve path)
     if moma:
         q, qd, q_t, xdot_t = make_moma_workload(model.q_lower, model.q_upper, model.v_limit, md["w"], B, seed=1000 * rank)

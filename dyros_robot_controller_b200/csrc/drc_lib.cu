@@ -49,8 +49,9 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     return step ? J(F_FROM_CACHE | F_QPID | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPID, jio, st);
   };
 
-  if (prio) {  // ---- priority pipeline: slots 0..*slow_count-1 of the compact scratch hold robots order[0..]
+  if (prio) {
     CU(cudaEventRecord(c->ev_sched, s));
+    // ---- priority pipeline: slots [0, *slow_count) of the compact scratch hold robots order[slot]
     CU(cudaStreamWaitEvent(c->prio_stream, c->ev_sched, 0));
     cudaStream_t ps = c->prio_stream;
     JobIO pio = io;
@@ -59,7 +60,8 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     rc = J(F_STORE, pio, ps); if (rc) return rc;
     CollisionIO pc;
     std::memset(&pc, 0, sizeof pc);
-    pc.B = kPrioSlots; pc.mode = id ? 2 : 1; pc.qp = c->prio.qp; pc.qp_stride = qp_stride; pc.qp_row_off = qp_row_off; pc.count = c->slow_count;
+    pc.B = kPrioSlots; pc.mode = id ? 2 : 1; pc.qp = c->prio.qp; pc.qp_stride = qp_stride; pc.qp_row_off = qp_row_off;
+    pc.count = c->slow_count;
     rc = launch_collision<NV, CHAIN>(c, pc, ps, false, &c->prio); if (rc) return rc;
     rc = build(pio, ps); if (rc) return rc;
     SolveIO ps_io;
@@ -222,20 +224,22 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   CU(cudaMalloc((void**)&c->sched_hist, kSchedBuckets * sizeof(int)));
   CU(cudaMalloc((void**)&c->slow_count, sizeof(int)));
   CU(cudaMemset(c->slow_count, 0, sizeof(int)));
-  {  // compact scratch of the priority pipeline
-    Scratch& p = c->prio;
-    const size_t P = kPrioSlots;
-    p.Bc = kPrioSlots;
-    CU(dalloc(&p.c_q, n * P)); CU(dalloc(&p.c_qd, n * P)); CU(dalloc(&p.c_oMi, 12 * n * P)); CU(dalloc(&p.c_M, n * n * P));
-    CU(dalloc(&p.c_Minv, n * n * P)); CU(dalloc(&p.c_g, n * P)); CU(dalloc(&p.c_nle, n * P));
-    CU(dalloc(&p.qp, (size_t)stride_id * P));
-    CU(cudaMalloc((void**)&p.epa_flag, P * sizeof(int)));
-    CU(cudaMalloc((void**)&p.cand_mask, P * sizeof(unsigned long long)));
-    CU(dalloc(&p.col_dist, P));
-    CU(cudaMalloc((void**)&p.col_pair, P * sizeof(int)));
-    CU(dalloc(&p.col_wit, 6 * P));
-    CU(cudaMalloc((void**)&p.epa_list, P * sizeof(int)));
-    CU(cudaMalloc((void**)&p.epa_count, sizeof(int)));
+  {  // compact scratch of the priority pipeline and of the single-kernel cycle of the slowest robots
+    auto alloc_scratch = [&](Scratch& p, size_t P) -> int {
+      p.Bc = (long long)P;
+      CU(dalloc(&p.c_q, n * P)); CU(dalloc(&p.c_qd, n * P)); CU(dalloc(&p.c_oMi, 12 * n * P)); CU(dalloc(&p.c_M, n * n * P));
+      CU(dalloc(&p.c_Minv, n * n * P)); CU(dalloc(&p.c_g, n * P)); CU(dalloc(&p.c_nle, n * P));
+      CU(dalloc(&p.qp, (size_t)stride_id * P));
+      CU(cudaMalloc((void**)&p.epa_flag, P * sizeof(int)));
+      CU(cudaMalloc((void**)&p.cand_mask, P * sizeof(unsigned long long)));
+      CU(dalloc(&p.col_dist, P));
+      CU(cudaMalloc((void**)&p.col_pair, P * sizeof(int)));
+      CU(dalloc(&p.col_wit, 6 * P));
+      CU(cudaMalloc((void**)&p.epa_list, P * sizeof(int)));
+      CU(cudaMalloc((void**)&p.epa_count, sizeof(int)));
+      return DRC_OK;
+    };
+    int arc = alloc_scratch(c->prio, kPrioSlots); if (arc) return arc;
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi));
@@ -273,10 +277,12 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->sched_hist) cudaFree(c->sched_hist);
   if (c->slow_count) cudaFree(c->slow_count);
   {
-    Scratch& p = c->prio;
-    void* ps[] = {p.c_q, p.c_qd, p.c_oMi, p.c_M, p.c_Minv, p.c_g, p.c_nle, p.qp, p.epa_flag, p.cand_mask, p.col_dist, p.col_pair, p.col_wit,
-                  p.epa_list, p.epa_count};
-    for (void* q : ps) if (q) cudaFree(q);
+    for (Scratch* sp : {&c->prio}) {
+      Scratch& p = *sp;
+      void* ps[] = {p.c_q, p.c_qd, p.c_oMi, p.c_M, p.c_Minv, p.c_g, p.c_nle, p.qp, p.epa_flag, p.cand_mask, p.col_dist, p.col_pair, p.col_wit,
+                    p.epa_list, p.epa_count};
+      for (void* q : ps) if (q) cudaFree(q);
+    }
     if (c->prio_stream) { cudaStreamSynchronize(c->prio_stream); cudaStreamDestroy(c->prio_stream); }
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
     if (c->ev_prio) cudaEventDestroy(c->ev_prio);
