@@ -397,7 +397,11 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_achieved = BYTES_PER_CYCLE * B / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "fp64", "kernel": "k_admm" + ("<QpCfg<7,2,2,0>>" if args.workload == "fr3_qpik" else ""), "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved is not None else None, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved is not None else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one k_admm launch at this batch from the ncu --set full capture
+                # (profiles/r01_ncu_summary_v3_scheduled.md: 42.66 MB + 0.28 MB); algorithmic: 632 B record + 64 B result per robot
+                "traffic": 42.94e6 if (args.workload == "fr3_qpik" and B == 65536) else None,
+                "traffic_algorithmic": (632.0 + 64.0) * B if args.workload == "fr3_qpik" else None,
                 "peak_source": peak_src,
                 "kernel_ms": admm_ms, "kernel_share_of_step": admm_ms / ms_per_step,
                 "stage_ms": {"state_and_qp_build": build_ms, "self_collision": col_ms, "admm": admm_ms},
@@ -407,6 +411,8 @@ def run_ours(args):
     cores = os.cpu_count() or 1
     sample = min(B, 32768)
     cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores, workload=args.workload)
+    # the reference's control loop is single-threaded (one controller instance per control thread): one-thread rate on a smaller sample
+    cpu1_val, cpu1_dt, _ = oracle_cycles_per_s(min(sample, 4096), 1, workload=args.workload)
     line = {"metric": METRIC if args.workload == "fr3_qpik" else f"batched control cycles/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -422,7 +428,10 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} cycles of the same workload, one pass, OpenMP over {cores} host threads "
-                                       f"({cpu_dt:.2f} s)"},
+                                       f"({cpu_dt:.2f} s)",
+                             "single_thread": {"value": cpu1_val, "cores": 1,
+                                               "sample": f"{min(sample, 4096)} cycles, one thread ({cpu1_dt:.2f} s); the reference's "
+                                                         "control loop is single-threaded"}},
             "solved_fraction": float(np.mean(status == 1)), "mean_admm_iters": float(np.mean(iters))}
     print(json.dumps(line), flush=True)
     if dist is not None:

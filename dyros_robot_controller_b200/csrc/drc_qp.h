@@ -86,8 +86,7 @@ struct BundleHot {
   double v, vb;  // row state, singleton-bound-row state
   double xd;     // singleton value (scaled)
   double e, qd, beta, l;  // singleton coefficient in the row, its cost, its bound-row coefficient, row lower bound
-  double kinv;            // 1/kappa of the eliminated singleton
-  double er, bb, cr, cg;  // pre-multiplied loop constants: e rho_row, beta rho_sb, c rho_row, c gamma (gamma = rho_row e / kappa)
+  double kinv, gam;       // 1/kappa, rho e / kappa
   double pz, pzb, bd;     // scratch carried from phase A to phase B
 };
 
@@ -99,7 +98,6 @@ struct Lane {
   bool row_eq;            // this lane's bundle rows are equalities  (projection onto {l})
   bool sb_free;           // this lane's singleton bound rows are (-inf, inf)
   double x, vc, q, betac, lc, uc, rhoc;  // core variable and its bound row
-  double brc;             // betac * rhoc
   double sig, al;         // sigma / alpha on core lanes, 0 on row lanes
   double rho_r, rho_b;    // rho of this lane's bundle rows / singleton bound rows
   double pzc;             // scratch
@@ -216,7 +214,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       for (int j = 0; j < NC; ++j) na += (int)((o.unit_mask >> j) & 1u);
       S.nx = NC + (Cfg::SLACK ? na * KU + ND : 0) + Cfg::NE;
     }
-    L.x = 0; L.vc = 0; L.q = 0; L.betac = 0; L.lc = -kOsqpInfty; L.uc = kOsqpInfty; L.rhoc = 0; L.brc = 0;
+    L.x = 0; L.vc = 0; L.q = 0; L.betac = 0; L.lc = -kOsqpInfty; L.uc = kOsqpInfty; L.rhoc = 0;
     L.sig = L.is_core ? sigma : 0.0; L.al = L.is_core ? alpha : 0.0;
     L.rho_r = 0; L.rho_b = 0; L.pzc = 0; L.et = 1.0;
     L.row_eq = false; L.sb_free = false; L.done = rb < 0;
@@ -224,7 +222,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
-      b.c = 0; b.v = 0; b.vb = 0; b.xd = 0; b.e = 0; b.qd = 0; b.beta = 0; b.l = -kOsqpInfty; b.kinv = 0; b.er = 0; b.bb = 0; b.cr = 0; b.cg = 0;
+      b.c = 0; b.v = 0; b.vb = 0; b.xd = 0; b.e = 0; b.qd = 0; b.beta = 0; b.l = -kOsqpInfty; b.kinv = 0; b.gam = 0;
       b.pz = 0; b.pzb = 0; b.bd = 0;
       C.E[k] = 1; C.Eb[k] = 1; C.Dd[k] = 1; C.dxd[k] = 0; C.dy[k] = 0; C.dyb[k] = 0; C.cls[k] = 0; C.clsb[k] = 0;
       C.active[k] = 0; C.has_sing[k] = 0; C.has_sb[k] = 0;
@@ -392,7 +390,6 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         const double rn = class_rho(C.clsc, rho);
         if (C.clsc >= 0) { const double pz = clampd(L.vc, L.lc, L.uc); L.vc = pz + ratio * (L.vc - pz); }
         L.rhoc = rn;
-        L.brc = L.betac * rn;
         diag += rn * L.betac * L.betac;
       }
 #pragma unroll
@@ -402,20 +399,19 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         const double rr = class_rho(C.cls[k], rho);
         if (C.cls[k] >= 0) { const double pz = proj_row(L, b.v, b.l); b.v = pz + ratio * (b.v - pz); }
         L.rho_r = rr;
-        double omega = rr, gam = 0.0, rbv = 0.0;
+        double omega = rr;
         if (C.has_sing[k]) {
           double kap = sigma + rr * b.e * b.e;
           if (C.has_sb[k]) {
-            rbv = class_rho(C.clsb[k], rho);
+            const double rbv = class_rho(C.clsb[k], rho);
             if (C.clsb[k] >= 0) { const double pz = proj_sb(L, b.vb); b.vb = pz + ratio * (b.vb - pz); }
             L.rho_b = rbv;
             kap += rbv * b.beta * b.beta;
           }
           b.kinv = 1.0 / kap;
-          gam = rr * b.e * b.kinv;
-          omega = rr * (1.0 - gam * b.e);
+          b.gam = rr * b.e * b.kinv;
+          omega = rr * (1.0 - b.gam * b.e);
         }
-        b.er = b.e * rr; b.bb = b.beta * rbv; b.cr = b.c * rr; b.cg = b.c * gam;
         if (L.is_core) diag += omega * b.c * b.c;
         else omega0 = omega;
       }
@@ -510,16 +506,15 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     if (L.done) return;
     const double pzc = first ? 0.0 : clampd(L.vc, L.lc, L.uc);
     L.pzc = pzc;
-    // rho z - y = rho (2 Proj(v) - v); the row multipliers are folded into er / bb / cr / cg / brc (set in factor())
-    double u = fma(L.brc, fma(2.0, pzc, -L.vc), fma(L.sig, L.x, -L.q));
+    double u = L.sig * L.x - L.q + L.betac * (L.rhoc * (2.0 * pzc - L.vc));
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
       const double pz = first ? 0.0 : proj_row(L, b.v, b.l), pzb = first ? 0.0 : proj_sb(L, b.vb);
-      const double t = fma(2.0, pz, -b.v), tb = fma(2.0, pzb, -b.vb);
-      const double bd = fma(b.bb, tb, fma(b.er, t, fma(sigma, b.xd, -b.qd)));
+      const double wr = L.rho_r * (2.0 * pz - b.v), wb = L.rho_b * (2.0 * pzb - b.vb);
+      const double bd = sigma * b.xd - b.qd + b.e * wr + b.beta * wb;
       b.pz = pz; b.pzb = pzb; b.bd = bd;
-      u = fma(-b.cg, bd, fma(b.cr, t, u));
+      u += b.c * (wr - b.gam * bd);
     }
     S.u[L.gl] = u;
   };
@@ -536,15 +531,16 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       if (i + 2 < GL) s2 += L.w[i + 2] * S.u[i + 2];
     }
     const double s = (s0 + s1) + s2;
-    L.x = fma(L.al, s, oma * L.x);
-    L.vc = fma(alpha, fma(L.betac, s, -L.pzc), L.vc);
+    L.x = L.al * s + oma * L.x;
+    L.vc += alpha * (L.betac * s - L.pzc);
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
-      const double xtd = fma(-b.cg, s, b.kinv * b.bd);
-      b.v = fma(alpha, fma(b.e, xtd, fma(b.c, s, -b.pz)), b.v);
-      b.vb = fma(alpha, fma(b.beta, xtd, -b.pzb), b.vb);
-      b.xd = fma(alpha, xtd, oma * b.xd);
+      const double sk = b.c * s;
+      const double xtd = b.kinv * b.bd - b.gam * sk;
+      b.v += alpha * (sk + b.e * xtd - b.pz);
+      b.vb += alpha * (b.beta * xtd - b.pzb);
+      b.xd = alpha * xtd + oma * b.xd;
     }
   };
   // phase B on a checked iteration: also records delta_x / delta_y of this iteration (cold data)
@@ -570,11 +566,12 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
-      const double xtd = fma(-b.cg, s, b.kinv * b.bd);
+      const double sk = b.c * s;
+      const double xtd = b.kinv * b.bd - b.gam * sk;
       const double y0 = L.rho_r * (b.v - b.pz), yb0 = L.rho_b * (b.vb - b.pzb);
-      b.v = fma(alpha, fma(b.e, xtd, fma(b.c, s, -b.pz)), b.v);
-      b.vb = fma(alpha, fma(b.beta, xtd, -b.pzb), b.vb);
-      const double xdn = fma(alpha, xtd, oma * b.xd);
+      b.v += alpha * (sk + b.e * xtd - b.pz);
+      b.vb += alpha * (b.beta * xtd - b.pzb);
+      const double xdn = alpha * xtd + oma * b.xd;
       C.dxd[k] = xdn - b.xd;
       b.xd = xdn;
       C.dy[k] = L.rho_r * (b.v - proj_row(L, b.v, b.l)) - y0;
