@@ -55,6 +55,8 @@ WORKLOADS = {
     "husky_qpid": dict(robot="husky_fr3", kind="id", desc="Husky-FR3 whole-body updateState+QPIDStep (18 vars / 39 rows)"),
     "xls_qpik": dict(robot="xls_fr3", kind="ik", desc="XLS-FR3 (mecanum, synthesized URDF) whole-body updateState+QPIKStep (11 vars / 27 rows)"),
     "xls_qpid": dict(robot="xls_fr3", kind="id", desc="XLS-FR3 whole-body updateState+QPIDStep (22 vars / 41 rows)"),
+    "ur5e_clik_osf": dict(robot="ur5e", kind="taskspace", link="tool0",
+                          desc="UR5e (synthesized URDF) updateState+CLIKStep+OSFStep, no QP (BASELINE config 2: run with --batch 4096)"),
 }
 MOMA_DESC = {
     "husky_fr3": dict(kin=dict(type="Differential", wheel_radius=0.1651, base_width=0.555), w=2,
@@ -187,15 +189,23 @@ def oracle_cycles_per_s(B: int, threads: int, seed: int = 0, passes: int = 1, wo
     from oracle.c_oracle import MomaOracle, Oracle
     wl = WORKLOADS[workload]
     urdf, srdf = robot_paths(wl["robot"])
-    if wl["robot"] == "fr3":
+    if wl["robot"] in ("fr3", "ur5e"):
         o = Oracle(urdf, srdf, threads=threads)
-        f = o.frame_id(LINK)
+        f = o.frame_id(wl.get("link", LINK))
 
         class M:  # the oracle's own model view, same fields as engine.Model
             dof, q_lower, q_upper, v_limit = o.nv, o.model.q_lo, o.model.q_hi, o.model.v_lim
         q, qd, q_t, xdot_t = make_workload(M, B, seed)
         mode = 1 if wl["kind"] == "ik" else 3
-        run = lambda *a: o.cycle(mode, *a, f)
+        if wl["kind"] == "taskspace":
+            class R:  # CLIKStep + OSFStep results; no QP iterations
+                pass
+            def run(*a):
+                o.taskspace(0, *a, f)
+                o.taskspace(1, *a, f)
+                return dict(iters=np.zeros(len(a[0]), np.int32), status=np.ones(len(a[0]), np.int32))
+        else:
+            run = lambda *a: o.cycle(mode, *a, f)
     else:
         md = MOMA_DESC[wl["robot"]]
         o = MomaOracle(urdf, srdf, md["kin"], md["joint_idx"], md["actuator_idx"], threads=threads)
@@ -255,7 +265,9 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     urdf, srdf = robot_paths(wl["robot"])
     model = drc.Model(urdf, srdf)
-    moma = wl["robot"] != "fr3"
+    moma = wl["robot"] not in ("fr3", "ur5e")
+    link = wl.get("link", LINK)
+    taskspace = wl["kind"] == "taskspace"
     if moma:
         md = MOMA_DESC[wl["robot"]]
         model.attach_mobile_base(md["kin"], md["joint_idx"], md["actuator_idx"])
@@ -273,7 +285,7 @@ def run_ours(args):
     else:
         q, qd, q_t, xdot_t = make_workload(model, B, seed=1000 * rank)
         ctx.update_state(q_t, qd)
-        x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+        x_t = ctx.get_frame(link, want=("pose",))["pose"]
         nout = model.dof
     tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xdot_t))
     out = torch.empty((B, nout), dtype=torch.float64, device=dev)
@@ -285,6 +297,10 @@ def run_ours(args):
     def cycle(a_q, a_qd, a_xt, a_xd, o_out, o_st, o_it, o_out2=None):
         if moma:
             ctx.moma_cycle(wl["kind"], a_q, a_qd, a_xt, a_xd, LINK, out=o_out, out2=o_out2, status=o_st, iters=o_it)
+        elif taskspace:   # config 2: updateState + CLIKStep (qdot*) + OSFStep (tau*), no QP
+            ctx.update_state(a_q, a_qd)
+            ctx.clik_step(a_xt, a_xd, link, out=o_out)
+            ctx.osf_step(a_xt, a_xd, link, out=o_out2)
         elif wl["kind"] == "ik":
             ctx.cycle_qpik_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
         else:
@@ -303,7 +319,7 @@ def run_ours(args):
     for k in range(max(args.warmup, 3)):
         step(k)
     torch.cuda.synchronize()
-    ctx.enable_timing(True)
+    ctx.enable_timing(not taskspace)
     sampler = ClockSampler(local)
     sampler.start()
     if dist is not None:
@@ -319,7 +335,7 @@ def run_ours(args):
         e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        stage_ms.append(ctx.last_timing())
+        stage_ms.append(ctx.last_timing() if not taskspace else dict(build_ms=0.0, collision_ms=0.0, admm_ms=0.0, total_ms=0.0))
     torch.cuda.synchronize()
     launches = ctx.launch_count - launches0
     if dist is not None:
@@ -332,6 +348,8 @@ def run_ours(args):
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    if taskspace:
+        it.zero_(); st.fill_(1)
     iters_last, status_last = it.cpu().numpy().astype(np.float64), st.cpu().numpy()
     # the same ticks with the schedule hint off (identity robot order), reported next to the headline for transparency
     ctx.set_params(schedule_hint=0)
@@ -369,7 +387,7 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = world * B * args.steps / e2e_s
     h2d = B * (model.dof * 2 + 12 + 6) * 8
-    d2h = B * (nout * 8 * (2 if (moma and wl['kind'] == 'id') else 1) + 4 + 4)
+    d2h = B * (nout * 8 * (2 if ((moma and wl['kind'] == 'id') or taskspace) else 1) + (0 if taskspace else 8))
 
     if rank != 0:
         if dist is not None:

@@ -280,11 +280,26 @@ class Context:
         return self._qp_host(lib().drc_host_qpid_step, "drc_host_qpid_step", B, (self._p(xt), self._p(xd), self._frame(link)),
                              n_out2=True)
 
-    def clik_step(self, x_target, xdot_target, link, null_qdot=None):
+    def _taskspace_torch(self, fn_name, x_target, xdot_target, null_vec, link, out):
+        """device path of CLIKStep / OSFStep: torch CUDA tensors in, torch tensor out (asynchronous)."""
+        import torch
+        xt, B = self._t_in(x_target, 12)
+        xd, _ = self._t_in(xdot_target, 6, B)
+        nv = None
+        if null_vec is not None:
+            nv, _ = self._t_in(null_vec, self.n, B)
+        out = torch.empty((B, self.n), dtype=torch.float64, device=xt.device) if out is None else out
+        check(getattr(lib(), fn_name)(self._h, B, self._tp(xt), self._tp(xd), self._tp(nv), self._frame(link), self._tp(out),
+                                      _capi.LAYOUT_AOS, self._stream()), fn_name)
+        return out
+
+    def clik_step(self, x_target, xdot_target, link, null_qdot=None, out=None):
+        if _is_torch(x_target):
+            return self._taskspace_torch("drc_batch_clik_step", x_target, xdot_target, null_qdot, link, out)
         xt, B = self._np_in(pose12(x_target), 12, self._B)
         xd, _ = self._np_in(xdot_target, 6, B)
         nq, _ = self._np_in(null_qdot, self.n, B)
-        out = np.zeros((B, self.n))
+        out = np.zeros((B, self.n)) if out is None else out
         check(lib().drc_host_clik_step(self._h, B, self._p(xt), self._p(xd), self._p(nq), self._frame(link), self._p(out)),
               "drc_host_clik_step")
         return out
@@ -296,11 +311,13 @@ class Context:
         check(lib().drc_host_osf(self._h, B, self._p(x), self._p(nt), self._frame(link), self._p(out)), "drc_host_osf")
         return out
 
-    def osf_step(self, x_target, xdot_target, link, null_torque=None):
+    def osf_step(self, x_target, xdot_target, link, null_torque=None, out=None):
+        if _is_torch(x_target):
+            return self._taskspace_torch("drc_batch_osf_step", x_target, xdot_target, null_torque, link, out)
         xt, B = self._np_in(pose12(x_target), 12, self._B)
         xd, _ = self._np_in(xdot_target, 6, B)
         nt, _ = self._np_in(null_torque, self.n, B)
-        out = np.zeros((B, self.n))
+        out = np.zeros((B, self.n)) if out is None else out
         check(lib().drc_host_osf_step(self._h, B, self._p(xt), self._p(xd), self._p(nt), self._frame(link), self._p(out)),
               "drc_host_osf_step")
         return out
