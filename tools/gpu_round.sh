@@ -10,9 +10,10 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_bench.log 2>&1
 for k in k_admm k_collision k_robot_job; do
-  # second control tick: the ADMM schedule then has the previous tick's iteration counts (k_robot_job: skip the two
-  # state-update launches of the set-up and the first tick)
-  skip=1; [ "$k" = "k_robot_job" ] && skip=3
+  # MAIN-pipeline launch of the second control tick (the ADMM schedule then has the previous tick's iteration counts).
+  # Launch order per tick: priority pipeline (FK store, collision, build, ADMM) then main pipeline (same kernels);
+  # tools/prof_cycle.py adds two k_robot_job launches for its set-up.
+  skip=3; [ "$k" = "k_robot_job" ] && skip=9
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip -c 1 -f -o gpurun_out/${tag}_${k} \
     python tools/prof_cycle.py 65536 2 > gpurun_out/${tag}_ncu_${k}.log 2>&1
   # gpurun_out/ is capped at 64 MiB: keep the CSV pages, drop the report

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""Memory-safety pass for compute-sanitizer: every pipeline once at small batches (incl. the priority pipeline).
+
+    compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_cycle.py
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import dyros_robot_controller_b200 as drc
+from bench import MOMA_DESC, make_moma_workload, make_workload, robot_paths
+
+LINK = "fr3_link8"
+model = drc.Model(drc.FR3_URDF, drc.FR3_SRDF)
+B = 9000                                   # >= 8192: the priority pipeline is live on the second tick
+ctx = drc.Context(model, B)
+q, qd, q_t, xd = make_workload(model, B, 0)
+ctx.update_state(q_t, qd)
+x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+for k in range(3):
+    r = ctx.cycle_qpik_step(q + k * 1e-3 * qd, qd, x_t, xd, LINK)
+print("qpik ticks ok", int((r["status"] == 1).sum()), int(r["iters"].max()))
+r = ctx.cycle_qpid_step(q[:9000], qd[:9000], x_t[:9000], xd[:9000], LINK)
+r = ctx.cycle_qpid_step(q[:9000], qd[:9000], x_t[:9000], xd[:9000], LINK)
+print("qpid ok", int((r["status"] == 1).sum()))
+ctx.update_state(q[:500], qd[:500])
+ctx.get_frame(LINK); ctx.get_dynamics(); ctx.get_manipulability(LINK, True); ctx.get_min_distance(True)
+ctx.clik_step(x_t[:500], xd[:500], LINK); ctx.osf_step(x_t[:500], xd[:500], LINK); ctx.qpik(xd[:500], LINK)
+print("getters ok")
+urdf, srdf = robot_paths("xls_fr3")
+md = MOMA_DESC["xls_fr3"]
+mm = drc.Model(urdf, srdf).attach_mobile_base(md["kin"], md["joint_idx"], md["actuator_idx"])
+mc = drc.Context(mm, 600)
+q, qd, q_t, xd = make_moma_workload(mm.q_lower, mm.q_upper, mm.v_limit, md["w"], 600, 1)
+mc.moma_update_state(q_t, qd)
+x_t = mc.moma_get_state(LINK, want=("pose",))["pose"]
+for kind in ("ik", "id"):
+    r = mc.moma_cycle(kind, q, qd, x_t, xd, LINK)
+    r = mc.moma_cycle(kind, q, qd, x_t, xd, LINK)
+    print("moma", kind, "ok", int((r["status"] == 1).sum()))
