@@ -428,9 +428,12 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
     sample = min(B, 32768)
-    cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores, workload=args.workload)
-    # the reference's control loop is single-threaded (one controller instance per control thread): one-thread rate on a smaller sample
-    cpu1_val, cpu1_dt, _ = oracle_cycles_per_s(min(sample, 4096), 1, workload=args.workload)
+    if world == 1:
+        cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores, workload=args.workload)
+        # the reference's control loop is single-threaded (one controller instance per control thread): one-thread rate on a smaller sample
+        cpu1_val, cpu1_dt, _ = oracle_cycles_per_s(min(sample, 4096), 1, workload=args.workload)
+    else:  # the CPU baseline is reported by the N = 1 run only
+        cpu_val = cpu_dt = cpu1_val = cpu1_dt = float("nan")
     line = {"metric": METRIC if args.workload == "fr3_qpik" else f"batched control cycles/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
@@ -444,7 +447,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": None if world > 1 else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} cycles of the same workload, one pass, OpenMP over {cores} host threads "
                                        f"({cpu_dt:.2f} s)",
                              "single_thread": {"value": cpu1_val, "cores": 1,

@@ -63,6 +63,8 @@ struct drc_ctx {
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
   cudaEvent_t ev_sched, ev_prio;
+  cudaStream_t copy;                     // host entry points: inputs that only stage 2 reads are uploaded here, behind stage 1
+  cudaEvent_t ev_late, ev_early; bool late_pending;
   int sm_count;
   // device staging for host entry points
   double* stage; size_t stage_doubles;
@@ -224,6 +226,22 @@ struct Stage {
     double* d = take(cnt);
     if (d && cudaMemcpyAsync(d, h, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) err = DRC_E_CUDA;
     return d;
+  }
+  // upload on the copy stream: overlaps the kernels that do not read it (run_qp waits for ev_late before stage 2)
+  bool late_started = false;
+  double* in_late(const double* h, size_t cnt) {
+    if (!h) return nullptr;
+    if (!late_started) {  // behind the inputs already queued on the main stream (they are needed first; one PCIe link)
+      late_started = true;
+      if (cudaEventRecord(c->ev_early, c->stream) != cudaSuccess || cudaStreamWaitEvent(c->copy, c->ev_early, 0) != cudaSuccess) err = DRC_E_CUDA;
+    }
+    double* d = take(cnt);
+    if (d && cudaMemcpyAsync(d, h, cnt * sizeof(double), cudaMemcpyHostToDevice, c->copy) != cudaSuccess) err = DRC_E_CUDA;
+    return d;
+  }
+  void late_done() {
+    if (cudaEventRecord(c->ev_late, c->copy) != cudaSuccess) err = DRC_E_CUDA;
+    c->late_pending = true;
   }
   double* out(double* h, size_t cnt) {
     if (!h) return nullptr;

@@ -63,6 +63,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     pc.B = kPrioSlots; pc.mode = id ? 2 : 1; pc.qp = c->prio.qp; pc.qp_stride = qp_stride; pc.qp_row_off = qp_row_off;
     pc.count = c->slow_count;
     rc = launch_collision<NV, CHAIN>(c, pc, ps, false, &c->prio); if (rc) return rc;
+    if (c->late_pending) CU(cudaStreamWaitEvent(ps, c->ev_late, 0));   // x_target / xdot_target still uploading (host entry points)
     rc = build(pio, ps); if (rc) return rc;
     SolveIO ps_io;
     std::memset(&ps_io, 0, sizeof ps_io);
@@ -84,6 +85,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (rc) return rc;
   if (c->timing) cudaEventRecord(c->ev[1], s);
   // stage 2 (next to the EPA pass)
+  if (c->late_pending) { CU(cudaStreamWaitEvent(s, c->ev_late, 0)); c->late_pending = false; }
   rc = build(io, s);
   if (rc) return rc;
 #undef J
@@ -245,6 +247,9 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
     CU(cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi));
     CU(cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_late, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming));
   }
   {
     cudaDeviceProp prop;
@@ -286,6 +291,9 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->prio_stream) { cudaStreamSynchronize(c->prio_stream); cudaStreamDestroy(c->prio_stream); }
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
     if (c->ev_prio) cudaEventDestroy(c->ev_prio);
+    if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    if (c->ev_late) cudaEventDestroy(c->ev_late);
+    if (c->ev_early) cudaEventDestroy(c->ev_early);
   }
   if (c->stage_i) cudaFree(c->stage_i);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -587,14 +595,17 @@ int drc_host_task_space_cubic(drc_ctx_t* c, int B, const double* x_target, const
 }
 int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* qdot_out, int* status, int* iters) {
   HOST_PRELUDE
-  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6);
+  // q, qdot feed stage 1 (FK, self-collision); the targets are only read by the QP-build kernel: upload them behind stage 1
+  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
+  st.late_done();
   double* dout = st.out(qdot_out, Bz * n);
   int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpik_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
 }
 int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* tau_out, int* status, int* iters) {
   HOST_PRELUDE
-  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6);
+  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
+  st.late_done();
   double* dout = st.out(tau_out, Bz * n);
   int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpid_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Memory-safety pass for compute-sanitizer: every pipeline once at small batches (incl. the priority pipeline).
+"""Every pipeline once at small batches (incl. the priority pipeline): a quick end-to-end pass; also the driver for
+compute-sanitizer where that tool is available (it is closed on the graft GPU pool).
 
     compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_cycle.py
 """
