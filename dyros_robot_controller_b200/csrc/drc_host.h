@@ -130,11 +130,9 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   if (!io.witness) io.witness = sc.col_wit;
   static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 128; return t >= 32 && t <= 128 ? t : 128; }();
   const int blocks = (io.B + threads - 1) / threads;
-  // resident blocks/SM the kernel is compiled for (register cap); tunable for experiments on the FR3 shape
-  static const int minb = [] { const char* e = getenv("DRC_COL_MINB"); return e ? atoi(e) : 2; }();
-  if (NV == 7 && minb == 3) k_collision<NV, CHAIN, (NV == 7 ? 3 : 2)><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
-  else if (NV == 7 && minb >= 4) k_collision<NV, CHAIN, (NV == 7 ? 4 : 2)><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
-  else k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  // (register budgets of 168 / 128 registers were measured too: 3 blocks/SM is slower, 4 blocks/SM saves 0.1 ms here and loses it
+  // again in the ADMM stage -- profiles/README.md)
+  k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
   CU(cudaGetLastError());
   // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it
   // on the side stream, concurrently with the state / QP-build kernel (disjoint parts of the QP record), and join
