@@ -8,7 +8,7 @@
 """
 from pathlib import Path
 
-from .engine import Context, Model, device_count, fp64_peak_tflops, pose12, pose44  # noqa: F401
+from .engine import Context, MobileBase, Model, device_count, fp64_peak_tflops, pose12, pose44  # noqa: F401
 
 ROBOTS_DIR = Path(__file__).resolve().parent / "robots"
 FR3_URDF = str(ROBOTS_DIR / "fr3" / "fr3.urdf")
@@ -16,4 +16,5 @@ FR3_SRDF = str(ROBOTS_DIR / "fr3" / "fr3.srdf")
 # synthesized mobile manipulators of BASELINE configs 4-5 (tools/make_moma_urdf.py; NOT from the reference)
 HUSKY_FR3_URDF, HUSKY_FR3_SRDF = str(ROBOTS_DIR / "husky_fr3" / "husky_fr3.urdf"), str(ROBOTS_DIR / "husky_fr3" / "husky_fr3.srdf")
 XLS_FR3_URDF, XLS_FR3_SRDF = str(ROBOTS_DIR / "xls_fr3" / "xls_fr3.urdf"), str(ROBOTS_DIR / "xls_fr3" / "xls_fr3.srdf")
+PCV_FR3_URDF, PCV_FR3_SRDF = str(ROBOTS_DIR / "pcv_fr3" / "pcv_fr3.urdf"), str(ROBOTS_DIR / "pcv_fr3" / "pcv_fr3.srdf")  # powered casters
 __version__ = "0.1.0"

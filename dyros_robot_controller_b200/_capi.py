@@ -54,6 +54,8 @@ SYMBOLS = [
     "drc_batch_moma_qpid", "drc_batch_moma_qpid_step", "drc_batch_moma_cycle_qpik_step", "drc_batch_moma_cycle_qpid_step",
     "drc_host_moma_update_state", "drc_host_moma_get_state", "drc_host_moma_qpik", "drc_host_moma_qpik_step",
     "drc_host_moma_qpid", "drc_host_moma_qpid_step", "drc_host_moma_cycle_qpik_step", "drc_host_moma_cycle_qpid_step",
+    "drc_mobile_create", "drc_mobile_destroy", "drc_mobile_wheel_num", "drc_mobile_synchronize", "drc_mobile_launch_count",
+    "drc_batch_mobile_fk", "drc_batch_mobile_ik", "drc_host_mobile_fk", "drc_host_mobile_ik",
 ]
 
 
@@ -76,6 +78,7 @@ def lib():
         L.drc_model_verbose.restype = C.c_char_p
         L.drc_ctx_stream.restype = C.c_void_p
         L.drc_ctx_launch_count.restype = C.c_longlong
+        L.drc_mobile_launch_count.restype = C.c_longlong
         _lib = L
     return _lib
 

@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libdrc_b200.so"
-SOURCES = [CSRC / "drc_lib.cu", CSRC / "drc_moma.cu", CSRC / "model.cpp"]
+SOURCES = [CSRC / "drc_lib.cu", CSRC / "drc_moma.cu", CSRC / "drc_mobile.cu", CSRC / "model.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 OBJDIR = PKG / "build"
 

@@ -9,6 +9,7 @@
 #pragma once
 #include "drc_geom.h"
 #include "drc_kin.h"
+#include "drc_mobile.h"
 #include "drc_qp.h"
 #include <type_traits>
 
@@ -156,11 +157,23 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   if (MOMA) {
     double sy, cy;
     sincos(q[m.virtual_start + 2], &sy, &cy);
+    // J_mobile: constant for differential / mecanum bases, a function of the steering angles for powered casters
+    // (mobile_manipulator/robot_data.cpp:112 -> Mobile::RobotData::computeFKJacobian, mobile/robot_data.cpp:122-204)
+    double Jm[3 * (W > 0 ? W : 1)];
+    if (m.drive_type == kCaster) {
+      double wp[W > 0 ? W : 1];
+#pragma unroll
+      for (int k = 0; k < W; ++k) wp[k] = q[m.mobi_start + k];
+      caster_fk_jacobian<(W > 1 ? W : 2)>(m.wheel_radius, m.wheel_offset, m.b2w_x, m.b2w_y, wp, W, Jm, W);
+    } else {
+#pragma unroll
+      for (int k = 0; k < W; ++k) { Jm[0 * W + k] = m.J_mobile[0][k]; Jm[1 * W + k] = m.J_mobile[1][k]; Jm[2 * W + k] = m.J_mobile[2][k]; }
+    }
 #pragma unroll
     for (int k = 0; k < W; ++k) {
-      Sm[0 * W + k] = cy * m.J_mobile[0][k] - sy * m.J_mobile[1][k];
-      Sm[1 * W + k] = sy * m.J_mobile[0][k] + cy * m.J_mobile[1][k];
-      Sm[2 * W + k] = m.J_mobile[2][k];
+      Sm[0 * W + k] = cy * Jm[0 * W + k] - sy * Jm[1 * W + k];
+      Sm[1 * W + k] = sy * Jm[0 * W + k] + cy * Jm[1 * W + k];
+      Sm[2 * W + k] = Jm[2 * W + k];
     }
     double T[NV * ACT], nleact[ACT], nle_full[NV];
 #pragma unroll

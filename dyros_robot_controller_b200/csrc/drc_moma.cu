@@ -14,7 +14,6 @@
 static int check_moma(const drc_ctx* c, int B) {
   int rc = check_batch(c, B); if (rc) return rc;
   if (c->model->hm.dev.drive_type == kNoBase) return fail(DRC_E_INVALID, "the model has no mobile base (drc_model_attach_mobile_base)");
-  if (c->model->hm.dev.drive_type == kCaster) return fail(DRC_E_UNSUPPORTED, "caster bases: state-dependent base Jacobian is not built into the whole-body kernels yet");
   if (!c->c_Mact) return fail(DRC_E_INVALID, "the context was created before the mobile base was attached");
   return DRC_OK;
 }
@@ -114,7 +113,7 @@ int drc_model_base_jacobian(const drc_model_t* m, double* J) {
   if (!m || !J) return fail(DRC_E_INVALID, "null argument");
   const DrcModelDev& d = m->hm.dev;
   if (d.drive_type == kNoBase) return fail(DRC_E_INVALID, "the model has no mobile base");
-  if (d.drive_type == kCaster) return fail(DRC_E_UNSUPPORTED, "caster base Jacobian depends on the steering angles");
+  if (d.drive_type == kCaster) return fail(DRC_E_UNSUPPORTED, "caster base Jacobian depends on the steering angles: use drc_batch_mobile_fk");
   for (int r = 0; r < 3; ++r) for (int k = 0; k < d.wheel_num; ++k) J[r * d.wheel_num + k] = d.J_mobile[r][k];
   return DRC_OK;
 }

@@ -296,6 +296,47 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
   return B.hm;
 }
 
+// Configuration-independent base Jacobians (w <= 8 wheels):
+//   forward  J_fk (3 x w): DifferentialFKJacobian / MecanumFKJacobian = PinvCOD(J_inv)   mobile/robot_data.cpp:138-177
+//   inverse  J_ik (w x 3): DifferentialIKJacobian / MecanumIKJacobian                    mobile/robot_controller.cpp:65-102
+void mobile_constant_jacobians(const MobileParam& p, int w, double J_fk[3][8], double J_ik[8][3]) {
+  std::memset(J_fk, 0, sizeof(double) * 3 * 8);
+  std::memset(J_ik, 0, sizeof(double) * 8 * 3);
+  if (p.drive_type == kDifferential) {
+    J_fk[0][0] = p.wheel_radius / 2; J_fk[0][1] = p.wheel_radius / 2;
+    J_fk[2][0] = -p.wheel_radius / p.base_width; J_fk[2][1] = p.wheel_radius / p.base_width;
+    J_ik[0][0] = 1 / p.wheel_radius; J_ik[0][2] = -p.base_width / (2 * p.wheel_radius);
+    J_ik[1][0] = 1 / p.wheel_radius; J_ik[1][2] = p.base_width / (2 * p.wheel_radius);
+  } else if (p.drive_type == kMecanum) {
+    for (int i = 0; i < w; ++i) {
+      const double r = p.wheel_radius, g = p.roller_angles[i], px = p.b2w_x[i], py = p.b2w_y[i], pt = p.b2w_angles[i];
+      const double a3[2] = {1.0, std::tan(g)};
+      const double a2[2][2] = {{std::cos(pt), std::sin(pt)}, {-std::sin(pt), std::cos(pt)}};
+      const double a1[2][3] = {{1, 0, -py}, {0, 1, px}};
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+        for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l) s += a3[k] * a2[k][l] * a1[l][c];
+        J_ik[i][c] = s / r;
+      }
+    }
+    // full column rank (3): pinv = (Ji' Ji)^-1 Ji'
+    double G[9] = {0};
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int i = 0; i < w; ++i) G[3 * a + b] += J_ik[i][a] * J_ik[i][b];
+    const double det = G[0] * (G[4] * G[8] - G[5] * G[7]) - G[1] * (G[3] * G[8] - G[5] * G[6]) + G[2] * (G[3] * G[7] - G[4] * G[6]);
+    if (std::fabs(det) < 1e-12) throw std::runtime_error("mobile base: mecanum inverse Jacobian is rank deficient");
+    double Gi[9];
+    Gi[0] = (G[4] * G[8] - G[5] * G[7]) / det; Gi[1] = (G[2] * G[7] - G[1] * G[8]) / det; Gi[2] = (G[1] * G[5] - G[2] * G[4]) / det;
+    Gi[3] = (G[5] * G[6] - G[3] * G[8]) / det; Gi[4] = (G[0] * G[8] - G[2] * G[6]) / det; Gi[5] = (G[2] * G[3] - G[0] * G[5]) / det;
+    Gi[6] = (G[3] * G[7] - G[4] * G[6]) / det; Gi[7] = (G[1] * G[6] - G[0] * G[7]) / det; Gi[8] = (G[0] * G[4] - G[1] * G[3]) / det;
+    for (int a = 0; a < 3; ++a)
+      for (int i = 0; i < w; ++i) {
+        double s = 0;
+        for (int b = 0; b < 3; ++b) s += Gi[3 * a + b] * J_ik[i][b];
+        J_fk[a][i] = s;
+      }
+  }
+}
+
 void attach_mobile_base(HostModel& m, const MobileParam& p, int virtual_start, int mani_start, int mobi_start,
                         int act_mani_start, int act_mobi_start) {
   DrcModelDev& d = m.dev;
@@ -314,39 +355,16 @@ void attach_mobile_base(HostModel& m, const MobileParam& p, int virtual_start, i
   d.act_mani_start = act_mani_start; d.act_mobi_start = act_mobi_start;
   d.wheel_radius = p.wheel_radius; d.wheel_offset = p.wheel_offset;
   std::memset(d.J_mobile, 0, sizeof d.J_mobile);
-  if (p.drive_type == kDifferential) {  // mobile/robot_data.cpp:138-147
-    d.J_mobile[0][0] = p.wheel_radius / 2; d.J_mobile[0][1] = p.wheel_radius / 2;
-    d.J_mobile[2][0] = -p.wheel_radius / p.base_width; d.J_mobile[2][1] = p.wheel_radius / p.base_width;
-  } else if (p.drive_type == kMecanum) {  // :149-177  J = pinv(J_inv)
-    std::vector<double> Ji(w * 3);
-    for (int i = 0; i < w; ++i) {
-      const double r = p.wheel_radius, g = p.roller_angles[i], px = p.b2w_x[i], py = p.b2w_y[i], pt = p.b2w_angles[i];
-      const double a3[2] = {1.0, std::tan(g)};
-      const double a2[2][2] = {{std::cos(pt), std::sin(pt)}, {-std::sin(pt), std::cos(pt)}};
-      const double a1[2][3] = {{1, 0, -py}, {0, 1, px}};
-      for (int c = 0; c < 3; ++c) {
-        double s = 0;
-        for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l) s += a3[k] * a2[k][l] * a1[l][c];
-        Ji[i * 3 + c] = s / r;
-      }
-    }
-    // full column rank (3): pinv = (Ji' Ji)^-1 Ji'
-    double G[9] = {0};
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int i = 0; i < w; ++i) G[3 * a + b] += Ji[i * 3 + a] * Ji[i * 3 + b];
-    const double det = G[0] * (G[4] * G[8] - G[5] * G[7]) - G[1] * (G[3] * G[8] - G[5] * G[6]) + G[2] * (G[3] * G[7] - G[4] * G[6]);
-    if (std::fabs(det) < 1e-12) throw std::runtime_error("mobile base: mecanum inverse Jacobian is rank deficient");
-    double Gi[9];
-    Gi[0] = (G[4] * G[8] - G[5] * G[7]) / det; Gi[1] = (G[2] * G[7] - G[1] * G[8]) / det; Gi[2] = (G[1] * G[5] - G[2] * G[4]) / det;
-    Gi[3] = (G[5] * G[6] - G[3] * G[8]) / det; Gi[4] = (G[0] * G[8] - G[2] * G[6]) / det; Gi[5] = (G[2] * G[3] - G[0] * G[5]) / det;
-    Gi[6] = (G[3] * G[7] - G[4] * G[6]) / det; Gi[7] = (G[1] * G[6] - G[0] * G[7]) / det; Gi[8] = (G[0] * G[4] - G[1] * G[3]) / det;
-    for (int a = 0; a < 3; ++a)
-      for (int i = 0; i < w; ++i) {
-        double s = 0;
-        for (int b = 0; b < 3; ++b) s += Gi[3 * a + b] * Ji[i * 3 + b];
-        d.J_mobile[a][i] = s;
-      }
+  if (p.drive_type != kCaster) {
+    double Jik[8][3];
+    mobile_constant_jacobians(p, w, d.J_mobile, Jik);
   } else {
-    for (size_t i = 0; i < p.b2w_x.size() && i < 4; ++i) { d.b2w_x[i] = p.b2w_x[i]; d.b2w_y[i] = p.b2w_y[i]; }
+    // powered casters: J_mobile depends on the steering angles and is evaluated per state (drc_mobile.h).  One caster
+    // alone leaves Jp' Jp rank deficient (the reference would return a reduced-rank pseudo-inverse): not supported.
+    if (p.b2w_x.size() < 2 || p.b2w_x.size() > 4 || p.b2w_y.size() != p.b2w_x.size())
+      throw std::runtime_error("mobile base: caster drives need 2..4 casters with base2wheel_positions for each");
+    if (!(p.wheel_offset > 0) || !(p.wheel_radius > 0)) throw std::runtime_error("mobile base: caster drives need wheel_offset > 0 and wheel_radius > 0");
+    for (size_t i = 0; i < p.b2w_x.size(); ++i) { d.b2w_x[i] = p.b2w_x[i]; d.b2w_y[i] = p.b2w_y[i]; }
   }
 }
 

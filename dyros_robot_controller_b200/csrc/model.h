@@ -41,7 +41,10 @@ struct MobileParam {
   int drive_type;  // DriveType
   double wheel_radius, base_width, wheel_offset;
   std::vector<double> roller_angles, b2w_x, b2w_y, b2w_angles;
+  double max_lin_speed = 0, max_ang_speed = 0, max_lin_acc = 0, max_ang_acc = 0;
 };
+// differential / mecanum forward (3 x w) and inverse (w x 3) base Jacobians; zero for caster bases (state dependent)
+void mobile_constant_jacobians(const MobileParam& p, int w, double J_fk[3][8], double J_ik[8][3]);
 void attach_mobile_base(HostModel& m, const MobileParam& p, int virtual_start, int mani_start, int mobi_start,
                         int act_mani_start, int act_mobi_start);
 

@@ -5,5 +5,6 @@ the batched sibling, a leading batch axis (q: (B,n), poses: (B,4,4)); results ca
 
     from dyros_robot_controller_b200.drc.manipulator import RobotData, RobotController
 """
-from . import manipulator, mobile_manipulator  # noqa: F401
-from .type_define import ManipulabilityResult, MinDistResult  # noqa: F401
+from . import manipulator, mobile, mobile_manipulator  # noqa: F401
+from .type_define import (ActuatorIndex, DriveType, JointIndex, KinematicParam, ManipulabilityResult,  # noqa: F401
+                          MinDistResult)

@@ -14,13 +14,18 @@ from ..type_define import ManipulabilityResult
 class RobotData:
     def __init__(self, mobile_param: dict, joint_idx: dict, actuator_idx: dict, urdf_path: str, srdf_path: str = "",
                  packages_path: str = "", max_batch: int = 1, device: int = 0):
+        as_dict = lambda a: a.as_dict() if hasattr(a, "as_dict") else a   # KinematicParam / JointIndex / ActuatorIndex or dicts
+        mobile_param, joint_idx, actuator_idx = as_dict(mobile_param), as_dict(joint_idx), as_dict(actuator_idx)
         self._model = engine.Model(urdf_path, srdf_path, packages_path).attach_mobile_base(mobile_param, joint_idx, actuator_idx)
         self._ctx = engine.Context(self._model, max_batch, device)
         m = self._model
         self._ji, self._ai = m.joint_idx, m.actuator_idx
         self._w, self._k, self._act, self._dof = m.wheel_num, m.mani_dof, m.actuated_dof, m.dof
         self._single = True
-        self._J_mobile = m.base_jacobian()
+        # base Jacobian: a constant for differential / mecanum drives, a function of the steering angles for casters
+        self._caster = m.drive_type == 2
+        self._base = engine.MobileBase(mobile_param, device) if self._caster else None
+        self._J_mobile = self._base.fk(np.zeros((1, self._w)), None)[0][0] if self._caster else m.base_jacobian()
 
     # ---- vector assembly (robot_data.cpp:417-437)
     def get_joint_vector(self, q_virtual, q_mobile, q_mani) -> np.ndarray:
@@ -55,6 +60,8 @@ class RobotData:
         self._q_act = self.get_actuator_vector(q_mobile, q_mani)
         self._qdot_act = self.get_actuator_vector(qdot_mobile, qdot_mani)
         self._wheel_vel = np.atleast_2d(np.asarray(qdot_mobile, np.float64))
+        if self._caster:   # Mobile::RobotData::updateState (mobile/robot_data.cpp:110)
+            self._J_mobile = self._base.fk(np.atleast_2d(np.asarray(q_mobile, np.float64)), None)[0]
         return bool(self._ctx.moma_update_state(self._q, self._qdot))
 
     def get_dof(self) -> int:
@@ -88,9 +95,11 @@ class RobotData:
         return self._sq(self._qdot_act)
 
     def get_FK_jacobian(self) -> np.ndarray:          # Mobile::RobotData::getFKJacobian
-        return self._J_mobile.copy()
+        return self._sq(self._J_mobile).copy() if self._J_mobile.ndim == 3 else self._J_mobile.copy()
 
     def get_base_vel(self) -> np.ndarray:             # Mobile::RobotData::getBaseVel = J_mobile * wheel_vel
+        if self._J_mobile.ndim == 3:
+            return self._sq(np.einsum("brk,bk->br", self._J_mobile, self._wheel_vel))
         return self._sq(self._wheel_vel @ self._J_mobile.T)
 
     def _get(self, link_name, key, neutral=None):

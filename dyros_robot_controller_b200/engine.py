@@ -106,6 +106,82 @@ class Model:
             pass
 
 
+class MobileBase:
+    """Batched mobile base (reference Mobile::RobotData + Mobile::RobotController; no URDF, only the KinematicParam).
+
+    kin: type ("Differential" | "Mecanum" | "Caster" or 0/1/2), wheel_radius, base_width, wheel_offset, max_lin_speed,
+    max_ang_speed, max_lin_acc, max_ang_acc, roller_angles, base2wheel_positions [(x, y)...], base2wheel_angles
+    (type_define.h:58-72).  numpy arrays go through the drc_host_mobile_* entry points, float64 CUDA tensors through
+    drc_batch_mobile_* on the current torch stream."""
+
+    def __init__(self, kin: dict, device: int = 0):
+        t = kin["type"] if isinstance(kin["type"], (int, np.integer)) else Model.DRIVE_TYPES[kin["type"]]
+        pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+        w = 2 if t == 0 else (len(kin.get("roller_angles", [])) if t == 1 else 2 * len(pos))
+        arr = lambda a: np.ascontiguousarray(np.asarray(a, np.float64))
+        ra = arr(kin.get("roller_angles", np.zeros(w)))
+        ba = arr(kin.get("base2wheel_angles", np.zeros(w)))
+        bx, by = (arr(pos[:, 0]), arr(pos[:, 1])) if len(pos) else (np.zeros(max(w, 1)), np.zeros(max(w, 1)))
+        h = C.c_void_p()
+        g = lambda k: C.c_double(float(kin.get(k, 0.0)))
+        check(lib().drc_mobile_create(int(t), g("wheel_radius"), g("base_width"), g("wheel_offset"), g("max_lin_speed"),
+                                      g("max_ang_speed"), g("max_lin_acc"), g("max_ang_acc"), int(w), ra.ctypes.data_as(_D),
+                                      bx.ctypes.data_as(_D), by.ctypes.data_as(_D), ba.ctypes.data_as(_D), int(device),
+                                      C.byref(h)), "drc_mobile_create")
+        self._h = h
+        self.drive_type, self.wheel_num, self.kin = int(t), int(w), dict(kin)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().drc_mobile_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def launch_count(self) -> int:
+        return int(lib().drc_mobile_launch_count(self._h))
+
+    def _run(self, fk, wheel_pos, vec, want_J, saturate=False):
+        w = self.wheel_num
+        kin_in, kout = (w, 3) if fk else (3, w)
+        name = "mobile_fk" if fk else "mobile_ik"
+        if _is_torch(wheel_pos) or _is_torch(vec):
+            import torch
+            ref = wheel_pos if _is_torch(wheel_pos) else vec
+            wp, B = Context._t_in(None, wheel_pos, w)
+            v, B = Context._t_in(None, vec, kin_in, B)
+            J = torch.empty((B, 3, w) if fk else (B, w, 3), dtype=torch.float64, device=ref.device) if want_J else None
+            out = torch.empty((B, kout), dtype=torch.float64, device=ref.device) if v is not None else None
+            tp, st = Context._tp, Context._stream()
+            if fk:
+                rc = lib().drc_batch_mobile_fk(self._h, B, tp(wp), tp(v), tp(J), tp(out), _capi.LAYOUT_AOS, st)
+            else:
+                rc = lib().drc_batch_mobile_ik(self._h, B, tp(wp), tp(v), int(bool(saturate)), tp(J), tp(out), _capi.LAYOUT_AOS, st)
+            check(rc, "drc_batch_" + name)
+            return J, out
+        wp, B = Context._np_in(wheel_pos, w)
+        v, B = Context._np_in(vec, kin_in, B)
+        J = np.zeros((B, 3, w) if fk else (B, w, 3)) if want_J else None
+        out = np.zeros((B, kout)) if v is not None else None
+        p = Context._p
+        if fk:
+            rc = lib().drc_host_mobile_fk(self._h, B, p(wp), p(v), p(J), p(out))
+        else:
+            rc = lib().drc_host_mobile_ik(self._h, B, p(wp), p(v), int(bool(saturate)), p(J), p(out))
+        check(rc, "drc_host_" + name)
+        return J, out
+
+    def fk(self, wheel_pos, wheel_vel=None, want_J=True):
+        """Mobile::RobotData::updateState: (J_fk (B,3,w), base_vel (B,3)).  wheel_pos may be None for differential /
+        mecanum bases when wheel_vel is given."""
+        return self._run(True, wheel_pos, wheel_vel, want_J)
+
+    def ik(self, wheel_pos, base_vel=None, saturate=False, want_J=True):
+        """Mobile::RobotController: (J_ik (B,w,3), wheel_vel (B,w)); saturate=True is VelocityCommand."""
+        return self._run(False, wheel_pos, base_vel, want_J, saturate)
+
+
 class Context:
     """Device state cache + scratch for up to `max_batch` robots on one GPU."""
 

@@ -227,6 +227,33 @@ int drc_host_moma_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const do
                                   const double* xdot_target, int frame, double* tau_out, double* etadot_out, int* status,
                                   int* iters);
 
+/* ---- mobile base alone (reference src/mobile/robot_data.cpp, src/mobile/robot_controller.cpp).  The base has no URDF:
+ * the handle holds the KinematicParam (type_define.h:58-72).  n_wheels: 2 (differential), roller_angles.size() (mecanum),
+ * 2 * base2wheel_positions.size() (caster: steer, roll per caster).  Replaces Mobile::RobotData::RobotData
+ * (mobile/robot_data.cpp:7-32) and Mobile::RobotController::RobotController (mobile/robot_controller.cpp:7-12). */
+typedef struct drc_mobile drc_mobile_t;
+int drc_mobile_create(int drive_type, double wheel_radius, double base_width, double wheel_offset, double max_lin_speed,
+                      double max_ang_speed, double max_lin_acc, double max_ang_acc, int n_wheels, const double* roller_angles,
+                      const double* b2w_x, const double* b2w_y, const double* b2w_angles, int device, drc_mobile_t** out);
+void drc_mobile_destroy(drc_mobile_t* h);
+int drc_mobile_wheel_num(const drc_mobile_t* h);
+int drc_mobile_synchronize(drc_mobile_t* h);
+long long drc_mobile_launch_count(const drc_mobile_t* h);
+/* Mobile::RobotData::updateState / computeBaseVel / computeFKJacobian (mobile/robot_data.cpp:103-204): per base
+ * J_fk (3 x w row-major; NULL = skip) and base_vel = J_fk * wheel_vel (3; NULL = skip).  wheel_pos is read for caster
+ * bases only (steering angles at the even indices).  DEVICE pointers. */
+int drc_batch_mobile_fk(drc_mobile_t* h, int B, const double* wheel_pos, const double* wheel_vel, double* J_fk, double* base_vel,
+                        int layout, void* stream);
+/* Mobile::RobotController::computeIKJacobian / computeWheelVel / VelocityCommand (mobile/robot_controller.cpp:14-124):
+ * J_ik (w x 3 row-major; NULL = skip), wheel_vel = J_ik * v with v = base_vel_des, saturated as VelocityCommand does
+ * (planar speed to max_lin_speed along its direction, yaw rate to max_ang_speed) when saturate != 0. */
+int drc_batch_mobile_ik(drc_mobile_t* h, int B, const double* wheel_pos, const double* base_vel_des, int saturate, double* J_ik,
+                        double* wheel_vel, int layout, void* stream);
+/* HOST-pointer siblings (batch-major arrays, synchronous) */
+int drc_host_mobile_fk(drc_mobile_t* h, int B, const double* wheel_pos, const double* wheel_vel, double* J_fk, double* base_vel);
+int drc_host_mobile_ik(drc_mobile_t* h, int B, const double* wheel_pos, const double* base_vel_des, int saturate, double* J_ik,
+                       double* wheel_vel);
+
 /* ---- instrumentation (replaces QP::TimeDuration / SuhanBenchmark, QP_base.h:19-43) */
 /* device time in ms of the stages of the LAST cycle/QP call on this context (CUDA events on its stream):
  * [0] joint placements + self-collision narrow phase  [1] state / QP build (EPA pass of the collision stage runs next to

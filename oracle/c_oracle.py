@@ -218,6 +218,30 @@ class Oracle:
         return tau
 
 
+def mobile_base(kin: dict, fk: bool, wheel_pos, vec, saturate: bool = False):
+    """Mobile::RobotData (fk: J (B,3,w), base velocity from wheel velocities) / Mobile::RobotController (not fk: J (B,w,3),
+    wheel velocities from a base velocity; VelocityCommand's saturation when `saturate`) restated in oracle/src/omoma.h.
+    kin: dict like Mobile::KinematicParam (type, wheel_radius, base_width, wheel_offset, max_lin_speed, max_ang_speed,
+    roller_angles, base2wheel_positions, base2wheel_angles)."""
+    t = kin["type"] if isinstance(kin["type"], int) else dict(Differential=0, Mecanum=1, Caster=2)[kin["type"]]
+    pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+    w = 2 if t == 0 else (len(kin["roller_angles"]) if t == 1 else 2 * len(pos))
+    wp = _c(wheel_pos).reshape(-1, w)
+    B = wp.shape[0]
+    v = None if vec is None else _c(vec).reshape(B, w if fk else 3)
+    J = np.zeros((B, 3, w) if fk else (B, w, 3))
+    out = np.zeros((B, 3) if fk else (B, w))
+    ra = _c(kin.get("roller_angles", np.zeros(w))) if t == 1 else None
+    ba = _c(kin.get("base2wheel_angles", np.zeros(w))) if t == 1 else None
+    bx = _c(pos[:, 0]) if len(pos) else None
+    by = _c(pos[:, 1]) if len(pos) else None
+    lib().orc_mobile_base(C.c_int(t), C.c_double(kin.get("wheel_radius", 0.0)), C.c_double(kin.get("base_width", 0.0)),
+                          C.c_double(kin.get("wheel_offset", 0.0)), C.c_double(kin.get("max_lin_speed", 0.0)),
+                          C.c_double(kin.get("max_ang_speed", 0.0)), C.c_int(w), _d(ra), _d(bx), _d(by), _d(ba),
+                          C.c_int(1 if fk else 0), C.c_int(1 if saturate else 0), C.c_int(B), _d(wp), _d(v), _d(J), _d(out))
+    return J, out
+
+
 class MomaOracle(Oracle):
     """Mobile-manipulator restatement (oracle/src/omoma.h).  kin: dict(type, wheel_radius, base_width, wheel_offset,
     roller_angles, base2wheel_positions [(x, y)...], base2wheel_angles) like the reference's Mobile::KinematicParam

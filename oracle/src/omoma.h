@@ -49,6 +49,53 @@ inline void mobile_fk_jacobian(const Model& m, const double* wheel_pos, double* 
   }
 }
 
+// Mobile::RobotController::computeIKJacobian (mobile/robot_controller.cpp:50-124): w x 3, row-major
+inline void mobile_ik_jacobian(const Model& m, const double* wheel_pos, double* Ji) {
+  const int w = m.wheel_num;
+  std::fill(Ji, Ji + 3 * w, 0.0);
+  if (m.drive_type == 0) {                     // DifferentialIKJacobian :65-74
+    Ji[0] = 1 / m.wheel_radius; Ji[2] = -m.base_width / (2 * m.wheel_radius);
+    Ji[3] = 1 / m.wheel_radius; Ji[5] = m.base_width / (2 * m.wheel_radius);
+  } else if (m.drive_type == 1) {              // MecanumIKJacobian :76-102
+    for (int i = 0; i < w; ++i) {
+      const double r = m.wheel_radius, g = m.roller_angles[i], px = m.b2w_x[i], py = m.b2w_y[i], pt = m.b2w_ang[i];
+      const double A1[2][3] = {{1, 0, -py}, {0, 1, px}};
+      const double A2[2][2] = {{std::cos(pt), std::sin(pt)}, {-std::sin(pt), std::cos(pt)}};
+      const double A3[2] = {1.0, std::tan(g)};
+      for (int c = 0; c < 3; ++c) {
+        double v = 0;
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) v += A3[a] * A2[a][b] * A1[b][c];
+        Ji[i * 3 + c] = v / r;
+      }
+    }
+  } else {                                     // CasterIKJacobian :104-123
+    for (int i = 0; i < w / 2; ++i) {
+      const double r = m.wheel_radius, b = m.wheel_offset, px = m.b2w_x[i], py = m.b2w_y[i], phi = wheel_pos[2 * i];
+      Ji[(2 * i) * 3 + 0] = -std::sin(phi) / b; Ji[(2 * i) * 3 + 1] = std::cos(phi) / b;
+      Ji[(2 * i) * 3 + 2] = (px * std::cos(phi) + py * std::sin(phi)) / b - 1;
+      Ji[(2 * i + 1) * 3 + 0] = std::cos(phi) / r; Ji[(2 * i + 1) * 3 + 1] = std::sin(phi) / r;
+      Ji[(2 * i + 1) * 3 + 2] = (px * std::sin(phi) - py * std::cos(phi)) / r;
+    }
+  }
+}
+
+// Mobile::RobotController::VelocityCommand (:14-41) when saturate, computeWheelVel (:43-47) otherwise
+inline void mobile_wheel_velocity(const Model& m, double max_lin_speed, double max_ang_speed, const double* wheel_pos,
+                                  const double* base_vel, bool saturate, double* wheel_vel) {
+  double v[3] = {base_vel[0], base_vel[1], base_vel[2]};
+  if (saturate) {
+    double speed = std::sqrt(v[0] * v[0] + v[1] * v[1]);
+    double dir[2] = {0, 0};
+    if (!(std::fabs(speed) < 1e-4)) { dir[0] = v[0] / speed; dir[1] = v[1] / speed; }
+    speed = std::min(std::max(speed, -max_lin_speed), max_lin_speed);
+    v[0] = dir[0] * speed; v[1] = dir[1] * speed;
+    v[2] = std::min(std::max(v[2], -max_ang_speed), max_ang_speed);
+  }
+  std::vector<double> Ji(3 * m.wheel_num);
+  mobile_ik_jacobian(m, wheel_pos, Ji.data());
+  for (int k = 0; k < m.wheel_num; ++k) wheel_vel[k] = Ji[k * 3] * v[0] + Ji[k * 3 + 1] * v[1] + Ji[k * 3 + 2] * v[2];
+}
+
 struct MomaState {
   int act = 0, mani = 0;
   double S[MAXV * MAXV];                          // dof x act

@@ -341,6 +341,38 @@ void orc_mobile_state(OrcHandle* h, int B, const double* wheel_pos, const double
       }
   }
 }
+// Mobile::RobotData / Mobile::RobotController without a URDF: the base is its KinematicParam (type_define.h:58-72).
+// fk != 0: J (B, 3, w) and out = base velocity (B, 3) from in = wheel velocities (B, w)
+// fk == 0: J (B, w, 3) and out = wheel velocities (B, w) from in = base velocity (B, 3) [VelocityCommand when saturate]
+void orc_mobile_base(int drive_type, double wheel_radius, double base_width, double wheel_offset, double max_lin_speed,
+                     double max_ang_speed, int wheel_num, const double* roller_angles, const double* b2w_x, const double* b2w_y,
+                     const double* b2w_ang, int fk, int saturate, int B, const double* wheel_pos, const double* in, double* J,
+                     double* out) {
+  Model m;
+  m.drive_type = drive_type; m.wheel_radius = wheel_radius; m.base_width = base_width; m.wheel_offset = wheel_offset;
+  m.wheel_num = wheel_num;
+  const int w = wheel_num, np = drive_type == 2 ? w / 2 : w;
+  m.roller_angles.assign(w, 0.0); m.b2w_x.assign(np, 0.0); m.b2w_y.assign(np, 0.0); m.b2w_ang.assign(w, 0.0);
+  for (int i = 0; i < w; ++i) { if (roller_angles) m.roller_angles[i] = roller_angles[i]; if (b2w_ang) m.b2w_ang[i] = b2w_ang[i]; }
+  for (int i = 0; i < np; ++i) { if (b2w_x) m.b2w_x[i] = b2w_x[i]; if (b2w_y) m.b2w_y[i] = b2w_y[i]; }
+  std::vector<double> zeros(w, 0.0), Jm(3 * w);
+  for (int b = 0; b < B; ++b) {
+    const double* wp = wheel_pos ? wheel_pos + w * b : zeros.data();
+    if (fk) {
+      mobile_fk_jacobian(m, wp, Jm.data());
+      if (J) std::copy(Jm.begin(), Jm.end(), J + 3 * w * b);
+      if (out && in)
+        for (int r = 0; r < 3; ++r) {
+          double v = 0;
+          for (int k = 0; k < w; ++k) v += Jm[r * w + k] * in[w * b + k];
+          out[3 * b + r] = v;
+        }
+    } else {
+      if (J) mobile_ik_jacobian(m, wp, J + 3 * w * b);
+      if (out && in) mobile_wheel_velocity(m, max_lin_speed, max_ang_speed, wp, in + 3 * b, saturate != 0, out + w * b);
+    }
+  }
+}
 // MobileManipulator::RobotData::updateState on full-dof vectors: S (n x act), M~, M~^-1, g~, nle~, J~, J~dot, manipulability
 void orc_moma_update_state(OrcHandle* h, int B, const double* q, const double* qd, int frame, double* S, double* Mact,
                            double* Minv_act, double* g_act, double* nle_act, double* Jt, double* Jtd, double* mani,

@@ -71,6 +71,11 @@ MOMA = {
                              base2wheel_positions=[(0.2225, 0.2045), (0.2225, -0.2045), (-0.2225, 0.2045), (-0.2225, -0.2045)],
                              base2wheel_angles=[0.0, 0.0, 0.0, 0.0]),
                     joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=7), actuator_idx=dict(mobi_start=0, mani_start=4)),
+    # powered casters (mobile/robot_data.cpp:179-203): two casters, wheel joints ordered (steer, roll) per caster
+    "pcv_fr3": dict(urdf=str(ROBOTS / "pcv_fr3" / "pcv_fr3.urdf"), srdf=str(ROBOTS / "pcv_fr3" / "pcv_fr3.srdf"),
+                    kin=dict(type="Caster", wheel_radius=0.055, wheel_offset=0.020,
+                             base2wheel_positions=[(0.215, 0.125), (-0.215, -0.125)]),
+                    joint_idx=dict(virtual_start=0, mobi_start=3, mani_start=7), actuator_idx=dict(mobi_start=0, mani_start=4)),
 }
 
 

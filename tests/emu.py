@@ -200,3 +200,25 @@ def pair_lower_bound(ta, prm_a, Ta, tb, prm_b, Tb):
         T = np.asarray(T, np.float64)
         return np.ascontiguousarray(T.reshape(-1)[:12] if T.size == 12 else T[:3, :].reshape(12))
     return float(lib().emu_pair_lower_bound(C.c_int(ta), _d(_c(prm_a)), _d(p12(Ta)), C.c_int(tb), _d(_c(prm_b)), _d(p12(Tb))))
+
+
+def mobile_base(kin: dict, fk: bool, wheel_pos, vec, saturate: bool = False):
+    """Bodies of k_mobile_fk / k_mobile_ik (csrc/drc_mobile.h) on the CPU; same interface as oracle.c_oracle.mobile_base."""
+    t = kin["type"] if isinstance(kin["type"], int) else dict(Differential=0, Mecanum=1, Caster=2)[kin["type"]]
+    pos = np.asarray(kin.get("base2wheel_positions", np.zeros((0, 2))), np.float64).reshape(-1, 2)
+    w = 2 if t == 0 else (len(kin["roller_angles"]) if t == 1 else 2 * len(pos))
+    wp = _c(wheel_pos).reshape(-1, w)
+    B = wp.shape[0]
+    v = None if vec is None else _c(vec).reshape(B, w if fk else 3)
+    J = np.zeros((B, 3, w) if fk else (B, w, 3))
+    out = np.zeros((B, 3) if fk else (B, w))
+    ra = _c(kin.get("roller_angles", np.zeros(w))) if t == 1 else None
+    ba = _c(kin.get("base2wheel_angles", np.zeros(w))) if t == 1 else None
+    bx = _c(pos[:, 0]) if len(pos) else None
+    by = _c(pos[:, 1]) if len(pos) else None
+    rc = lib().emu_mobile(C.c_int(t), C.c_double(kin.get("wheel_radius", 0.0)), C.c_double(kin.get("base_width", 0.0)),
+                          C.c_double(kin.get("wheel_offset", 0.0)), C.c_double(kin.get("max_lin_speed", 0.0)),
+                          C.c_double(kin.get("max_ang_speed", 0.0)), C.c_int(w), _d(ra), _d(bx), _d(by), _d(ba),
+                          C.c_int(1 if fk else 0), C.c_int(1 if saturate else 0), C.c_int(B), _d(wp), _d(v), _d(J), _d(out))
+    assert rc == 0, rc
+    return J, out

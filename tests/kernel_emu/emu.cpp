@@ -420,3 +420,35 @@ int emu_moma_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q,
 }
 
 }  // extern "C"
+
+// ---- mobile base alone (Mobile::RobotData / Mobile::RobotController): the bodies of k_mobile_fk / k_mobile_ik
+extern "C" int emu_mobile(int drive_type, double wheel_radius, double base_width, double wheel_offset, double max_lin_speed,
+                          double max_ang_speed, int w, const double* roller, const double* b2w_x, const double* b2w_y,
+                          const double* b2w_ang, int fk, int saturate, int B, const double* wheel_pos, const double* in, double* J,
+                          double* out) {
+  try {
+    MobileParam p;
+    p.drive_type = drive_type; p.wheel_radius = wheel_radius; p.base_width = base_width; p.wheel_offset = wheel_offset;
+    const int np = drive_type == kCaster ? w / 2 : w;
+    for (int i = 0; i < w && roller; ++i) p.roller_angles.push_back(roller[i]);
+    for (int i = 0; i < np && b2w_x; ++i) { p.b2w_x.push_back(b2w_x[i]); p.b2w_y.push_back(b2w_y[i]); }
+    for (int i = 0; i < w && b2w_ang; ++i) p.b2w_angles.push_back(b2w_ang[i]);
+    MobileDev d;
+    std::memset(&d, 0, sizeof d);
+    d.drive_type = drive_type; d.wheel_num = w; d.wheel_radius = wheel_radius; d.base_width = base_width; d.wheel_offset = wheel_offset;
+    d.max_lin_speed = max_lin_speed; d.max_ang_speed = max_ang_speed;
+    for (size_t i = 0; i < p.b2w_x.size(); ++i) { d.b2w_x[i] = p.b2w_x[i]; d.b2w_y[i] = p.b2w_y[i]; }
+    mobile_constant_jacobians(p, w, d.J_fk, d.J_ik);
+    MobileIO io;
+    std::memset(&io, 0, sizeof io);
+    io.B = B; io.wheel_pos = wheel_pos; io.swp = aos(w); io.J = J; io.sj = aos(3 * w); io.out = out; io.saturate = saturate;
+    if (fk) { io.wheel_vel = in; io.swv = aos(w); io.so = aos(3); }
+    else { io.base_vel = in; io.sbv = aos(3); io.so = aos(w); }
+    for (int b = 0; b < B; ++b) {
+      if (fk) mobile_fk_job(d, io, b); else mobile_ik_job(d, io, b);
+    }
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}

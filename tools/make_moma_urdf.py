@@ -2,6 +2,7 @@
 """Synthesize the two mobile-manipulator models of BASELINE configs 4-5 (NOT from the reference, which ships no
 mobile-manipulator URDF): the reference's FR3 arm (examples/robots/fr3/fr3.urdf) mounted on
   * husky_fr3: differential-drive base, 2 wheel joints, r = 0.1651 m, track 0.555 m (public Husky A200 figures, synthetic inertia)
+  * pcv_fr3:   powered-caster base, 2 casters = 4 joints (steer about z, roll about y, offset 0.020 m, r = 0.055 m); synthetic
   * xls_fr3:   mecanum base, 4 wheel joints; base mass/inertia and wheel mass from the reference's
                examples/robots/xls/summit_xls.xml:38,58-61, wheel parameters from examples/C++/src/xls_controller.cpp:18-27
 behind three virtual joints (prismatic x, prismatic y, revolute z) as MobileManipulator::RobotData requires
@@ -20,7 +21,7 @@ def inertial(mass, ixx, iyy, izz, xyz="0 0 0"):
             f'<inertia ixx="{ixx}" ixy="0" ixz="0" iyy="{iyy}" iyz="0" izz="{izz}"/></inertial>')
 
 
-def build(name, base_mass, base_inertia, base_box, base_z, wheels, wheel_mass, wheel_r, mount_xyz):
+def build(name, base_mass, base_inertia, base_box, base_z, wheels, wheel_mass, wheel_r, mount_xyz, caster_offset=None):
     fr3 = (ROBOTS / "fr3" / "fr3.urdf").read_text()
     body = fr3[fr3.index("<robot"):]
     body = body[body.index(">") + 1: body.rindex("</robot>")].replace('"base_link"', '"fr3_base"')
@@ -38,6 +39,18 @@ def build(name, base_mass, base_inertia, base_box, base_z, wheels, wheel_mass, w
            f'<collision><origin xyz="0 0 {base_z}" rpy="0 0 0"/><geometry><box size="{base_box[0]} {base_box[1]} {base_box[2]}"/></geometry></collision></link>']
     iw = 0.5 * wheel_mass * wheel_r ** 2
     for wname, (x, y) in wheels:
+        if caster_offset is not None:
+            # powered caster: steering joint about z on the base, rolling joint about y on the steering fork, trailing the
+            # steering axis by the caster offset b (joint order steer, roll = the reference's wheel_pos layout,
+            # mobile/robot_data.cpp:181-182)
+            h = 2.0 * wheel_r
+            out.append(f'  <joint name="{wname}_steer" type="continuous"><parent link="mobile_base"/><child link="{wname}_fork"/>'
+                       f'<origin xyz="{x} {y} {h}" rpy="0 0 0"/><axis xyz="0 0 1"/><limit velocity="20" effort="100"/></joint>')
+            out.append(f'  <link name="{wname}_fork">{inertial(0.5, 0.001, 0.001, 0.001)}</link>')
+            out.append(f'  <joint name="{wname}_roll" type="continuous"><parent link="{wname}_fork"/><child link="{wname}_link"/>'
+                       f'<origin xyz="{-caster_offset} 0 {-(h - wheel_r)}" rpy="0 0 0"/><axis xyz="0 1 0"/><limit velocity="40" effort="100"/></joint>')
+            out.append(f'  <link name="{wname}_link">{inertial(wheel_mass, 0.5 * iw + wheel_mass * 0.001, iw, 0.5 * iw + wheel_mass * 0.001)}</link>')
+            continue
         out.append(f'  <joint name="{wname}" type="continuous"><parent link="mobile_base"/><child link="{wname}_link"/>'
                    f'<origin xyz="{x} {y} {wheel_r}" rpy="0 0 0"/><axis xyz="0 1 0"/><limit velocity="20" effort="100"/></joint>')
         out.append(f'  <link name="{wname}_link">{inertial(wheel_mass, 0.5 * iw + wheel_mass * 0.01, iw, 0.5 * iw + wheel_mass * 0.01)}</link>')
@@ -59,3 +72,7 @@ if __name__ == "__main__":
     build("xls_fr3", 125.0, (1.391, 6.853, 6.125), (0.72, 0.61, 0.30), 0.25,
           [("wheel_fl", (0.2225, 0.2045)), ("wheel_fr", (0.2225, -0.2045)), ("wheel_rl", (-0.2225, 0.2045)),
            ("wheel_rr", (-0.2225, -0.2045))], 6.5, 0.120, (0.25, 0.0, 0.42))
+    # powered-caster base (Holmberg & Khatib's PCV class): two casters, 4 joints (steer, roll each); all figures synthetic
+    build("pcv_fr3", 80.0, (1.2, 3.4, 4.1), (0.70, 0.50, 0.25), 0.25,
+          [("caster_front", (0.215, 0.125)), ("caster_rear", (-0.215, -0.125))], 1.2, 0.055, (0.20, 0.0, 0.40),
+          caster_offset=0.020)
