@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_c
   }
 }
 
-constexpr int kAdmmWarps = 1;  // one warp per block: a finished warp frees its slot without waiting for block-mates
+#ifndef DRC_ADMM_WARPS
+#define DRC_ADMM_WARPS 1
+#endif
+constexpr int kAdmmWarps = DRC_ADMM_WARPS;  // one warp per block: a finished warp frees its slot without waiting for block-mates
 template <class Cfg, bool ID, int MINB>
-__global__ void __launch_bounds__(kAdmmWarps * 32, 4 * MINB) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
+__global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
   extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
   GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -40,11 +40,12 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; }
 
 #define J(FL, IO, ST) launch_job<NV, CHAIN, FL>(c, fr, IO, ST)
+  // QPIK does not read the dynamics (M, M^-1, g, nle of updateState): in fused calls they leave the critical path -- the QP
+  // record is built from the state stage 1 has just cached, and a dynamics-only kernel runs on its own stream behind the
+  // ADMM launch, where it fills the SMs the convergence tail leaves idle (the call still ends with the full cache).
+  const bool split_dyn = fused && !id;
   auto build = [&](const JobIO& jio, cudaStream_t st) -> int {  // state update, manipulability, QP record except the collision row
-    if (!id) {
-      if (fused) return step ? J(F_DYN | F_STORE | F_QPIK | F_STEP, jio, st) : J(F_DYN | F_STORE | F_QPIK, jio, st);
-      return step ? J(F_FROM_CACHE | F_QPIK | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPIK, jio, st);
-    }
+    if (!id) return step ? J(F_FROM_CACHE | F_QPIK | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPIK, jio, st);
     if (fused) return step ? J(F_DYN | F_STORE | F_QPID | F_STEP, jio, st) : J(F_DYN | F_STORE | F_QPID, jio, st);
     return step ? J(F_FROM_CACHE | F_QPID | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPID, jio, st);
   };
@@ -78,6 +79,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   // ---- main pipeline
   // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; its EPA pass goes to the side stream
   if (fused) { rc = J(F_STORE, io, s); if (rc) return rc; }
+  if (split_dyn) CU(cudaEventRecord(c->ev_store, s));
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp; cio.qp_stride = qp_stride; cio.qp_row_off = qp_row_off;
@@ -99,6 +101,12 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (prio) sio.order_off = c->slow_count;   // those robots are solved by the priority pipeline
   rc = id ? launch_admm<QpidCfg<NV>, true>(c, sio, s) : launch_admm<QpikCfg<NV>, false>(c, sio, s);
   if (rc) return rc;
+  if (split_dyn) {  // enqueued behind the ADMM launch: its blocks are dispatched as the solver's grid drains
+    CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_store, 0));
+    rc = launch_job<NV, CHAIN, F_DYN | F_FROM_CACHE>(c, fr, io, c->dyn_stream); if (rc) return rc;
+    CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
+    CU(cudaStreamWaitEvent(s, c->ev_dyn, 0));
+  }
   if (prio) CU(cudaStreamWaitEvent(s, c->ev_prio, 0));
   if (c->timing) cudaEventRecord(c->ev[3], s);
   return rc;
@@ -248,6 +256,9 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
     CU(cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->dyn_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_store, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_dyn, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_late, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming));
   }
@@ -292,6 +303,9 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
     if (c->ev_prio) cudaEventDestroy(c->ev_prio);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+    if (c->dyn_stream) { cudaStreamSynchronize(c->dyn_stream); cudaStreamDestroy(c->dyn_stream); }
+    if (c->ev_store) cudaEventDestroy(c->ev_store);
+    if (c->ev_dyn) cudaEventDestroy(c->ev_dyn);
     if (c->ev_late) cudaEventDestroy(c->ev_late);
     if (c->ev_early) cudaEventDestroy(c->ev_early);
   }
@@ -343,6 +357,7 @@ int drc_ctx_synchronize(drc_ctx_t* c) {
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->side));
   CU(cudaStreamSynchronize(c->prio_stream));
+  CU(cudaStreamSynchronize(c->dyn_stream));
   return DRC_OK;
 }
 void* drc_ctx_stream(drc_ctx_t* c) { return c ? (void*)c->stream : nullptr; }

@@ -112,6 +112,26 @@ def test_unfused_equals_fused(gpu_ctx, oracle):
     assert same.mean() > 0.99 and np.abs(c["out"] - ref["out"])[same].max() < 1e-4
 
 
+def test_fused_cycle_leaves_the_full_state_cache(gpu_ctx, oracle):
+    """updateState + QPIKStep in one call: the dynamics (M, M^-1, g, nle) are computed by a kernel that runs next to the ADMM
+    solve (QPIK does not read them); after the call every getter must answer for the NEW state, batches large and small."""
+    model, ctx = gpu_ctx
+    f = oracle.frame_id(LINK)
+    for B, seed in ((9000, 31), (300, 32)):
+        q0, qd0, _, _ = workload(oracle.model, B, seed + 100)
+        ctx.update_state(q0, qd0)                       # stale cache of another state
+        q, qd, q_t, xdot_t = workload(oracle.model, B, seed)
+        x_t = oracle.update_state(q_t, qd, f)["pose"]
+        ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)
+        ref = oracle.update_state(q, qd, f)
+        dy = ctx.get_dynamics()
+        rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+        assert rel(dy["M"], ref["M"]) < 1e-9 and rel(dy["g"], ref["g"]) < 1e-9 and rel(dy["nle"], ref["nle"]) < 1e-9
+        assert np.abs(np.einsum("bij,bjk->bik", dy["Minv"], ref["M"]) - np.eye(7)).max() < 1e-7
+        fr = ctx.get_frame(LINK)
+        assert rel(fr["J"], ref["J"]) < 1e-12 and rel(fr["pose"], ref["pose"]) < 1e-12
+
+
 def test_device_pointer_path(gpu_ctx, oracle):
     """torch CUDA tensors -> drc_batch_* (device pointers, async) gives the host path's result."""
     import torch
