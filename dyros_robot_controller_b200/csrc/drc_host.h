@@ -63,6 +63,7 @@ struct drc_ctx {
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
   cudaEvent_t ev_sched, ev_prio;
+  cudaEvent_t ev_in, ev_out;   // joins of a caller stream with the context's prioritised streams (fused QPIK cycles)
   cudaStream_t dyn_stream; cudaEvent_t ev_store, ev_dyn;  // fused QPIK cycles: dynamics-only kernel behind the ADMM launch
   cudaStream_t copy;                     // host entry points: inputs that only stage 2 reads are uploaded here, behind stage 1
   cudaEvent_t ev_late, ev_early; bool late_pending;

@@ -30,9 +30,17 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   io.qp = c->qp;
   bind_cache(c, io);
   const DrcFrame fr = frame_of(c->model, frame);
+  const bool fused = q != nullptr;
+  // Fused QPIK cycles run on the context's own streams, whose priorities order the block dispatch: priority pipeline >
+  // main pipeline > dynamics-only kernel.  A caller stream is joined by events on both sides.
+  cudaStream_t caller = s;
+  if (fused && !id && s != c->stream) {
+    CU(cudaEventRecord(c->ev_in, caller));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
+    s = c->stream;
+  }
   if (c->timing) cudaEventRecord(c->ev[0], s);
   int rc;
-  const bool fused = q != nullptr;
   const int qp_stride = id ? QpidCfg<NV>::STRIDE : QpikCfg<NV>::STRIDE;
   const int qp_row_off = (id ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (NV + 1);
   const bool sched = c->prm.schedule_hint != 0 && B >= 64;
@@ -109,6 +117,10 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   }
   if (prio) CU(cudaStreamWaitEvent(s, c->ev_prio, 0));
   if (c->timing) cudaEventRecord(c->ev[3], s);
+  if (caller != s) {
+    CU(cudaEventRecord(c->ev_out, s));
+    CU(cudaStreamWaitEvent(caller, c->ev_out, 0));
+  }
   return rc;
 }
 
@@ -205,8 +217,13 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   for (int i = 0; i < kMaxV; ++i) { c->prm.Kp_joint[i] = 400; c->prm.Kv_joint[i] = 40; }
   const int n = m->hm.dev.nv;
   const size_t B = (size_t)max_batch;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority; lo is the default (lowest) level
+  CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  const int prio_main = prio_hi < prio_lo ? prio_lo - 1 : prio_lo;   // one level above the dynamics-only stream
+  CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_main));
+  CU(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_main));
+  CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming));
   auto dalloc = [&](double** p, size_t cnt) { return cudaMalloc((void**)p, cnt * sizeof(double)); };
@@ -256,7 +273,7 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
     CU(cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->dyn_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&c->dyn_stream, cudaStreamNonBlocking, prio_lo));
     CU(cudaEventCreateWithFlags(&c->ev_store, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_dyn, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_late, cudaEventDisableTiming));
@@ -305,6 +322,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
     if (c->dyn_stream) { cudaStreamSynchronize(c->dyn_stream); cudaStreamDestroy(c->dyn_stream); }
     if (c->ev_store) cudaEventDestroy(c->ev_store);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->ev_dyn) cudaEventDestroy(c->ev_dyn);
     if (c->ev_late) cudaEventDestroy(c->ev_late);
     if (c->ev_early) cudaEventDestroy(c->ev_early);

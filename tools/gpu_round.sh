@@ -13,7 +13,7 @@ for k in k_admm k_collision k_robot_job; do
   # MAIN-pipeline launch of the second control tick (the ADMM schedule then has the previous tick's iteration counts).
   # Launch order per tick: priority pipeline (FK store, collision, build, ADMM) then main pipeline (same kernels);
   # tools/prof_cycle.py adds two k_robot_job launches for its set-up.
-  skip=3; [ "$k" = "k_robot_job" ] && skip=9
+  skip=3; [ "$k" = "k_robot_job" ] && skip=10   # per tick: prio FK, prio build, main FK, main build, dynamics-only
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip -c 1 -f -o gpurun_out/${tag}_${k} \
     python tools/prof_cycle.py 65536 2 > gpurun_out/${tag}_ncu_${k}.log 2>&1
   # gpurun_out/ is capped at 64 MiB: keep the CSV pages, drop the report
