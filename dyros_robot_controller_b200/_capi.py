@@ -54,6 +54,7 @@ SYMBOLS = [
     "drc_batch_moma_qpid", "drc_batch_moma_qpid_step", "drc_batch_moma_cycle_qpik_step", "drc_batch_moma_cycle_qpid_step",
     "drc_host_moma_update_state", "drc_host_moma_get_state", "drc_host_moma_qpik", "drc_host_moma_qpik_step",
     "drc_host_moma_qpid", "drc_host_moma_qpid_step", "drc_host_moma_cycle_qpik_step", "drc_host_moma_cycle_qpid_step",
+    "drc_batch_rollout_qpik", "drc_host_rollout_qpik",
     "drc_mobile_create", "drc_mobile_destroy", "drc_mobile_wheel_num", "drc_mobile_synchronize", "drc_mobile_launch_count",
     "drc_batch_mobile_fk", "drc_batch_mobile_ik", "drc_host_mobile_fk", "drc_host_mobile_ik",
 ]

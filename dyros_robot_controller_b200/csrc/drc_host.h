@@ -59,6 +59,7 @@ struct drc_ctx {
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
+  double* roll; int* roll_i;             // rollout scratch (command, cubic profile; status, iterations), allocated on first use
   int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline

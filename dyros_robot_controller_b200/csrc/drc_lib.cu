@@ -124,6 +124,29 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   return rc;
 }
 
+// Closed-loop rollout: the caller's integrate step between control ticks,
+// q_desired = q + qdot_desired * dt (examples/C++/src/fr3_controller.cpp:129-131), with ideal tracking of the command
+// (q <- q_desired, qdot <- qdot_desired) standing in for the simulator.  One thread per robot.
+struct RolloutIO {
+  int B, nv;
+  double dt;
+  double *q, *qd; Strided sq;
+  const double* cmd; Strided sc;
+  const int *status, *iters;
+  int *fail_ticks, *iters_total;
+};
+static __global__ void __launch_bounds__(128) k_rollout_integrate(const RolloutIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= io.B) return;
+  for (int i = 0; i < io.nv; ++i) {
+    const double v = io.cmd[b * io.sc.sb + i * io.sc.sk];
+    io.q[b * io.sq.sb + i * io.sq.sk] += io.dt * v;
+    io.qd[b * io.sq.sb + i * io.sq.sk] = v;
+  }
+  if (io.fail_ticks) io.fail_ticks[b] += io.status[b] != kQpSolved ? 1 : 0;
+  if (io.iters_total) io.iters_total[b] += io.iters[b];
+}
+
 extern "C" {
 
 const char* drc_last_error(void) { return g_err.c_str(); }
@@ -306,6 +329,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->epa_list) cudaFree(c->epa_list);
   if (c->epa_count) cudaFree(c->epa_count);
   if (c->prev_iters) cudaFree(c->prev_iters);
+  if (c->roll) cudaFree(c->roll);
+  if (c->roll_i) cudaFree(c->roll_i);
   if (c->order) cudaFree(c->order);
   if (c->sched_hist) cudaFree(c->sched_hist);
   if (c->slow_count) cudaFree(c->slow_count);
@@ -492,6 +517,46 @@ int drc_batch_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double
   QP_ENTRY(true, true, q, qdot, x_target, xdot_target, tau_out, nullptr)
 }
 
+// T control ticks of QPIKCubic / QPIKStep + the integrate step, without a host round trip between ticks
+int drc_batch_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,
+                           const double* xdot_target, const double* x_init, const double* xdot_init, double t_start, double t0,
+                           double duration, int frame, int* fail_ticks, int* iters_total, int layout, void* stream) {
+  int rc = check_batch(c, B); if (rc) return rc;
+  rc = check_frame(c, frame); if (rc) return rc;
+  if (!q || !qdot || !x_target || !xdot_target) return fail(DRC_E_INVALID, "null argument");
+  if (T <= 0 || !(dt > 0)) return fail(DRC_E_INVALID, "rollout needs T > 0 ticks and dt > 0");
+  const bool cubic = duration > 0;
+  if (cubic && (!x_init || !xdot_init)) return fail(DRC_E_INVALID, "a cubic profile needs x_init and xdot_init");
+  CU(cudaSetDevice(c->device));
+  const int n = c->model->hm.dev.nv;
+  if (!c->roll) {  // command / profile scratch, allocated on first use
+    CU(cudaMalloc((void**)&c->roll, (size_t)c->cap * (n + 12 + 6) * sizeof(double)));
+    CU(cudaMalloc((void**)&c->roll_i, (size_t)c->cap * 2 * sizeof(int)));
+  }
+  double *cmd = c->roll, *x_des = c->roll + (size_t)c->cap * n, *xd_des = x_des + (size_t)c->cap * 12;
+  int *st = c->roll_i, *it = c->roll_i + c->cap;
+  cudaStream_t s = pick(c, stream);
+  if (fail_ticks) CU(cudaMemsetAsync(fail_ticks, 0, (size_t)B * sizeof(int), s));
+  if (iters_total) CU(cudaMemsetAsync(iters_total, 0, (size_t)B * sizeof(int), s));
+  for (int k = 0; k < T; ++k) {
+    const double *xt = x_target, *xd = xdot_target;
+    if (cubic) {  // DyrosMath::getTaskSpaceCubic at the tick's time (QPIKCubic, robot_controller.cpp:302-317)
+      rc = drc_batch_task_space_cubic(c, B, x_target, xdot_target, x_init, xdot_init, t_start + k * dt, t0, duration, x_des, xd_des, layout, s);
+      if (rc) return rc;
+      xt = x_des; xd = xd_des;
+    }
+    rc = drc_batch_cycle_qpik_step(c, B, q, qdot, xt, xd, frame, cmd, st, it, layout, s);
+    if (rc) return rc;
+    RolloutIO io;
+    io.B = B; io.nv = n; io.dt = dt; io.q = q; io.qd = qdot; io.sq = lay(layout, n, B); io.cmd = cmd; io.sc = io.sq;
+    io.status = st; io.iters = it; io.fail_ticks = fail_ticks; io.iters_total = iters_total;
+    k_rollout_integrate<<<(B + 127) / 128, 128, 0, s>>>(io);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
+  return DRC_OK;
+}
+
 static int taskspace(drc_ctx_t* c, int B, int kind, const double* x_target, const double* xdot, const double* aux, const double* aux2,
                      int frame, double* out, int layout, void* stream) {
   int rc = check_batch(c, B); if (rc) return rc;
@@ -643,6 +708,20 @@ int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double*
   double* dout = st.out(tau_out, Bz * n);
   int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpid_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
+}
+
+int drc_host_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,
+                          const double* xdot_target, const double* x_init, const double* xdot_init, double t_start, double t0,
+                          double duration, int frame, int* fail_ticks, int* iters_total) {
+  HOST_PRELUDE
+  if (!q || !qdot) return fail(DRC_E_INVALID, "null state pointer");
+  double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n);
+  const double *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6), *dxi = st.in(x_init, Bz * 12), *dxdi = st.in(xdot_init, Bz * 6);
+  if (dq) st.outs.push_back({q, dq, Bz * n * sizeof(double)});      // the state arrays are updated in place
+  if (dqd) st.outs.push_back({qdot, dqd, Bz * n * sizeof(double)});
+  int *df = st.out_i(fail_ticks, Bz), *di = st.out_i(iters_total, Bz);
+  return st.finish(st.err ? st.err : drc_batch_rollout_qpik(c, B, T, dt, dq, dqd, dxt, dx, dxi, dxdi, t_start, t0, duration, frame, df, di,
+                                                            DRC_LAYOUT_AOS, nullptr));
 }
 
 int drc_bench_fp64_peak(int device, double* tflops) {

@@ -447,6 +447,43 @@ class Context:
         self._B = B
         return dict(out=out, status=status, iters=iters)
 
+    def rollout_qpik(self, q, qdot, x_target, xdot_target, link, ticks, dt, x_init=None, xdot_init=None, t_start=0.0, t0=0.0,
+                     duration=0.0):
+        """Closed-loop rollout: `ticks` control cycles of updateState + QPIKCubic (duration > 0) / QPIKStep, each followed by
+        the example's integrate step q += qdot* dt, qdot = qdot* (examples/C++/src/fr3_controller.cpp:116-131); no host round
+        trip between ticks.  torch tensors are updated in place; numpy inputs are copied.  Returns q, qdot, fail_ticks,
+        iters_total."""
+        f = self._frame(link)
+        if _is_torch(q):
+            import torch
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            xt, _ = self._t_in(x_target if x_target.shape[-1] == 12 else x_target[..., :3, :].reshape(-1, 12), 12, B)
+            xd, _ = self._t_in(xdot_target, 6, B)
+            xi = xdi = None
+            if duration > 0:
+                xi, _ = self._t_in(x_init if x_init.shape[-1] == 12 else x_init[..., :3, :].reshape(-1, 12), 12, B)
+                xdi, _ = self._t_in(xdot_init, 6, B)
+            fail = torch.empty(B, dtype=torch.int32, device=q.device)
+            its = torch.empty(B, dtype=torch.int32, device=q.device)
+            check(lib().drc_batch_rollout_qpik(self._h, B, int(ticks), C.c_double(dt), self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd),
+                                               self._tp(xi), self._tp(xdi), C.c_double(t_start), C.c_double(t0), C.c_double(duration), f,
+                                               self._tp(fail), self._tp(its), _capi.LAYOUT_AOS, self._stream()), "drc_batch_rollout_qpik")
+            return dict(q=q, qdot=qd, fail_ticks=fail, iters_total=its)
+        q, B = self._np_in(np.array(q, np.float64), self.n)
+        qd, _ = self._np_in(np.array(qdot, np.float64), self.n, B)
+        xt, _ = self._np_in(pose12(x_target), 12, B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        xi = xdi = None
+        if duration > 0:
+            xi, _ = self._np_in(pose12(x_init), 12, B)
+            xdi, _ = self._np_in(xdot_init, 6, B)
+        fail, its = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        check(lib().drc_host_rollout_qpik(self._h, B, int(ticks), C.c_double(dt), self._p(q), self._p(qd), self._p(xt), self._p(xd),
+                                          self._p(xi), self._p(xdi), C.c_double(t_start), C.c_double(t0), C.c_double(duration), f,
+                                          self._pi(fail), self._pi(its)), "drc_host_rollout_qpik")
+        return dict(q=q, qdot=qd, fail_ticks=fail, iters_total=its)
+
     def cycle_qpid_step(self, q, qdot, x_target, xdot_target, link, out=None, status=None, iters=None):
         """updateState + QPIDStep -> torque.  numpy in -> numpy out (host path); torch CUDA in -> torch out (async)."""
         f = self._frame(link)

@@ -141,6 +141,16 @@ int drc_batch_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double
                               void* stream);
 
 /* ---- host-buffer variants (AoS, synchronous): what a CPU caller of the reference classes uses */
+/* ---- closed-loop rollout (the caller of the path: examples/C++/src/fr3_controller.cpp:116-131).  T control ticks of
+ * updateState + QPIKCubic (duration > 0: DyrosMath::getTaskSpaceCubic from (x_init, xdot_init) at t0 to (x_target,
+ * xdot_target) at t0 + duration, evaluated at t_start + k dt; robot_controller.cpp:302-317) or QPIKStep (duration <= 0,
+ * x_init / xdot_init may be NULL), each followed by the example's integrate step q_desired = q + qdot_desired dt with ideal
+ * tracking (q <- q_desired, qdot <- qdot_desired).  q, qdot are updated IN PLACE; nothing returns to the host between
+ * ticks.  fail_ticks / iters_total (int, B; may be NULL): ticks whose QP was not Solved (command 0), total ADMM iterations. */
+int drc_batch_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,
+                           const double* xdot_target, const double* x_init, const double* xdot_init, double t_start, double t0,
+                           double duration, int frame, int* fail_ticks, int* iters_total, int layout, void* stream);
+
 int drc_host_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot);
 int drc_host_get_frame(drc_ctx_t* c, int B, int frame, double* pose12, double* J, double* Jdot, double* vel);
 int drc_host_get_dynamics(drc_ctx_t* c, int B, double* M, double* Minv, double* g, double* coriolis, double* nle);
@@ -162,6 +172,9 @@ int drc_host_osf_step(drc_ctx_t* c, int B, const double* x_target, const double*
 int drc_host_joint_torque_step(drc_ctx_t* c, int B, const double* q_target, const double* qdot_target, double* tau_out);
 int drc_host_task_space_cubic(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* x_init,
                               const double* xdot_init, double t, double t0, double duration, double* x_des, double* xdot_des);
+int drc_host_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,
+                          const double* xdot_target, const double* x_init, const double* xdot_init, double t_start, double t0,
+                          double duration, int frame, int* fail_ticks, int* iters_total);
 int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
                              const double* xdot_target, int frame, double* qdot_out, int* status, int* iters);
 int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,

@@ -1,0 +1,86 @@
+"""GPU parity of the closed-loop rollout: T control ticks of QPIKCubic / QPIKStep + the example's
+integrate step (examples/C++/src/fr3_controller.cpp:116-131) in one call, against the same loop run tick by tick through
+the oracle on the CPU."""
+import numpy as np
+import pytest
+
+from tests.conftest import LINK, workload
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_rollout(oracle, q, qd, x_t, xd_t, T, dt, x_i=None, xd_i=None, t_start=0.0, t0=0.0, dur=0.0):
+    from oracle import c_oracle
+    f = oracle.frame_id(LINK)
+    q, qd = q.copy(), qd.copy()
+    fail, its = np.zeros(len(q), np.int32), np.zeros(len(q), np.int32)
+    for k in range(T):
+        if dur > 0:
+            xs, xds = [], []
+            for b in range(len(q)):
+                X, V = c_oracle.task_space_cubic(c_oracle.pose44(x_t[b]), xd_t[b], c_oracle.pose44(x_i[b]), xd_i[b], t_start + k * dt, t0, dur)
+                xs.append(c_oracle.pose12(X)); xds.append(V)
+            xs, xds = np.array(xs), np.array(xds)
+        else:
+            xs, xds = x_t, xd_t
+        r = oracle.cycle(1, q, qd, xs, xds, f)
+        q = q + dt * r["out"]
+        qd = r["out"].copy()
+        fail += (r["status"] != 1)
+        its += r["iters"]
+    return q, qd, fail, its
+
+
+@pytest.mark.parametrize("cubic", [False, True])
+def test_rollout_matches_tick_by_tick_oracle(gpu_ctx, oracle, cubic):
+    model, ctx = gpu_ctx
+    B, T, dt = 160, 12, 1e-3
+    q, qd, q_t, xd_t = workload(oracle.model, B, 91)
+    f = oracle.frame_id(LINK)
+    x_t = oracle.update_state(q_t, qd, f)["pose"]
+    x_i = oracle.update_state(q, qd, f)["pose"]
+    xd_i = np.einsum("bij,bj->bi", oracle.update_state(q, qd, f)["J"], qd)
+    kw = dict(x_init=x_i, xdot_init=xd_i, t_start=0.05, t0=0.0, duration=0.5) if cubic else {}
+    okw = dict(x_i=x_i, xd_i=xd_i, t_start=0.05, t0=0.0, dur=0.5) if cubic else {}
+    ref_q, ref_qd, ref_fail, ref_its = oracle_rollout(oracle, q, qd, x_t, xd_t if not cubic else np.zeros_like(xd_t), T, dt, **okw)
+    r = ctx.rollout_qpik(q, qd, x_t, xd_t if not cubic else np.zeros_like(xd_t), LINK, T, dt, **kw)
+    same = (r["iters_total"] == ref_its) & (r["fail_ticks"] == ref_fail)
+    assert same.mean() > 0.9, same.mean()                      # every tick of the robot took the oracle's iteration count
+    assert np.abs(r["q"] - ref_q)[same].max() < 1e-6           # 12 ticks of 1e-4-accurate commands times dt = 1e-3
+    assert np.abs(r["qdot"] - ref_qd)[same].max() < 1e-3
+    assert np.abs(r["q"] - q).max() > 1e-4                      # the state really moved
+    assert (r["fail_ticks"] <= T).all() and (r["iters_total"] >= 25 * T).all() and (r["iters_total"] % 25 == 0).all()
+
+
+def test_rollout_equals_repeated_cycles_on_the_device(gpu_ctx, oracle):
+    """device tensors, in place: one rollout call == T fused cycles + integrate on the caller's side (same iteration counts, states equal to rounding)"""
+    import torch
+    model, ctx = gpu_ctx
+    B, T, dt = 5000, 5, 1e-3
+    q, qd, q_t, xd_t = workload(oracle.model, B, 92)
+    x_t = oracle.update_state(q_t, qd, oracle.frame_id(LINK))["pose"]
+    dev = torch.device("cuda", 0)
+    tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xd_t))
+    a_q, a_qd = tq.clone(), tqd.clone()
+    its = torch.zeros(B, dtype=torch.int32, device=dev)
+    for k in range(T):
+        r = ctx.cycle_qpik_step(a_q, a_qd, txt, txd, LINK)
+        a_q = a_q + dt * r["out"]
+        a_qd = r["out"].clone()
+        its += r["iters"]
+    b = ctx.rollout_qpik(tq, tqd, txt, txd, LINK, T, dt)
+    torch.cuda.synchronize()
+    assert b["q"].data_ptr() == tq.data_ptr()                 # in place
+    assert torch.equal(b["iters_total"], its)
+    # the integrate kernel fuses q + dt * qdot into one FMA (torch rounds twice): equal up to that rounding
+    assert (b["q"] - a_q).abs().max().item() < 1e-12 and (b["qdot"] - a_qd).abs().max().item() < 1e-9
+
+
+def test_rollout_rejects_bad_arguments(gpu_ctx, oracle):
+    model, ctx = gpu_ctx
+    q, qd, q_t, xd_t = workload(oracle.model, 8, 93)
+    x_t = oracle.update_state(q_t, qd, oracle.frame_id(LINK))["pose"]
+    with pytest.raises(RuntimeError):
+        ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, 0, 1e-3)
+    with pytest.raises(RuntimeError):
+        ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, 3, 0.0)
