@@ -220,3 +220,28 @@ def test_caster_moma_kernel_bodies_cycle(pcv, mode):
     # regulariser) is worse conditioned than on the other bases, a few loosely converged iterates differ by 1e-4 relative
     assert (err < 1e-5 * scale).mean() > 0.95 and err.max() < 1e-3 * scale
     assert (ref["status"] == 1).mean() > 0.8
+
+
+# ---- committed golden vectors (tools/make_golden_mobile.py): regression pin of the oracle and of the kernel bodies
+def test_oracle_and_kernel_bodies_reproduce_mobile_golden_vectors(pcv):
+    from pathlib import Path
+    from oracle.c_oracle import mobile_base
+    from tests import emu
+    G = np.load(Path(__file__).resolve().parent / "golden" / "mobile_golden.npz")
+    for name, kin in KINS.items():
+        g = lambda k: G[f"{name}_{k}"]
+        for impl in (mobile_base, emu.mobile_base):
+            J, vel = impl(kin, True, g("wheel_pos"), g("wheel_vel"))
+            Ji, wheel = impl(kin, False, g("wheel_pos"), g("base_vel_des"))
+            _, wsat = impl(kin, False, g("wheel_pos"), g("base_vel_des"), saturate=True)
+            for got, key in ((J, "J_fk"), (vel, "base_vel"), (Ji, "J_ik"), (wheel, "wheel_cmd"), (wsat, "wheel_cmd_saturated")):
+                assert np.abs(got - g(key)).max() < 1e-11 * max(1.0, np.abs(g(key)).max()), (name, key)
+    d, o, e = pcv
+    f = o.frame_id("fr3_link8")
+    ms = o.moma_update_state(G["pcv_q"], G["pcv_qd"], f)
+    r = e.moma_state(G["pcv_q"], G["pcv_qd"], e.frame_id("fr3_link8"))
+    for src in (ms, r):
+        assert np.abs(src["M"] - G["pcv_M"]).max() < 1e-9 * np.abs(G["pcv_M"]).max()
+        assert np.abs(src["J"] - G["pcv_J"]).max() < 1e-12 and np.abs(src["mani"] - G["pcv_mani"]).max() < 1e-11
+    c = o.moma_cycle(1, G["pcv_q"], G["pcv_qd"], G["pcv_x_target"], G["pcv_xdot_target"], f)
+    assert (c["iters"] == G["pcv_qpik_step_iters"]).all() and np.abs(c["out"] - G["pcv_qpik_step_out"]).max() < 1e-9
