@@ -111,6 +111,30 @@ int main(int argc, char** argv) {
         if (rep > 0 && ms < b0) b0 = ms;
       }
       printf("full load, 25 iterations, no checks (setup: load + Ruiz + factor): %.3f ms\n", b0);
+      for (int sc : {0, 5}) {   // Ruiz passes: cost of the equilibration itself
+        QpOptions os = on; os.scaling = sc;
+        float bs = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+          CK(cudaEventRecord(a));
+          k_admm<Cfg, false, LAB_MINB><<<blocks, kAdmmWarps * 32, smem>>>(io, os);
+          CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+          float ms; CK(cudaEventElapsedTime(&ms, a, b));
+          if (rep > 0 && ms < bs) bs = ms;
+        }
+        printf("  same with %d Ruiz passes: %.3f ms\n", sc, bs);
+      }
+      {
+        QpOptions os = on; os.max_iter = 1;
+        float bs = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+          CK(cudaEventRecord(a));
+          k_admm<Cfg, false, LAB_MINB><<<blocks, kAdmmWarps * 32, smem>>>(io, os);
+          CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+          float ms; CK(cudaEventElapsedTime(&ms, a, b));
+          if (rep > 0 && ms < bs) bs = ms;
+        }
+        printf("  10 Ruiz passes, 1 iteration + final check: %.3f ms\n", bs);
+      }
     }
     // all warps loaded, nobody converges, 400 iterations
     ol.max_iter = 400;
