@@ -71,6 +71,28 @@ def test_compute_entry_points_fail_loudly_without_a_gpu(capi):
         drc.fp64_peak_tflops(0)
 
 
+def test_mobile_base_fails_loudly_without_a_gpu_and_type_records(capi):
+    """Mobile::KinematicParam / JointIndex / ActuatorIndex mirrors are plain host records; the base itself needs the GPU."""
+    import dyros_robot_controller_b200 as drc
+    from dyros_robot_controller_b200.drc import ActuatorIndex, DriveType, JointIndex, KinematicParam
+    kp = KinematicParam(type=DriveType.Mecanum, wheel_radius=0.12, roller_angles=[-0.78, 0.78, 0.78, -0.78],
+                        base2wheel_positions=[np.array([0.2, 0.2]), np.array([0.2, -0.2]), np.array([-0.2, 0.2]), np.array([-0.2, -0.2])],
+                        base2wheel_angles=[0, 0, 0, 0])
+    d = kp.as_dict()
+    assert d["type"] == 1 and d["max_lin_speed"] == 2.0 and len(d["base2wheel_positions"]) == 4   # defaults of drc/type_define.py:15-18
+    with pytest.raises(AssertionError):
+        KinematicParam(type=DriveType.Differential, wheel_radius=0.1)          # base_width is required (type_define.py:35-36)
+    with pytest.raises(AssertionError):
+        KinematicParam(type=DriveType.Caster, wheel_radius=0.05, base2wheel_positions=[(0.2, 0.1), (-0.2, -0.1)])   # wheel_offset
+    assert JointIndex(0, 7, 3).as_dict() == dict(virtual_start=0, mani_start=7, mobi_start=3)
+    assert ActuatorIndex(4, 0).as_dict() == dict(mani_start=4, mobi_start=0)
+    if drc.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.DrcError) as e:
+        drc.MobileBase(d)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+
+
 def test_product_package_does_not_import_the_oracle():
     """The oracle is test infrastructure: nothing under the product package may import or call it."""
     pkg = ROOT / "dyros_robot_controller_b200"
