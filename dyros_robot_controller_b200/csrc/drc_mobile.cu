@@ -16,14 +16,24 @@ struct drc_mobile {
 
 namespace {
 
+// One thread per base.  WMAX / EXACT: see drc_mobile.h -- bases with 2, 4 or 8 wheels get predicate-free bodies.
+template <int WMAX, bool EXACT>
 __global__ void __launch_bounds__(128) k_mobile_fk(const __grid_constant__ MobileDev m, const MobileIO io) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) mobile_fk_job(m, io, b);
+  if (b < io.B) mobile_fk_job_t<WMAX, EXACT>(m, io, b);
 }
+template <int WMAX, bool EXACT>
 __global__ void __launch_bounds__(128) k_mobile_ik(const __grid_constant__ MobileDev m, const MobileIO io) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < io.B) mobile_ik_job(m, io, b);
+  if (b < io.B) mobile_ik_job_t<WMAX, EXACT>(m, io, b);
 }
+#define DRC_DISPATCH_WHEELS(w, KERNEL, ...)                                             \
+  switch (w) {                                                                          \
+    case 2: KERNEL<2, true> __VA_ARGS__; break;                                         \
+    case 4: KERNEL<4, true> __VA_ARGS__; break;                                         \
+    case 8: KERNEL<8, true> __VA_ARGS__; break;                                         \
+    default: KERNEL<kMaxWheel, false> __VA_ARGS__; break;                               \
+  }
 
 int check_mobile(const drc_mobile* h, int B) {
   if (!h) return fail(DRC_E_INVALID, "null mobile base handle");
@@ -40,7 +50,7 @@ int launch_fk(drc_mobile* h, int B, const double* wheel_pos, const double* wheel
   std::memset(&io, 0, sizeof io);
   io.B = B; io.wheel_pos = wheel_pos; io.swp = lay(layout, w, B); io.wheel_vel = wheel_vel; io.swv = io.swp;
   io.J = J; io.sj = lay(layout, 3 * w, B); io.out = base_vel; io.so = lay(layout, 3, B);
-  k_mobile_fk<<<(B + 127) / 128, 128, 0, s>>>(h->dev, io);
+  DRC_DISPATCH_WHEELS(w, k_mobile_fk, <<<(B + 127) / 128, 128, 0, s>>>(h->dev, io))
   CU(cudaGetLastError());
   h->launches += 1;
   return DRC_OK;
@@ -54,7 +64,7 @@ int launch_ik(drc_mobile* h, int B, const double* wheel_pos, const double* base_
   std::memset(&io, 0, sizeof io);
   io.B = B; io.wheel_pos = wheel_pos; io.swp = lay(layout, w, B); io.base_vel = base_vel_des; io.sbv = lay(layout, 3, B);
   io.J = J; io.sj = lay(layout, 3 * w, B); io.out = wheel_vel; io.so = lay(layout, w, B); io.saturate = saturate;
-  k_mobile_ik<<<(B + 127) / 128, 128, 0, s>>>(h->dev, io);
+  DRC_DISPATCH_WHEELS(w, k_mobile_ik, <<<(B + 127) / 128, 128, 0, s>>>(h->dev, io))
   CU(cudaGetLastError());
   h->launches += 1;
   return DRC_OK;

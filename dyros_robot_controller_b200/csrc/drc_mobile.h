@@ -67,13 +67,14 @@ template <int W>
 DRC_HD void caster_ik_jacobian(double r, double b, const double* px, const double* py, const double* wheel_pos, int w,
                                double* Ji) {
   const int ns = w / 2;
+  const double ib = 1.0 / b, ir = 1.0 / r;   // two divisions per base instead of six per caster (fp64 division is ~30 instructions)
 #pragma unroll
   for (int i = 0; i < W / 2; ++i) {
     if (i < ns) {
       double s, c;
       sincos(wheel_pos[2 * i], &s, &c);
-      Ji[(2 * i) * 3 + 0] = -s / b; Ji[(2 * i) * 3 + 1] = c / b; Ji[(2 * i) * 3 + 2] = (px[i] * c + py[i] * s) / b - 1.0;
-      Ji[(2 * i + 1) * 3 + 0] = c / r; Ji[(2 * i + 1) * 3 + 1] = s / r; Ji[(2 * i + 1) * 3 + 2] = (px[i] * s - py[i] * c) / r;
+      Ji[(2 * i) * 3 + 0] = -s * ib; Ji[(2 * i) * 3 + 1] = c * ib; Ji[(2 * i) * 3 + 2] = (px[i] * c + py[i] * s) * ib - 1.0;
+      Ji[(2 * i + 1) * 3 + 0] = c * ir; Ji[(2 * i + 1) * 3 + 1] = s * ir; Ji[(2 * i + 1) * 3 + 2] = (px[i] * s - py[i] * c) * ir;
     }
   }
 }
@@ -89,79 +90,101 @@ struct MobileIO {
 };
 
 // Mobile::RobotData::updateState (mobile/robot_data.cpp:103-114): J_mobile = computeFKJacobian(wheel_pos),
-// base_vel = J_mobile * wheel_vel
-DRC_HD void mobile_fk_job(const MobileDev& m, const MobileIO& io, int b) {
-  const int w = m.wheel_num;
-  double J[3 * kMaxWheel];
+// base_vel = J_mobile * wheel_vel.  WMAX = compile-time bound of the wheel count; EXACT: the base has exactly WMAX wheels
+// (the loops then carry no predicates and differential / mecanum bases read their constant Jacobian straight from the
+// parameter block -- the kernels are HBM bound only when the per-base instruction count stays in the tens).
+template <int WMAX, bool EXACT>
+DRC_HD void mobile_fk_job_t(const MobileDev& m, const MobileIO& io, int b) {
+  const int w = EXACT ? WMAX : m.wheel_num;
+  double v0 = 0, v1 = 0, v2 = 0;
   if (m.drive_type == kCaster) {
-    double wp[kMaxWheel];
+    double J[3 * WMAX], wp[WMAX];
 #pragma unroll
-    for (int k = 0; k < kMaxWheel; ++k) wp[k] = k < w ? io.wheel_pos[b * io.swp.sb + k * io.swp.sk] : 0.0;
-    caster_fk_jacobian<kMaxWheel>(m.wheel_radius, m.wheel_offset, m.b2w_x, m.b2w_y, wp, w, J, kMaxWheel);
-  } else {
+    for (int k = 0; k < WMAX; ++k) wp[k] = k < w ? io.wheel_pos[b * io.swp.sb + k * io.swp.sk] : 0.0;
+    caster_fk_jacobian<WMAX>(m.wheel_radius, m.wheel_offset, m.b2w_x, m.b2w_y, wp, w, J, WMAX);
+    if (io.J) {
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < w; ++k) io.J[b * io.sj.sb + (r * w + k) * io.sj.sk] = J[r * WMAX + k];
+    }
+    if (io.wheel_vel && io.out) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int k = 0; k < kMaxWheel; ++k) J[r * kMaxWheel + k] = m.J_fk[r][k];
-  }
-  if (io.J) {
-    for (int r = 0; r < 3; ++r)
-      for (int k = 0; k < w; ++k) io.J[b * io.sj.sb + (r * w + k) * io.sj.sk] = J[r * kMaxWheel + k];
-  }
-  if (io.wheel_vel && io.out) {
-    double v0 = 0, v1 = 0, v2 = 0;
-#pragma unroll
-    for (int k = 0; k < kMaxWheel; ++k) {
-      if (k < w) {
-        const double wv = io.wheel_vel[b * io.swv.sb + k * io.swv.sk];
-        v0 += J[0 * kMaxWheel + k] * wv; v1 += J[1 * kMaxWheel + k] * wv; v2 += J[2 * kMaxWheel + k] * wv;
+      for (int k = 0; k < WMAX; ++k) {
+        if (k < w) {
+          const double wv = io.wheel_vel[b * io.swv.sb + k * io.swv.sk];
+          v0 += J[0 * WMAX + k] * wv; v1 += J[1 * WMAX + k] * wv; v2 += J[2 * WMAX + k] * wv;
+        }
       }
     }
+  } else {
+    if (io.J) {
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < w; ++k) io.J[b * io.sj.sb + (r * w + k) * io.sj.sk] = m.J_fk[r][k];
+    }
+    if (io.wheel_vel && io.out) {
+#pragma unroll
+      for (int k = 0; k < WMAX; ++k) {
+        if (k < w) {
+          const double wv = io.wheel_vel[b * io.swv.sb + k * io.swv.sk];
+          v0 += m.J_fk[0][k] * wv; v1 += m.J_fk[1][k] * wv; v2 += m.J_fk[2][k] * wv;
+        }
+      }
+    }
+  }
+  if (io.wheel_vel && io.out) {
     io.out[b * io.so.sb + 0 * io.so.sk] = v0;
     io.out[b * io.so.sb + 1 * io.so.sk] = v1;
     io.out[b * io.so.sb + 2 * io.so.sk] = v2;
   }
 }
+DRC_HD void mobile_fk_job(const MobileDev& m, const MobileIO& io, int b) { mobile_fk_job_t<kMaxWheel, false>(m, io, b); }
 
 // VelocityCommand's saturation (mobile/robot_controller.cpp:14-41): the planar speed is clipped to max_lin_speed along its
 // own direction (directions of speeds below 1e-4 are dropped), the yaw rate to +-max_ang_speed.
 DRC_HD void saturate_base_velocity(const MobileDev& m, double* v) {
   const double sp = sqrt(v[0] * v[0] + v[1] * v[1]);
-  double dx = 0, dy = 0;
-  if (!(fabs(sp) < 1e-4)) { dx = v[0] / sp; dy = v[1] / sp; }
   const double sc = fmin(fmax(sp, -m.max_lin_speed), m.max_lin_speed);
-  v[0] = dx * sc; v[1] = dy * sc;
+  const double k = fabs(sp) < 1e-4 ? 0.0 : sc / sp;   // direction (v / speed) times the clipped speed, one division
+  v[0] *= k; v[1] *= k;
   v[2] = fmin(fmax(v[2], -m.max_ang_speed), m.max_ang_speed);
 }
 
 // Mobile::RobotController::VelocityCommand / computeWheelVel / computeIKJacobian (mobile/robot_controller.cpp:14-124)
-DRC_HD void mobile_ik_job(const MobileDev& m, const MobileIO& io, int b) {
-  const int w = m.wheel_num;
-  double Ji[kMaxWheel * 3];
-  if (m.drive_type == kCaster) {
-    double wp[kMaxWheel];
-#pragma unroll
-    for (int k = 0; k < kMaxWheel; ++k) wp[k] = k < w ? io.wheel_pos[b * io.swp.sb + k * io.swp.sk] : 0.0;
-    caster_ik_jacobian<kMaxWheel>(m.wheel_radius, m.wheel_offset, m.b2w_x, m.b2w_y, wp, w, Ji);
-  } else {
-#pragma unroll
-    for (int k = 0; k < kMaxWheel; ++k)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) Ji[k * 3 + c] = m.J_ik[k][c];
-  }
-  if (io.J) {
-    for (int k = 0; k < w; ++k)
-      for (int c = 0; c < 3; ++c) io.J[b * io.sj.sb + (k * 3 + c) * io.sj.sk] = Ji[k * 3 + c];
-  }
-  if (io.base_vel && io.out) {
-    double v[3];
+template <int WMAX, bool EXACT>
+DRC_HD void mobile_ik_job_t(const MobileDev& m, const MobileIO& io, int b) {
+  const int w = EXACT ? WMAX : m.wheel_num;
+  double v[3] = {0, 0, 0};
+  const bool cmd = io.base_vel && io.out;
+  if (cmd) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[c] = io.base_vel[b * io.sbv.sb + c * io.sbv.sk];
     if (io.saturate) saturate_base_velocity(m, v);
+  }
+  if (m.drive_type == kCaster) {
+    double Ji[WMAX * 3], wp[WMAX];
 #pragma unroll
-    for (int k = 0; k < kMaxWheel; ++k)
-      if (k < w) io.out[b * io.so.sb + k * io.so.sk] = Ji[k * 3 + 0] * v[0] + Ji[k * 3 + 1] * v[1] + Ji[k * 3 + 2] * v[2];
+    for (int k = 0; k < WMAX; ++k) wp[k] = k < w ? io.wheel_pos[b * io.swp.sb + k * io.swp.sk] : 0.0;
+    caster_ik_jacobian<WMAX>(m.wheel_radius, m.wheel_offset, m.b2w_x, m.b2w_y, wp, w, Ji);
+    if (io.J) {
+      for (int k = 0; k < w; ++k)
+        for (int c = 0; c < 3; ++c) io.J[b * io.sj.sb + (k * 3 + c) * io.sj.sk] = Ji[k * 3 + c];
+    }
+    if (cmd) {
+#pragma unroll
+      for (int k = 0; k < WMAX; ++k)
+        if (k < w) io.out[b * io.so.sb + k * io.so.sk] = Ji[k * 3 + 0] * v[0] + Ji[k * 3 + 1] * v[1] + Ji[k * 3 + 2] * v[2];
+    }
+  } else {
+    if (io.J) {
+      for (int k = 0; k < w; ++k)
+        for (int c = 0; c < 3; ++c) io.J[b * io.sj.sb + (k * 3 + c) * io.sj.sk] = m.J_ik[k][c];
+    }
+    if (cmd) {
+#pragma unroll
+      for (int k = 0; k < WMAX; ++k)
+        if (k < w) io.out[b * io.so.sb + k * io.so.sk] = m.J_ik[k][0] * v[0] + m.J_ik[k][1] * v[1] + m.J_ik[k][2] * v[2];
+    }
   }
 }
+DRC_HD void mobile_ik_job(const MobileDev& m, const MobileIO& io, int b) { mobile_ik_job_t<kMaxWheel, false>(m, io, b); }
 
 }  // namespace drc
