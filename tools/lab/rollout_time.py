@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""LAB: time per tick of drc_batch_rollout_qpik at the benchmark batch (device tensors, CUDA events)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
+import dyros_robot_controller_b200 as drc
+from bench import LINK, make_workload
+
+B, T = 65536, 20
+model = drc.Model(drc.FR3_URDF, drc.FR3_SRDF)
+ctx = drc.Context(model, B)
+q, qd, q_t, xd = make_workload(model, B, 0)
+ctx.update_state(q_t, qd)
+x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+dev = torch.device("cuda", 0)
+for rep in range(3):
+    tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xd))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = ctx.rollout_qpik(tq, tqd, txt, txd, LINK, T, 1e-3)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"rollout B={B} T={T}: {ms:.2f} ms total, {ms / T:.3f} ms / tick, {B * T / ms / 1e3:.2f} M cycles/s, "
+          f"failed ticks {int(r['fail_ticks'].sum())}, mean iterations / tick {float(r['iters_total'].double().mean()) / T:.1f}")
