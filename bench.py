@@ -428,8 +428,9 @@ def run_ours(args):
     roofline = {"bound": "fp64", "kernel": "k_admm" + ("<QpCfg<7,2,2,0>>" if args.workload == "fr3_qpik" else ""), "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved is not None else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_admm launch at this batch from the ncu --set full capture
-                # (profiles/r01_ncu_summary_v3_scheduled.md: 42.66 MB + 0.28 MB); algorithmic: 632 B record + 64 B result per robot
-                "traffic": 42.94e6 if (args.workload == "fr3_qpik" and B == 65536) else None,
+                # of the final build (profiles/r01_ncu_summary_v5_dynamics_split.md: 41.83 MB + 0.39 MB); algorithmic: 632 B record +
+                # 64 B result per robot
+                "traffic": 42.22e6 if (args.workload == "fr3_qpik" and B == 65536) else None,
                 "traffic_algorithmic": (632.0 + 64.0) * B if args.workload == "fr3_qpik" else None,
                 "peak_source": peak_src,
                 "kernel_ms": admm_ms, "kernel_share_of_step": admm_ms / ms_per_step,
