@@ -64,6 +64,7 @@ struct drc_ctx {
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
   cudaEvent_t ev_sched, ev_prio;
+  cudaStream_t last_stream; bool last_stream_set; cudaEvent_t ev_last;  // cross-stream ordering of consecutive calls (pick)
   cudaEvent_t ev_in, ev_out;   // joins of a caller stream with the context's prioritised streams (fused QPIK cycles)
   cudaStream_t dyn_stream; cudaEvent_t ev_store, ev_dyn;  // fused QPIK cycles: dynamics-only kernel behind the ADMM launch
   cudaStream_t copy;                     // host entry points: inputs that only stage 2 reads are uploaded here, behind stage 1
@@ -114,7 +115,7 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
 
 template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
-  static const int threads = [] { const char* e = getenv("DRC_JOB_THREADS"); const int t = e ? atoi(e) : 64; return t >= 32 && t <= 128 ? t : 64; }();
+  constexpr int threads = 64;
   const int blocks = (io.B + threads - 1) / threads;
   k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
   c->launches++;
@@ -131,7 +132,7 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   if (!io.dist) io.dist = sc.col_dist;
   if (!io.pair_out) io.pair_out = sc.col_pair;
   if (!io.witness) io.witness = sc.col_wit;
-  static const int threads = [] { const char* e = getenv("DRC_COL_THREADS"); const int t = e ? atoi(e) : 128; return t >= 32 && t <= 128 ? t : 128; }();
+  constexpr int threads = 128;
   const int blocks = (io.B + threads - 1) / threads;
   // (register budgets of 168 / 128 registers were measured too: 3 blocks/SM is slower, 4 blocks/SM saves 0.1 ms here and loses it
   // again in the ADMM stage -- profiles/README.md)
@@ -183,19 +184,12 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   const QpOptions o = qp_options(c->prm, unit_mask);
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
   io.iters_hint = c->prev_iters;
-  // blocks/SM the kernel is compiled for (register cap 65536 / (128 * MINB)); tunable for experiments
-  static const int minb = [] { const char* e = getenv("DRC_ADMM_MINB"); return e ? atoi(e) : 3; }();
+  // one instantiation per QP shape (register cap 65536 / (128 * 3) = 168).  The dynamic shared-memory opt-in is a per-device
+  // function attribute: set it for the context's device on every launch (cheap) so that contexts on several GPUs of one
+  // process all get it.
   constexpr size_t smem = sizeof(GroupShared<Cfg>) * kAdmmWarps * Cfg::NG;
-  static const cudaError_t attr = [] {
-    cudaError_t e1 = cudaFuncSetAttribute(k_admm<Cfg, ID, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(k_admm<Cfg, ID, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e3 = cudaFuncSetAttribute(k_admm<Cfg, ID, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-  }();
-  CU(attr);
-  if (minb <= 2) k_admm<Cfg, ID, 2><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
-  else if (minb == 3) k_admm<Cfg, ID, 3><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
-  else k_admm<Cfg, ID, 4><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
+  CU(cudaFuncSetAttribute(k_admm<Cfg, ID, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_admm<Cfg, ID, 3><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
   c->launches++;
   CU(cudaGetLastError());
   return DRC_OK;
@@ -210,7 +204,19 @@ static int check_frame(const drc_ctx* c, int frame) {
   if (frame < 0 || frame >= (int)c->model->hm.frames.size()) return fail(DRC_E_INVALID, "unknown frame id");
   return DRC_OK;
 }
-static cudaStream_t pick(drc_ctx* c, void* s) { return s ? (cudaStream_t)s : c->stream; }
+// Stream of this call.  The state cache and the scratch belong to the context, not to a stream: when consecutive calls use
+// different streams (torch inputs run on the caller's stream, the drc_host_* getters on the context's non-blocking stream),
+// the new stream first waits for everything the previous call enqueued -- an event recorded at the tail of the previous
+// stream (calls are host-serialised per context, so that tail covers the whole previous call).
+static cudaStream_t pick(drc_ctx* c, void* s) {
+  cudaStream_t st = s ? (cudaStream_t)s : c->stream;
+  if (c->last_stream_set && c->last_stream != st) {
+    if (cudaEventRecord(c->ev_last, c->last_stream) == cudaSuccess) cudaStreamWaitEvent(st, c->ev_last, 0);
+    else cudaGetLastError();  // the previous caller stream no longer exists: nothing of it can still be running
+  }
+  c->last_stream = st; c->last_stream_set = true;
+  return st;
+}
 
 
 // ------------------------------------------------------------------------------------------------ host entry points

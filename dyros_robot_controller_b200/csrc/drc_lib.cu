@@ -224,17 +224,8 @@ int drc_model_info(const drc_model_t* m, int* s) {
 const char* drc_model_verbose(const drc_model_t* m) { return m ? m->verbose.c_str() : ""; }
 
 // ------------------------------------------------------------------------------------------------ context
-int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** out) {
-  if (!m || !out || max_batch <= 0) return fail(DRC_E_INVALID, "bad argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    cudaGetLastError();
-    return fail(DRC_E_CUDA, "no CUDA device: drc_b200 has no CPU fallback");
-  }
-  if (device < 0 || device >= ndev) return fail(DRC_E_INVALID, "device index out of range");
-  CU(cudaSetDevice(device));
-  std::unique_ptr<drc_ctx> c(new drc_ctx);
-  std::memset(c.get(), 0, sizeof(drc_ctx));
+// allocations of drc_ctx_create; on any failure the caller releases whatever was created so far (drc_ctx_destroy skips nulls)
+static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max_batch) {
   c->model = m; c->device = device; c->cap = max_batch;
   c->prm = DrcParams();
   for (int i = 0; i < kMaxV; ++i) { c->prm.Kp_joint[i] = 400; c->prm.Kv_joint[i] = 40; }
@@ -246,6 +237,7 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_main));
   CU(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_main));
   CU(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming));
@@ -313,13 +305,34 @@ int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** 
   c->stage_ints = 2 * B;
   CU(cudaMalloc((void**)&c->stage_i, c->stage_ints * sizeof(int)));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
-  *out = c.release();
+  return DRC_OK;
+}
+int drc_ctx_create(const drc_model_t* m, int device, int max_batch, drc_ctx_t** out) {
+  if (!m || !out || max_batch <= 0) return fail(DRC_E_INVALID, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(DRC_E_CUDA, "no CUDA device: drc_b200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(DRC_E_INVALID, "device index out of range");
+  CU(cudaSetDevice(device));
+  drc_ctx* c = new drc_ctx;
+  std::memset(c, 0, sizeof(drc_ctx));
+  const int rc = ctx_create_impl(c, m, device, max_batch);
+  if (rc != DRC_OK) {  // e.g. out of memory for a large batch: free the partial context so that the caller can retry smaller
+    const std::string msg = g_err;
+    cudaGetLastError();
+    drc_ctx_destroy(c);
+    g_err = msg;
+    return rc;
+  }
+  *out = c;
   return DRC_OK;
 }
 void drc_ctx_destroy(drc_ctx_t* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   double* ds[] = {c->c_q, c->c_qd, c->c_oMi, c->c_M, c->c_Minv, c->c_g, c->c_nle, c->qp, c->col_dist, c->col_wit, c->stage,
                   c->c_Mact, c->c_Minvact, c->c_gact, c->c_nleact};
   for (double* p : ds) if (p) cudaFree(p);
@@ -348,6 +361,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->dyn_stream) { cudaStreamSynchronize(c->dyn_stream); cudaStreamDestroy(c->dyn_stream); }
     if (c->ev_store) cudaEventDestroy(c->ev_store);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->ev_dyn) cudaEventDestroy(c->ev_dyn);
     if (c->ev_late) cudaEventDestroy(c->ev_late);
@@ -358,7 +372,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->ev_col) cudaEventDestroy(c->ev_col);
   if (c->ev_epa) cudaEventDestroy(c->ev_epa);
   if (c->side) cudaStreamDestroy(c->side);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 int drc_ctx_get_params(const drc_ctx_t* c, drc_params_t* p) {

@@ -92,6 +92,7 @@ struct BundleHot {
 
 template <class Cfg>
 struct Lane {
+  static constexpr bool kHasEq = Cfg::NE > 0;  // only equality bundles have row_eq / sb_free set
   int gl, grp;            // lane within the group (-1 = idle), group within the warp
   bool is_core;
   bool done;               // register copy of the group's done flag (refreshed after every termination check)
@@ -101,7 +102,8 @@ struct Lane {
   double sig, al;         // sigma / alpha on core lanes, 0 on row lanes
   double rho_r, rho_b;    // rho of this lane's bundle rows / singleton bound rows
   double pzc;             // scratch
-  double et;              // scratch (E_temp of a dense row during scaling)
+  double et;              // set-up scratch: D_temp of the own column (core lanes) / E_temp of the own row (row lanes)
+  double pr[Cfg::NC];     // set-up scratch: row j of P (core lanes) / row r of A (row lanes) during the equilibration
   BundleHot b[Cfg::NB];
   double w[Cfg::GL];      // operator row of U S^-1 U'
 };
@@ -116,11 +118,12 @@ struct ColdLane {
   unsigned char active[Cfg::NB], has_sing[Cfg::NB], has_sb[Cfg::NB];
 };
 
-constexpr int kNumRed = 22;  // group-wide reductions of one termination check
+constexpr int kNumRed = 16;  // group-wide reductions of one termination check
 template <class Cfg>
 struct GroupShared {
   double u[Cfg::GL];                                 // exchange vector of the hot loop
-  double v[Cfg::GL];                                 // second exchange vector (checks, setup)
+  double v[Cfg::GL];                                 // checks: dx_c | projected dy_r;  setup: D_temp / omega
+  double xy[Cfg::GL];                                // checks: x_c | y_r
   double P[Cfg::NC * Cfg::NC];                       // scaled P_cc (symmetric, dense)
   double A[(Cfg::NR > 0 ? Cfg::NR : 1) * Cfg::NC];   // scaled dense-row coefficients
   // S (Schur complement -> inverse) and T (S^-1 a_r) live only inside factor(); red (per-lane partial
@@ -185,9 +188,10 @@ struct WarpEmu {
 
 // projections of the row kinds
 template <class LaneT>
-DRC_HD double proj_row(const LaneT& L, double v, double l) { return L.row_eq ? l : dmax(v, l); }
+DRC_HD double proj_row(const LaneT& L, double v, double l) { return (LaneT::kHasEq && L.row_eq) ? l : dmax(v, l); }
+// max(v, 0) = (v + |v|) / 2 exactly: two FP64 operations instead of a compare + select chain
 template <class LaneT>
-DRC_HD double proj_sb(const LaneT& L, double v) { return L.sb_free ? v : dmax(v, 0.0); }
+DRC_HD double proj_sb(const LaneT& L, double v) { return (LaneT::kHasEq && L.sb_free) ? v : 0.5 * (v + fabs(v)); }
 
 // ------------------------------------------------------------------------------------------------
 // The solver.  `qp` points at the per-robot records (Cfg::STRIDE doubles each); robots[g] is the
@@ -232,7 +236,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     if (L.is_core) {
       const int j = L.gl;
 #pragma unroll
-      for (int i = 0; i < NC; ++i) S.P[j * NC + i] = rec[Cfg::OFF_P + symidx<NC>(i, j)];
+      for (int i = 0; i < NC; ++i) L.pr[i] = rec[Cfg::OFF_P + symidx<NC>(i, j)];
       L.q = rec[Cfg::OFF_Q + j];
       if (Cfg::BOUNDS) { L.betac = 1.0; L.lc = rec[Cfg::OFF_LO + j]; L.uc = rec[Cfg::OFF_HI + j]; }
       const bool act = ((o.unit_mask >> j) & 1u) != 0u;
@@ -252,7 +256,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       const int r = L.gl - NC;
       const double* row = rec + Cfg::OFF_ROW + r * (NC + 1);
 #pragma unroll
-      for (int i = 0; i < NC; ++i) S.A[r * NC + i] = row[i];
+      for (int i = 0; i < NC; ++i) { L.pr[i] = row[i]; S.A[r * NC + i] = row[i]; }
       BundleHot& b = L.b[0];
       C.active[0] = 1;
       b.c = 1.0;
@@ -269,101 +273,111 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
   });
 
   // ---------------------------------------------------------------- Ruiz equilibration (OSQP scale_data)
+  // Two phases per pass.  During the passes every lane keeps ITS row of P (core lanes) / of A (row lanes) in registers
+  // (L.pr): P is symmetric, so lane j only ever needs row j; the row lanes publish their scaled row to shared memory for
+  // the column norms of the core lanes.  The KU unit bundles of a core lane start from the same magnitudes
+  // (|c| = e = beta = 1, cost = slack weight) and every scaling factor depends on magnitudes only, so they stay
+  // identical through all passes: bundle 0 is scaled as their representative and copied to the others afterwards.
+  // The cost normalisation of a pass (c_temp) is applied at the start of the next one (apply_cost), which saves a phase.
+  auto apply_cost = [&](LaneT& L, GS& S) {
+    // c_temp = 1 / limit(max(mean_j ||P_j||_inf, limit(||q||_inf))) from the per-lane values published by phase Y
+    double sum = 0, qm = 0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) sum += S.red[i];
+#pragma unroll
+    for (int i = 0; i < GL; ++i) qm = dmax(qm, S.red[GL + i]);
+    const double ct = 1.0 / limit_scaling(dmax(sum / (double)S.nx, limit_scaling(qm)));
+    if (L.is_core) {
+      L.q *= ct;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) L.pr[i] *= ct;
+    }
+    L.b[0].qd *= ct;
+    if (L.gl == 0) S.c *= ct;
+  };
   for (int it = 0; it < o.scaling; ++it) {
-    // (1) D_temp of the core columns: inf-norm over P, the bound row, unit rows and dense rows
-    w.each([&](LaneT& L, GS& S) {
-      if (S.done || !L.is_core) return;
-      const int j = L.gl;
-      double cn = fabs(L.betac);
-#pragma unroll
-      for (int i = 0; i < NC; ++i) cn = dmax(cn, fabs(S.P[j * NC + i]));
-#pragma unroll
-      for (int r = 0; r < NR; ++r) cn = dmax(cn, fabs(S.A[r * NC + j]));
-#pragma unroll
-      for (int k = 0; k < KU; ++k) cn = dmax(cn, fabs(L.b[k].c));
-      S.u[j] = inv_sqrt(limit_scaling(cn));
-    });
-    // (2) E_temp of every row, D_temp of the singleton columns; apply to everything lane-local
+    // (X) D_temp of the core columns, E_temp of every row, D_temp of the singleton columns; apply to everything lane-local
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
       Cold& C = S.cold[L.gl];
-      auto scale_bundle = [&](int k, double core_norm) -> double {
-        BundleHot& b = L.b[k];
-        if (!C.active[k]) return 1.0;
-        double dt = 1.0, eb = 1.0;
-        if (C.has_sing[k]) {
-          double cn = fabs(b.e);
-          if (C.has_sb[k]) { cn = dmax(cn, fabs(b.beta)); eb = inv_sqrt(limit_scaling(fabs(b.beta))); }
-          dt = inv_sqrt(limit_scaling(cn));
-        }
-        const double et = inv_sqrt(limit_scaling(dmax(core_norm, fabs(b.e))));
-        C.E[k] *= et;
-        if (C.has_sing[k]) {
-          b.e *= et * dt; C.Dd[k] *= dt; b.qd *= dt;
-          if (C.has_sb[k]) { b.beta *= eb * dt; C.Eb[k] *= eb; }
-        }
-        return et;
-      };
+      if (it > 0) apply_cost(L, S);
+      BundleHot& b = L.b[0];
+      double core_norm, dj = 1.0;
       if (L.is_core) {
-        const double dj = S.u[L.gl];
-        if (Cfg::BOUNDS) { const double eb = inv_sqrt(limit_scaling(fabs(L.betac))); L.betac *= eb * dj; C.Ecb *= eb; }
+        const int j = L.gl;
+        double cn = dmax(fabs(L.betac), fabs(b.c));
 #pragma unroll
-        for (int k = 0; k < KU; ++k) {
-          const double et = scale_bundle(k, fabs(L.b[k].c));
-          L.b[k].c *= et * dj;
-        }
-        L.q *= dj; C.D *= dj;
+        for (int i = 0; i < NC; ++i) cn = dmax(cn, fabs(L.pr[i]));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) cn = dmax(cn, fabs(S.A[r * NC + j]));
+        dj = inv_sqrt(limit_scaling(cn));
+        S.u[j] = dj;
+        core_norm = fabs(b.c);
       } else {
-        const int r = L.gl - NC;
         double rn = 0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) rn = dmax(rn, fabs(S.A[r * NC + i]));
-        L.et = scale_bundle(0, rn);  // E_temp of the dense row, applied to S.A in (3)
+        for (int i = 0; i < NC; ++i) rn = dmax(rn, fabs(L.pr[i]));
+        core_norm = rn;
+      }
+      double et = 1.0;
+      if (C.active[0]) {
+        double dt = 1.0, eb = 1.0;
+        if (C.has_sing[0]) {
+          double cn = fabs(b.e);
+          if (C.has_sb[0]) { cn = dmax(cn, fabs(b.beta)); eb = inv_sqrt(limit_scaling(fabs(b.beta))); }
+          dt = inv_sqrt(limit_scaling(cn));
+        }
+        et = inv_sqrt(limit_scaling(dmax(core_norm, fabs(b.e))));
+        C.E[0] *= et;
+        if (C.has_sing[0]) {
+          b.e *= et * dt; C.Dd[0] *= dt; b.qd *= dt;
+          if (C.has_sb[0]) { b.beta *= eb * dt; C.Eb[0] *= eb; }
+        }
+      }
+      if (L.is_core) {
+        if (Cfg::BOUNDS) { const double eb = inv_sqrt(limit_scaling(fabs(L.betac))); L.betac *= eb * dj; C.Ecb *= eb; }
+        b.c *= et * dj;
+        L.q *= dj; C.D *= dj;
+        L.et = dj;
+      } else {
+        L.et = et;
       }
     });
-    // (3) scale P and the dense rows; publish the inputs of the cost normalisation
+    // (Y) scale P and the dense rows; publish the inputs of the cost normalisation
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
       Cold& C = S.cold[L.gl];
       double cn = 0, qm = 0;
       if (L.is_core) {
-        const int j = L.gl;
-        const double dj = S.u[j];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { const double pv = S.P[j * NC + i] * dj * S.u[i]; S.P[j * NC + i] = pv; cn = dmax(cn, fabs(pv)); }
+        for (int i = 0; i < NC; ++i) { const double pv = L.pr[i] * L.et * S.u[i]; L.pr[i] = pv; cn = dmax(cn, fabs(pv)); }
         qm = fabs(L.q);
-#pragma unroll
-        for (int k = 0; k < KU; ++k) if (C.has_sing[k]) qm = dmax(qm, fabs(L.b[k].qd));
       } else {
         const int r = L.gl - NC;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) S.A[r * NC + i] *= L.et * S.u[i];
-        if (C.has_sing[0]) qm = fabs(L.b[0].qd);
+        for (int i = 0; i < NC; ++i) { const double av = L.pr[i] * (L.et * S.u[i]); L.pr[i] = av; S.A[r * NC + i] = av; }
       }
+      if (C.has_sing[0]) qm = dmax(qm, fabs(L.b[0].qd));
       S.red[L.gl] = cn; S.red[GL + L.gl] = qm;
     });
-    // (4) c_temp = 1 / limit(max(mean_j ||P_j||_inf, limit(||q||_inf)))
-    w.each([&](LaneT& L, GS& S) {
-      if (S.done) return;
-      double sum = 0, qm = 0;
-#pragma unroll
-      for (int i = 0; i < GL; ++i) { sum += S.red[i]; qm = dmax(qm, S.red[GL + i]); }
-      const double ct = 1.0 / limit_scaling(dmax(sum / (double)S.nx, limit_scaling(qm)));
-      if (L.is_core) {
-        const int j = L.gl;
-        L.q *= ct;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) S.P[j * NC + i] *= ct;
-      }
-#pragma unroll
-      for (int k = 0; k < NB; ++k) L.b[k].qd *= ct;
-      if (L.gl == 0) S.c *= ct;
-    });
   }
-  // scaled bounds, constraint classes
+  // last cost normalisation, P to shared memory, unit bundles 1.. = copies of bundle 0, scaled bounds, constraint classes
   w.each([&](LaneT& L, GS& S) {
     if (S.done) return;
     Cold& C = S.cold[L.gl];
+    if (o.scaling > 0) apply_cost(L, S);
+    if (L.is_core) {
+      const int j = L.gl;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) S.P[j * NC + i] = L.pr[i];
+#pragma unroll
+      for (int k = 1; k < KU; ++k) {
+        if (!C.active[k]) continue;
+        L.b[k].c = (k & 1) ? -L.b[0].c : L.b[0].c;
+        L.b[k].e = L.b[0].e; L.b[k].beta = L.b[0].beta; L.b[k].qd = L.b[0].qd;
+        C.E[k] = C.E[0]; C.Eb[k] = C.Eb[0]; C.Dd[k] = C.Dd[0];
+      }
+    }
     if (L.is_core && Cfg::BOUNDS) { L.lc *= C.Ecb; L.uc *= C.Ecb; C.clsc = row_class(L.lc, L.uc); }
     C.Dinv = 1.0 / C.D; C.Ecbinv = 1.0 / C.Ecb;
 #pragma unroll
@@ -433,7 +447,8 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
         for (int i = 0; i < NC; ++i) S.S[j * NC + i] += wa * S.A[r * NC + i];
       }
     });
-    // (b) in-place Gauss-Jordan inverse (S is SPD: no pivoting)
+    // (b) in-place Gauss-Jordan inverse (S is SPD: no pivoting); the pivot loop stays rolled (code size)
+#pragma unroll 1
     for (int kk = 0; kk < NC; ++kk) {
       w.each([&](LaneT& L, GS& S) {
         if (!S.need_factor || !L.is_core) return;
@@ -511,7 +526,9 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
       const double pz = first ? 0.0 : proj_row(L, b.v, b.l), pzb = first ? 0.0 : proj_sb(L, b.vb);
-      const double wr = L.rho_r * (2.0 * pz - b.v), wb = L.rho_b * (2.0 * pzb - b.vb);
+      // singleton bound row: 2 Proj(vb) - vb = |vb| on [0, inf), vb on a free row (exact)
+      const double wr = L.rho_r * (2.0 * pz - b.v);
+      const double wb = L.rho_b * (first ? -b.vb : ((LaneT::kHasEq && L.sb_free) ? b.vb : fabs(b.vb)));
       const double bd = sigma * b.xd - b.qd + b.e * wr + b.beta * wb;
       b.pz = pz; b.pzb = pzb; b.bd = bd;
       u += b.c * (wr - b.gam * bd);
@@ -543,7 +560,14 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       b.xd = alpha * xtd + oma * b.xd;
     }
   };
-  // phase B on a checked iteration: also records delta_x / delta_y of this iteration (cold data)
+  // project delta_y onto the polar of the recession cone of [l,u] (is_primal_infeasible)
+  auto proj_dy = [](double dy, bool lo_inf, bool hi_inf) {
+    if (hi_inf) return lo_inf ? 0.0 : dmin(dy, 0.0);
+    if (lo_inf) return dmax(dy, 0.0);
+    return dy;
+  };
+  // phase B on a checked iteration: also records delta_x / delta_y of this iteration (cold data) and publishes the
+  // exchange vectors of the termination check: x_c | y_r  and  dx_c | projected dy_r
   auto phase_b_keep = [&](LaneT& L, GS& S) {
     if (L.done) return;
     Cold& C = S.cold[L.gl];
@@ -576,6 +600,12 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       b.xd = xdn;
       C.dy[k] = L.rho_r * (b.v - proj_row(L, b.v, b.l)) - y0;
       C.dyb[k] = L.rho_b * (b.vb - proj_sb(L, b.vb)) - yb0;
+    }
+    if (L.is_core) { S.xy[L.gl] = L.x; S.v[L.gl] = C.dx; }
+    else {
+      const BundleHot& b = L.b[0];
+      S.xy[L.gl] = L.rho_r * (b.v - proj_row(L, b.v, b.l));
+      S.v[L.gl] = proj_dy(C.dy[0], is_inf_lo(b.l), !L.row_eq && is_inf_hi(kOsqpInfty * C.E[0]));
     }
   };
 
@@ -612,50 +642,37 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     w.each(phase_b_keep);
 
     // ---------------- OSQP update_info + check_termination + adapt_rho
-    // project delta_y onto the polar of the recession cone of [l,u] (is_primal_infeasible)
-    auto proj_dy = [](double dy, bool lo_inf, bool hi_inf) {
-      if (hi_inf) return lo_inf ? 0.0 : dmin(dy, 0.0);
-      if (lo_inf) return dmax(dy, 0.0);
-      return dy;
-    };
-    // C0: exchange x_c | y_r and dx_c | projected dy_r
+    // C1: per-lane partial reductions (registers; published once at the end).  Group totals:
+    //   rows:      0 pri_u | 1 max(ax_u, z_u) | 2 pri_s | 3 max(ax_s, z_s) | 4 ||E dy|| | 5 sum(u dy+ + l dy-)
+    //              6 max Adx over rows with a finite u | 7 max -Adx over rows with a finite l
+    //   variables: 8 dua_u | 9 max(px_u, aty_u, q_u) | 10 dua_s | 11 max(px_s, aty_s, q_s) | 12 ||Dinv A'dy||
+    //              13 ||D dx|| | 14 q'dx | 15 ||Dinv P dx||
+    // (_u = unscaled, what OSQP tests with scaled_termination off; _s = scaled, what adapt_rho uses.)
+    // One code path for core and row lanes: bundle 0 is the dense / equality row of a row lane and the first unit bundle
+    // of a core lane; only its core part (A_row x_c) differs.
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
       Cold& C = S.cold[L.gl];
-      if (L.is_core) { S.u[L.gl] = L.x; S.v[L.gl] = C.dx; }
-      else {
-        const BundleHot& b = L.b[0];
-        S.u[L.gl] = L.rho_r * (b.v - proj_row(L, b.v, b.l));
-        S.v[L.gl] = proj_dy(C.dy[0], is_inf_lo(b.l), !L.row_eq && is_inf_hi(kOsqpInfty * C.E[0]));
-      }
-    });
-    // C1: per-lane partial reductions
-    w.each([&](LaneT& L, GS& S) {
-      if (S.done) return;
-      Cold& C = S.cold[L.gl];
-      // per-lane partial reductions in registers (the hot-loop temporaries are dead here), published once at the end
       double m[kNumRed];
 #pragma unroll
       for (int i = 0; i < kNumRed; ++i) m[i] = 0.0;
-      m[20] = -1e300; m[21] = 1e300;
-      // rows:      0 pri_u 1 ax_u 2 z_u | 7 pri_s 8 ax_s 9 z_s | 14 ||E dy|| 15 sum(u dy+ + l dy-) | 20 max Adx (finite u) 21 min Adx (finite l)
-      // variables: 3 dua_u 4 px_u 5 aty_u 6 q_u | 10 dua_s 11 px_s 12 aty_s 13 q_s | 16 ||Dinv A'dy|| | 17 ||D dx|| 18 q'dx 19 ||Dinv P dx||
+      m[6] = -1e300; m[7] = -1e300;
       auto row_acc = [&](double ax, double z, double E, double Ei, double l, double u, bool lo_inf, bool hi_inf, double dy, double adx) {
         const double r = ax - z;
-        m[0] = dmax(m[0], fabs(Ei * r)); m[1] = dmax(m[1], fabs(Ei * ax)); m[2] = dmax(m[2], fabs(Ei * z));
-        m[7] = dmax(m[7], fabs(r)); m[8] = dmax(m[8], fabs(ax)); m[9] = dmax(m[9], fabs(z));
+        m[0] = dmax(m[0], fabs(Ei * r)); m[1] = dmax(m[1], dmax(fabs(Ei * ax), fabs(Ei * z)));
+        m[2] = dmax(m[2], fabs(r)); m[3] = dmax(m[3], dmax(fabs(ax), fabs(z)));
         const double pdy = proj_dy(dy, lo_inf, hi_inf);
-        m[14] = dmax(m[14], fabs(E * pdy));
-        m[15] += u * dmax(pdy, 0.0) + l * dmin(pdy, 0.0);
-        if (!hi_inf) m[20] = dmax(m[20], Ei * adx);
-        if (!lo_inf) m[21] = dmin(m[21], Ei * adx);
+        m[4] = dmax(m[4], fabs(E * pdy));
+        m[5] += u * dmax(pdy, 0.0) + l * dmin(pdy, 0.0);
+        if (!hi_inf) m[6] = dmax(m[6], Ei * adx);
+        if (!lo_inf) m[7] = dmax(m[7], -(Ei * adx));
       };
       auto var_acc = [&](double px, double aty, double q, double D, double Di, double atdy, double dx, double pdx) {
         const double r = px + q + aty;
-        m[3] = dmax(m[3], fabs(Di * r)); m[4] = dmax(m[4], fabs(Di * px)); m[5] = dmax(m[5], fabs(Di * aty)); m[6] = dmax(m[6], fabs(Di * q));
-        m[10] = dmax(m[10], fabs(r)); m[11] = dmax(m[11], fabs(px)); m[12] = dmax(m[12], fabs(aty)); m[13] = dmax(m[13], fabs(q));
-        m[16] = dmax(m[16], fabs(Di * atdy));
-        m[17] = dmax(m[17], fabs(D * dx)); m[18] += q * dx; m[19] = dmax(m[19], fabs(Di * pdx));
+        m[8] = dmax(m[8], fabs(Di * r)); m[9] = dmax(m[9], dmax(fabs(Di * px), dmax(fabs(Di * aty), fabs(Di * q))));
+        m[10] = dmax(m[10], fabs(r)); m[11] = dmax(m[11], dmax(fabs(px), dmax(fabs(aty), fabs(q))));
+        m[12] = dmax(m[12], fabs(Di * atdy));
+        m[13] = dmax(m[13], fabs(D * dx)); m[14] += q * dx; m[15] = dmax(m[15], fabs(Di * pdx));
       };
       // a bundle: its row, its singleton variable and that variable's bound row; y_out / pdy_out return the
       // row's multiplier and projected delta for the core column sum (core lanes)
@@ -680,32 +697,40 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
           var_acc(0.0, aty, b.qd, C.Dd[k], C.Ddinv[k], atdy, C.dxd[k], 0.0);
         }
       };
+      double cax, cadx;                          // core part of bundle 0's row:  A_row x_c,  A_row dx_c
+      double px = 0, pdx = 0, aty = 0, atdy = 0;  // core variable: (P x)_j, (P dx)_j, (A'y)_j, (A'dy)_j
       if (L.is_core) {
         const int j = L.gl;
-        double px = 0, pdx = 0, aty = 0, atdy = 0;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { px += S.P[j * NC + i] * S.u[i]; pdx += S.P[j * NC + i] * S.v[i]; }
+        for (int i = 0; i < NC; ++i) { px += S.P[j * NC + i] * S.xy[i]; pdx += S.P[j * NC + i] * S.v[i]; }
 #pragma unroll
-        for (int r = 0; r < NR; ++r) { aty += S.A[r * NC + j] * S.u[NC + r]; atdy += S.A[r * NC + j] * S.v[NC + r]; }
+        for (int r = 0; r < NR; ++r) { aty += S.A[r * NC + j] * S.xy[NC + r]; atdy += S.A[r * NC + j] * S.v[NC + r]; }
         if (Cfg::BOUNDS) {
           const double zc = clampd(L.vc, L.lc, L.uc), yc = L.rhoc * (L.vc - zc);
           const bool lo_inf = is_inf_lo(L.lc), hi_inf = is_inf_hi(L.uc);
           aty += L.betac * yc; atdy += L.betac * proj_dy(C.dyc, lo_inf, hi_inf);
           row_acc(L.betac * L.x, zc, C.Ecb, C.Ecbinv, L.lc, L.uc, lo_inf, hi_inf, C.dyc, L.betac * C.dx);
         }
+        cax = L.b[0].c * L.x; cadx = L.b[0].c * C.dx;
+      } else {
+        const int r = L.gl - NC;
+        cax = 0; cadx = 0;
 #pragma unroll
-        for (int k = 0; k < KU; ++k) {
+        for (int i = 0; i < NC; ++i) { cax += S.A[r * NC + i] * S.xy[i]; cadx += S.A[r * NC + i] * S.v[i]; }
+      }
+      {
+        double y, pdy;
+        bundle_acc(0, cax, cadx, y, pdy);
+        aty += L.b[0].c * y; atdy += L.b[0].c * pdy;
+      }
+      if (L.is_core) {
+#pragma unroll
+        for (int k = 1; k < KU; ++k) {
           double y, pdy;
           bundle_acc(k, L.b[k].c * L.x, L.b[k].c * C.dx, y, pdy);
           aty += L.b[k].c * y; atdy += L.b[k].c * pdy;
         }
         var_acc(px, aty, L.q, C.D, C.Dinv, atdy, C.dx, pdx);
-      } else {
-        const int r = L.gl - NC;
-        double ax = 0, adx = 0, y, pdy;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) { ax += S.A[r * NC + i] * S.u[i]; adx += S.A[r * NC + i] * S.v[i]; }
-        bundle_acc(0, ax, adx, y, pdy);
       }
 #pragma unroll
       for (int i = 0; i < kNumRed; ++i) S.red[i * GL + L.gl] = m[i];
@@ -714,12 +739,12 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     w.each([&](LaneT& L, GS& S) {
       if (S.done) return;
       for (int i = L.gl; i < kNumRed; i += GL) {
-        const bool is_sum = (i == 15 || i == 18), is_min = (i == 21);
-        double acc = is_sum ? 0.0 : (is_min ? 1e300 : (i == 20 ? -1e300 : 0.0));
+        const bool is_sum = (i == 5 || i == 14);
+        double acc = (i == 6 || i == 7) ? -1e300 : 0.0;
 #pragma unroll
         for (int l = 0; l < GL; ++l) {
           const double val = S.red[i * GL + l];
-          acc = is_sum ? acc + val : (is_min ? dmin(acc, val) : dmax(acc, val));
+          acc = is_sum ? acc + val : dmax(acc, val);
         }
         S.tot[i] = acc;
       }
@@ -730,20 +755,20 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       double m[kNumRed];
 #pragma unroll
       for (int i = 0; i < kNumRed; ++i) m[i] = S.tot[i];
-      const double pri_res = m[0], dua_res = S.cinv * m[3];
+      const double pri_res = m[0], dua_res = S.cinv * m[8];
       S.pri_res = pri_res; S.dua_res = dua_res;
       if (can_check) {
         auto evaluate = [&](double mult) -> int {
           const double ea = o.eps_abs * mult, er = o.eps_rel * mult, epi = o.eps_prim_inf * mult, edi = o.eps_dual_inf * mult;
           if (pri_res > kOsqpInfty || dua_res > kOsqpInfty) return kQpNonConvex;
           bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
-          const double eps_prim = ea + er * dmax(m[2], m[1]);
+          const double eps_prim = ea + er * m[1];
           if (pri_res < eps_prim) prim_ok = true;
-          else if (m[14] > epi && m[15] < -epi * m[14]) prim_inf = m[16] < epi * m[14];
-          const double eps_dual = ea + er * S.cinv * dmax(m[6], dmax(m[5], m[4]));
+          else if (m[4] > epi && m[5] < -epi * m[4]) prim_inf = m[12] < epi * m[4];
+          const double eps_dual = ea + er * S.cinv * m[9];
           if (dua_res < eps_dual) dual_ok = true;
-          else if (m[17] > edi && m[18] < -S.c * edi * m[17] && m[19] < S.c * edi * m[17])
-            dual_inf = !(m[20] > edi * m[17]) && !(m[21] < -edi * m[17]);
+          else if (m[13] > edi && m[14] < -S.c * edi * m[13] && m[15] < S.c * edi * m[13])
+            dual_inf = !(m[6] > edi * m[13]) && !(m[7] > edi * m[13]);
           if (prim_ok && dual_ok) return mult > 1.0 ? kQpSolvedInaccurate : kQpSolved;
           if (prim_inf) return kQpPrimalInfeasible;
           if (dual_inf) return kQpDualInfeasible;
@@ -758,8 +783,8 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       }
       if (can_adapt) {
         // compute_rho_estimate on the SCALED residuals
-        const double pr = m[7] / (dmax(m[9], m[8]) + 1e-10);
-        const double dr = m[10] / (dmax(m[13], dmax(m[12], m[11])) + 1e-10);
+        const double pr = m[2] / (m[3] + 1e-10);
+        const double dr = m[10] / (m[11] + 1e-10);
         double rho_new = S.rho * sqrt(pr / (dr + 1e-10));
         rho_new = dmin(dmax(rho_new, kRhoMin), kRhoMax);
         if (rho_new > S.rho * o.adaptive_rho_tolerance || rho_new < S.rho / o.adaptive_rho_tolerance) {

@@ -182,21 +182,36 @@ class Oracle:
         return dict(status=st, x=x, y=y, iters=it.value, pri_res=info[0], dua_res=info[1], rho=info[2],
                     rho_updates=int(info[3]))
 
-    def cycle(self, mode: int, q, qd, x_target, xdot_target, frame: int, want_x=False):
-        """mode 0 QPIK(xdot_des) 1 QPIKStep 2 QPID(xddot_des) 3 QPIDStep. x_target: (B,12) or None."""
+    def cycle(self, mode: int, q, qd, x_target, xdot_target, frame: int, want_x=False, want_y=False):
+        """mode 0 QPIK(xdot_des) 1 QPIKStep 2 QPID(xddot_des) 3 QPIDStep. x_target: (B,12) or None.
+        want_x / want_y: primal / dual vector of the QP in the reference's order (QP_base.h:204-226:
+        rows = [bounds; inequalities; equalities])."""
         q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
         B, n = q.shape
         xt = None if x_target is None else _c(x_target).reshape(B, 12)
         xd = _c(xdot_target).reshape(B, 6)
         out, st, it = np.zeros((B, n)), np.zeros(B, np.int32), np.zeros(B, np.int32)
-        nx, _ = self.qp_sizes(0 if mode <= 1 else 1)
+        nx, nc = self.qp_sizes(0 if mode <= 1 else 1)
         qx = np.zeros((B, nx)) if want_x else None
-        lib().orc_cycle(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out),
-                        _i(st), _i(it), _d(qx))
+        qy = np.zeros((B, nc)) if want_y else None
+        lib().orc_cycle_xy(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out),
+                           _i(st), _i(it), _d(qx), _d(qy))
         r = dict(out=out, status=st, iters=it)
         if want_x:
             r["x"] = qx
+        if want_y:
+            r["y"] = qy
         return r
+
+    def desired_task(self, mode: int, q, qd, x_target, xdot_target, frame: int):
+        """desired task-space signal the Step controllers hand to the QP (robot_controller.cpp:292-300, 335-345):
+        Kp e + Kv edot (modes 1, 3)."""
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B = q.shape[0]
+        des = np.zeros((B, 6))
+        lib().orc_desired_task(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(_c(x_target).reshape(B, 12)),
+                               _d(_c(xdot_target).reshape(B, 6)), C.c_int(frame), _d(des))
+        return des
 
     def taskspace(self, mode: int, q, qd, x_target, xdot_target, frame: int, null_vec=None):
         """mode 0 CLIKStep, 1 OSFStep, 2 OSF(xddot given in xdot_target)."""
@@ -301,17 +316,24 @@ class MomaOracle(Oracle):
                                 _d(l), _d(u))
         return P, qv, A, l, u
 
-    def moma_cycle(self, mode: int, q, qd, x_target, xdot_target, frame: int):
-        """mode 0 QPIK 1 QPIKStep 2 QPID 3 QPIDStep -> out (B, act): eta* | tau*; out2: eta_dot* (modes 2/3)."""
+    def moma_cycle(self, mode: int, q, qd, x_target, xdot_target, frame: int, want_xy=False):
+        """mode 0 QPIK 1 QPIKStep 2 QPID 3 QPIDStep -> out (B, act): eta* | tau*; out2: eta_dot* (modes 2/3).
+        want_xy: also the primal / dual vectors of the QP in the reference's order."""
         q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
         B = q.shape[0]
         xt = None if x_target is None else _c(x_target).reshape(B, 12)
         xd = _c(xdot_target).reshape(B, 6)
         out, out2 = np.zeros((B, self.act)), np.zeros((B, self.act))
         st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
-        lib().orc_moma_cycle(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out), _d(out2),
-                             _i(st), _i(it))
-        return dict(out=out, out2=out2, status=st, iters=it)
+        nx, nc = self.moma_qp_sizes(0 if mode <= 1 else 1)
+        qx = np.zeros((B, nx)) if want_xy else None
+        qy = np.zeros((B, nc)) if want_xy else None
+        lib().orc_moma_cycle_xy(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out),
+                                _d(out2), _i(st), _i(it), _d(qx), _d(qy))
+        r = dict(out=out, out2=out2, status=st, iters=it)
+        if want_xy:
+            r["x"], r["y"] = qx, qy
+        return r
 
 
 def task_space_cubic(x_target, xdot_target, x_init, xdot_init, t, t0, dur):

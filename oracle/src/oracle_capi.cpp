@@ -242,8 +242,15 @@ int orc_solve_qp(OrcHandle* h, int n, int m, const double* P, const double* qv, 
 // mode: 0 QPIK(xdot_des given, 6)      1 QPIKStep(x_target 12, xdot_target 6)
 //       2 QPID(xddot_des given, 6)     3 QPIDStep(x_target, xdot_target)
 // out: (B, n) qdot* (modes 0/1) or tau* (modes 2/3); status/iters: (B,)
+void orc_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                  const double* xdot_target, int frame, double* out, int* status, int* iters, double* qp_x, double* qp_y);
 void orc_cycle(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
                const double* xdot_target, int frame, double* out, int* status, int* iters, double* qp_x) {
+  orc_cycle_xy(h, mode, B, q, qd, x_target, xdot_target, frame, out, status, iters, qp_x, nullptr);
+}
+// same, plus the dual vector y of the QP (rows in the reference's order [bounds; inequalities; equalities], QP_base.h:204-226)
+void orc_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                  const double* xdot_target, int frame, double* out, int* status, int* iters, double* qp_x, double* qp_y) {
   const Model& m = h->m;
   const int n = m.nv;
 #pragma omp parallel num_threads(h->threads)
@@ -261,7 +268,21 @@ void orc_cycle(OrcHandle* h, int mode, int B, const double* q, const double* qd,
       if (status) status[b] = st;
       if (iters) iters[b] = ws.res.iters;
       if (qp_x) std::copy(ws.res.x.begin(), ws.res.x.end(), qp_x + size_t(b) * ws.res.x.size());
+      if (qp_y) std::copy(ws.res.y.begin(), ws.res.y.end(), qp_y + size_t(b) * ws.res.y.size());
     }
+  }
+}
+
+// desired task signal of the Step controllers: Kp e + Kv edot (QPIKStep / QPIDStep, robot_controller.cpp:292-300, 335-345)
+void orc_desired_task(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                      const double* xdot_target, int frame, double* des) {
+  (void)mode;
+  const Model& m = h->m;
+  const int n = m.nv;
+  State s;
+  for (int b = 0; b < B; ++b) {
+    update_state(m, s, q + b * n, qd + b * n);
+    desired_from_error(m, s, frame, pose_from12(x_target + 12 * b), xdot_target + 6 * b, h->cp, true, des + 6 * b);
   }
 }
 
@@ -422,8 +443,16 @@ void orc_moma_build_qp(OrcHandle* h, int kind, const double* q, const double* qd
   std::copy(ws.pb.u.begin(), ws.pb.u.end(), u);
 }
 // mode: 0 QPIK(xdot_des) 1 QPIKStep 2 QPID(xddot_des) 3 QPIDStep.  out: (B, act) eta* | tau*;  out2: (B, act) eta_dot* (modes 2/3)
+void orc_moma_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                       const double* xdot_target, int frame, double* out, double* out2, int* status, int* iters, double* qp_x,
+                       double* qp_y);
 void orc_moma_cycle(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
                     const double* xdot_target, int frame, double* out, double* out2, int* status, int* iters) {
+  orc_moma_cycle_xy(h, mode, B, q, qd, x_target, xdot_target, frame, out, out2, status, iters, nullptr, nullptr);
+}
+void orc_moma_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                       const double* xdot_target, int frame, double* out, double* out2, int* status, int* iters, double* qp_x,
+                       double* qp_y) {
   const Model& m = h->m;
   const int n = m.nv;
 #pragma omp parallel num_threads(h->threads)
@@ -446,6 +475,8 @@ void orc_moma_cycle(OrcHandle* h, int mode, int B, const double* q, const double
       }
       if (status) status[b] = st;
       if (iters) iters[b] = ws.res.iters;
+      if (qp_x) std::copy(ws.res.x.begin(), ws.res.x.end(), qp_x + size_t(b) * ws.res.x.size());
+      if (qp_y) std::copy(ws.res.y.begin(), ws.res.y.end(), qp_y + size_t(b) * ws.res.y.size());
     }
   }
 }
