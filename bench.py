@@ -42,8 +42,41 @@ LINK = "fr3_link8"
 # Algorithmic fp64 flop model of the structured ADMM kernel for FR3 QPIK (NC=7, KU=2, ND=2; FMA = 2 flops),
 # derived in DESIGN.md section "ADMM flop model": per iteration, per termination check, per (re)factorisation,
 # and the one-off Ruiz scaling.
-FLOPS_ITER, FLOPS_CHECK, FLOPS_FACTOR, FLOPS_SCALE = 867.0, 1450.0, 1900.0, 4300.0
+FLOPS_ITER, FLOPS_CHECK, FLOPS_FACTOR, FLOPS_SCALE = 867.0, 1450.0, 1900.0, 4300.0   # fallback (round-1 hand count, FR3 QPIK)
 BYTES_PER_CYCLE = 320.0  # q, qdot, x_target(12), xdot_target in; qdot*, status, iters out
+
+
+def flops_model(workload: str):
+    """Algorithmic fp64 flop counts per robot from bench/flops_model.json (written by tools/count_flops.py: the oracle run with a
+    flop-counting scalar on the benchmark inputs): ADMM per iteration / termination check / factorisation / equilibration, and the
+    per-cycle front stages (kinematics, dynamics, manipulability, self-collision, QP build)."""
+    try:
+        m = json.loads((ROOT / "bench" / "flops_model.json").read_text())["workloads"].get(workload)
+    except Exception:
+        m = None
+    if m is None and workload == "fr3_qpik":
+        m = dict(admm=dict(iter=FLOPS_ITER, check=FLOPS_CHECK, factor=FLOPS_FACTOR, scale=FLOPS_SCALE), front=None, source="fallback hand count")
+    return m
+
+
+def ncu_traffic(workload: str, B: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_admm launch from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, keyed by the source hash of the build it was taken from); None when the library has changed since."""
+    try:
+        from dyros_robot_controller_b200 import build as _b
+        t = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        e = t.get(f"{workload}@{B}")
+        return float(e["k_admm_dram_bytes"]) if (e and e.get("source_hash") == _b._source_hash()) else None
+    except Exception:
+        return None
+
+
+def admm_flops(model, iters):
+    """sum over robots of the ADMM flops for their iteration counts (rho updates: see flops_model.json 'refactor_rate')."""
+    a = model["admm"]
+    checks = np.ceil(iters / 25.0)
+    refactors = 1.0 + a.get("refactor_rate", 0.01) * iters   # measured mean rho updates per iteration on the benchmark inputs
+    return float(np.sum(a["scale"] + a["factor"] * refactors + a["iter"] * iters + a["check"] * checks))
 
 
 # ---- workloads: "fr3_qpik" is BASELINE.json's metric (config 1 at the headline batch); the others are the sibling configs
@@ -227,7 +260,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 8192
+    sample = args.batch   # same config as the product arm: one step = the whole batch (65536 robots take ~0.6 s on 16 threads)
     times = []
     for i in range(args.warmup + args.steps):
         cps, dt, _ = oracle_cycles_per_s(sample, threads, seed=i, workload=args.workload)
@@ -349,6 +382,7 @@ def run_ours(args):
         step(max(args.warmup, 3) + args.steps - 1 - k)
         torch.cuda.synchronize()
         stage_ms.append(ctx.last_timing() if not taskspace else dict(build_ms=0.0, collision_ms=0.0, admm_ms=0.0, total_ms=0.0))
+    trace = ctx.last_trace() if (not taskspace and not moma) else []
     if dist is not None:
         dist.barrier()
     clocks = sampler.stop()
@@ -406,9 +440,8 @@ def run_ours(args):
         return
     # ---- roofline of the dominant kernel (ADMM), algorithmic flops from the per-robot iteration counts
     iters, status = iters_last, status_last
-    checks = np.ceil(iters / 25.0)
-    refactors = 1.0 + np.floor(iters / 50.0) * 0.5  # upper-bound model: at most one rho update per 50 iterations
-    flops = float(np.sum(FLOPS_SCALE + FLOPS_FACTOR * refactors + FLOPS_ITER * iters + FLOPS_CHECK * checks))
+    fm = flops_model(args.workload)
+    flops = admm_flops(fm, iters) if (fm and not taskspace) else None
     admm_ms = float(np.mean([s["admm_ms"] for s in stage_ms]))
     build_ms = float(np.mean([s["build_ms"] for s in stage_ms]))
     col_ms = float(np.mean([s["collision_ms"] for s in stage_ms]))
@@ -417,7 +450,10 @@ def run_ours(args):
         peak_src = "measured in-run by drc_bench_fp64_peak (FP64 FMA, 8 chains/thread)"
     except Exception as e:  # pragma: no cover
         peak, peak_src = 37.0, f"fallback nominal B200 FP64 ({e})"
-    achieved = flops / (admm_ms * 1e-3) / 1e12 if args.workload == "fr3_qpik" else None  # flop model exists for the metric's QP only
+    achieved = flops / (admm_ms * 1e-3) / 1e12 if (flops is not None and admm_ms > 0) else None
+    # whole-step view: front stages (kinematics, dynamics, manipulability, self-collision, QP build) + ADMM over the step time
+    step_flops = (flops + fm["front"]["total"] * B) if (flops is not None and fm.get("front")) else None
+    step_achieved = step_flops / (ms_per_step * 1e-3) / 1e12 if step_flops is not None else None
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -430,11 +466,16 @@ def run_ours(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of one k_admm launch at this batch from the ncu --set full capture
                 # of the final build (profiles/r01_ncu_summary_v5_dynamics_split.md: 41.83 MB + 0.39 MB); algorithmic: 632 B record +
                 # 64 B result per robot
-                "traffic": 42.22e6 if (args.workload == "fr3_qpik" and B == 65536) else None,
+                "traffic": ncu_traffic(args.workload, B),
                 "traffic_algorithmic": (632.0 + 64.0) * B if args.workload == "fr3_qpik" else None,
                 "peak_source": peak_src,
+                "flops_model": (fm or {}).get("source"),
+                "whole_step": {"achieved": step_achieved, "frac": (step_achieved / peak) if step_achieved is not None else None,
+                               "flops_per_cycle": (step_flops / B) if step_flops is not None else None},
                 "kernel_ms": admm_ms, "kernel_share_of_step": admm_ms / ms_per_step,
                 "stage_ms": {"state_and_qp_build": build_ms, "self_collision": col_ms, "admm": admm_ms},
+                # end time [ms since the call started] of every stage of the last instrumented step, main and priority pipeline
+                "trace_ms": {k: round(v, 4) for k, v in trace},
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}}
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample
@@ -459,6 +500,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
+            "peaks": {"fp64_tflops": peak, "fp64_source": peak_src, "hbm_gbs": hbm_peak, "hbm_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
             "roofline": roofline,
             "cpu_baseline": None if world > 1 else {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} cycles of the same workload, one pass, OpenMP over {cores} host threads "
@@ -467,9 +509,128 @@ def run_ours(args):
                                                "sample": f"{min(sample, 4096)} cycles, one thread ({cpu1_dt:.2f} s); the reference's "
                                                          "control loop is single-threaded"}},
             "solved_fraction": float(np.mean(status == 1)), "mean_admm_iters": float(np.mean(iters))}
+    if world == 1 and args.workload == "fr3_qpik" and not args.no_siblings:
+        del ctx, flush
+        torch.cuda.empty_cache()
+        sib = {}
+        for name, Bs in SIBLINGS:
+            try:
+                sib[name] = measure_sibling(name, Bs, local, peak)
+            except Exception as e:  # a sibling must never cost the headline line
+                sib[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["siblings"] = sib
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+# BASELINE.json configs 2-5 at their stated batch sizes (config 5: the full 1 M batch on one GPU), measured after the headline so
+# that they are driver-run numbers too.  Shorter runs than the headline: 3 warm-up + 5 timed steps each.
+SIBLINGS = [("ur5e_clik_osf", 4096), ("fr3_qpid", 65536), ("husky_qpik", 262144), ("husky_qpid", 262144),
+            ("xls_qpik", 1048576), ("xls_qpid", 1048576)]
+
+
+def measure_sibling(name: str, B: int, local: int, peak: float, steps: int = 5, warmup: int = 3):
+    """one sibling configuration on this GPU: device-timed value, e2e through the host-buffer C-ABI, CPU baseline on a bounded sample,
+    ADMM roofline from the flop model.  Same measurement rules as the headline (CUDA events on the launch stream, L2 flushed
+    between steps, consecutive control ticks)."""
+    import torch
+    import dyros_robot_controller_b200 as drc
+    wl = WORKLOADS[name]
+    urdf, srdf = robot_paths(wl["robot"])
+    model = drc.Model(urdf, srdf)
+    moma = wl["robot"] not in ("fr3", "ur5e")
+    link = wl.get("link", LINK)
+    taskspace = wl["kind"] == "taskspace"
+    dev = torch.device("cuda", local)
+    if moma:
+        md = MOMA_DESC[wl["robot"]]
+        model.attach_mobile_base(md["kin"], md["joint_idx"], md["actuator_idx"])
+    ctx = drc.Context(model, B, device=local)
+    if moma:
+        q, qd, q_t, xdot_t = make_moma_workload(model.q_lower, model.q_upper, model.v_limit, md["w"], B, seed=0)
+        ctx.moma_update_state(q_t, qd)
+        x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
+        nout = model.actuated_dof
+    else:
+        q, qd, q_t, xdot_t = make_workload(model, B, seed=0)
+        ctx.update_state(q_t, qd)
+        x_t = ctx.get_frame(link, want=("pose",))["pose"]
+        nout = model.dof
+    tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xdot_t))
+    out, out2 = (torch.empty((B, nout), dtype=torch.float64, device=dev) for _ in range(2))
+    st, it = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def cycle(a_q, a_qd, a_xt, a_xd, o_out, o_st, o_it, o_out2):
+        if moma:
+            ctx.moma_cycle(wl["kind"], a_q, a_qd, a_xt, a_xd, LINK, out=o_out, out2=o_out2, status=o_st, iters=o_it)
+        elif taskspace:
+            ctx.update_state(a_q, a_qd)
+            ctx.clik_step(a_xt, a_xd, link, out=o_out)
+            ctx.osf_step(a_xt, a_xd, link, out=o_out2)
+        elif wl["kind"] == "ik":
+            ctx.cycle_qpik_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
+        else:
+            ctx.cycle_qpid_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
+
+    DT = 1e-3
+    for k in range(warmup):
+        cycle(tq + (k * DT) * tqd, tqd, txt, txd, out, st, it, out2)
+    torch.cuda.synchronize()
+    ctx.enable_timing(not taskspace)
+    l0 = ctx.launch_count
+    pairs = []
+    for k in range(steps):
+        qk = tq + ((warmup + k) * DT) * tqd
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cycle(qk, tqd, txt, txd, out, st, it, out2)
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in pairs]))
+    launches = ctx.launch_count - l0
+    stage = ctx.last_timing() if not taskspace else dict(build_ms=0.0, collision_ms=0.0, admm_ms=0.0, total_ms=0.0)
+    if taskspace:
+        it.zero_(); st.fill_(1)
+    iters, status = it.cpu().numpy().astype(np.float64), st.cpu().numpy()
+    # e2e: pinned host buffers through the drc_host_* entry points
+    ctx.enable_timing(False)
+    hq, hqd, hxt, hxd = (torch.from_numpy(a).pin_memory().numpy() for a in (q, qd, x_t, xdot_t))
+    hout, hout2 = (torch.empty((B, nout), dtype=torch.float64).pin_memory().numpy() for _ in range(2))
+    hst, hit = (torch.empty(B, dtype=torch.int32).pin_memory().numpy() for _ in range(2))
+    cycle(hq, hqd, hxt, hxd, hout, hst, hit, hout2)
+    n_e2e = 3
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        cycle(hq, hqd, hxt, hxd, hout, hst, hit, hout2)
+    e2e = B * n_e2e / (time.perf_counter() - t0)
+    h2d = B * (model.dof * 2 + 12 + 6) * 8
+    d2h = B * (nout * 8 * (2 if ((moma and wl["kind"] == "id") or taskspace) else 1) + (0 if taskspace else 8))
+    # CPU baseline on a bounded sample of the same workload
+    cores = os.cpu_count() or 1
+    sample = min(B, 8192)
+    cpu_val, cpu_dt, _ = oracle_cycles_per_s(sample, cores, workload=name)
+    fm = flops_model(name)
+    admm_ms = float(stage["admm_ms"])
+    fl = admm_flops(fm, iters) if (fm and not taskspace) else None
+    ach = fl / (admm_ms * 1e-3) / 1e12 if (fl and admm_ms > 0) else None
+    if taskspace and fm and fm.get("front"):   # no QP: the whole step is the front stage
+        ach = fm["front"]["total"] * B / (ms * 1e-3) / 1e12
+    del ctx, flush
+    torch.cuda.empty_cache()
+    return {"workload": wl["desc"], "batch": B, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "k_admm" if not taskspace else "k_robot_job", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (ach / peak) if ach is not None else None, "kernel_ms": admm_ms if not taskspace else ms,
+                         "stage_ms": {"state_and_qp_build": float(stage["build_ms"]), "self_collision": float(stage["collision_ms"]), "admm": admm_ms},
+                         "flops_model": (fm or {}).get("source")},
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} cycles of the same workload, one pass, OpenMP over {cores} host threads ({cpu_dt:.2f} s)"},
+            "solved_fraction": float(np.mean(status == 1)), "mean_admm_iters": float(np.mean(iters))}
 
 
 def main():
@@ -480,6 +641,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="robots per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fr3_qpik", choices=sorted(WORKLOADS), help="default = BASELINE.json's metric")
+    ap.add_argument("--no-siblings", action="store_true", help="skip the sibling configurations (BASELINE configs 2-5) after the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

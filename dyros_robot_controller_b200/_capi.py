@@ -49,6 +49,7 @@ SYMBOLS = [
     "drc_host_clik_step", "drc_host_osf", "drc_host_osf_step", "drc_host_joint_torque_step",
     "drc_host_task_space_cubic", "drc_host_cycle_qpik_step", "drc_host_cycle_qpid_step",
     "drc_ctx_enable_timing", "drc_ctx_last_timing", "drc_ctx_launch_count", "drc_bench_fp64_peak",
+    "drc_ctx_last_trace", "drc_ctx_enable_qp_debug", "drc_host_get_qp_debug",
     "drc_model_attach_mobile_base", "drc_model_moma_info", "drc_model_base_jacobian",
     "drc_batch_moma_update_state", "drc_batch_moma_get_state", "drc_batch_moma_qpik", "drc_batch_moma_qpik_step",
     "drc_batch_moma_qpid", "drc_batch_moma_qpid_step", "drc_batch_moma_cycle_qpik_step", "drc_batch_moma_cycle_qpid_step",

@@ -81,6 +81,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def check() -> None:
+    """Host-code syntax pass in seconds: every translation unit with empty kernel bodies (-DDRC_SYNTAX_CHECK).  nvcc runs the
+    device compilation (minutes for the real kernels) BEFORE the host compiler, so a typo in the C ABI otherwise shows up late."""
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    for src in SOURCES:
+        r = subprocess.run([_nvcc(), *NVCC_FLAGS, "-DDRC_SYNTAX_CHECK", "-c", "-o", "/dev/null", str(src)], capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"syntax check failed on {src.name}:\n" + r.stdout + r.stderr)
+    print("syntax check ok")
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print("built", LIB)
+    if "--check" in sys.argv:
+        check()
+    else:
+        build(force="--force" in sys.argv, verbose=True)
+        print("built", LIB)

@@ -620,6 +620,8 @@ template <int NV, bool CHAIN>
 DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io, int b) {
   BestPair best;
   best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
+  int best_k = -1;                 // closed-form pass: only (distance, reference order, pair index) of the running minimum travel
+                                   // through the loop; the witness points of the winner are re-evaluated once afterwards
   unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair whose bound beats the best exact distance so far
   float lbs[64];                   // its certified lower bound (rounded DOWN to float: still a lower bound)
   int gi = 0;
@@ -633,8 +635,9 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
       const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
       const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
       if (has_closed_form(A.type, Bp.type)) {
-        const PairResult r = closed_form_distance(A, Bp);
-        consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
+        const double d = closed_form_distance(A, Bp).d;
+        const int id = m.geom.pair_id[k];
+        if (d < best.d || (d == best.d && id < best.id)) { best.d = d; best.id = id; best_k = k; }
       } else {
         const double lb = pair_lower_bound(A, Bp);
         if (lb <= best.d) cand |= 1ull << gi;
@@ -644,6 +647,16 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
         ++gi;
       }
     }
+  }
+  if (best_k >= 0) {  // witness points of the closed-form winner (same evaluation as in the loop: same bits)
+    const int ga = m.geom.pair_a[best_k], gb = m.geom.pair_b[best_k];
+    const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
+    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+    const Mat3 Rab = tmul(FA.R, FB.R);
+    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
+    const PairResult r = closed_form_distance(A, Bp);
+    best.ja = ja; best.jb = jb; best.pa = r.pa; best.pb = r.pb;
   }
   // GJK pass, best first: every thread resolves ITS most promising candidate (smallest lower bound) first, so that
   // the improving minimum culls most of the others before they cost a GJK run (and the warp's lanes stay in step)
@@ -741,11 +754,13 @@ struct SolveIO {
   int* status; int* iters;      // per robot (optional)
   const double* c_g; long long Bc;  // gravity cache for the QPID fallback
   double* qp_x;                 // optional debug: [core x (NC) | unit slacks (KU*NC) | row singletons (NR)] per robot
+  double* qp_y;                 // optional debug: unscaled duals [core bound rows (NC) | unit rows (KU*NC) | unit-slack bound rows (KU*NC) | rows (NR) | row-singleton bound rows (NR)]
   const int* order;             // optional schedule: the i-th solver group takes robot order[i] (null = identity)
   int* iters_hint;              // optional: iteration count of every robot, kept by the context for the next tick's schedule
   const int* order_off;         // optional (device): skip the first *order_off entries of `order` (they run in the priority launch)
   const int* out_ids;           // optional: outputs / hints of QP slot i go to robot out_ids[i] (priority launch: records are compact)
   const int* count;             // optional (device): number of slots (null = B)
+  const int* skip;              // optional: robots (QP slots) with skip[slot] != 0 are left to another launch (EPA-pending robots)
 };
 
 template <class Cfg, bool ID, class W>
@@ -762,6 +777,11 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
       if (io.iters_hint) io.iters_hint[b] = S.iters;
     }
     const ColdLane<Cfg>& C = S.cold[L.gl];
+    constexpr int NY = Cfg::NC * (1 + 2 * Cfg::KU) + 2 * Cfg::NR;
+    double* yr = io.qp_y ? io.qp_y + (long long)b * NY : nullptr;
+    // OSQP unscale_solution: y = E y_scaled / c, y_scaled = rho (v - Proj(v))
+    auto dual_row = [&](int k) { return S.cinv * C.E[k] * (L.rho_r * (L.b[k].v - proj_row(L, L.b[k].v, L.b[k].l))); };
+    auto dual_sb = [&](int k) { return S.cinv * C.Eb[k] * (L.rho_b * (L.b[k].vb - proj_sb(L, L.b[k].vb))); };
     if (L.is_core) {
       const int j = L.gl;
       const double xc = C.D * L.x;
@@ -773,6 +793,14 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
 #pragma unroll
         for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = C.has_sing[k] ? C.Dd[k] * L.b[k].xd : 0.0;
       }
+      if (yr) {
+        yr[j] = Cfg::BOUNDS ? S.cinv * C.Ecb * (L.rhoc * (L.vc - clampd(L.vc, L.lc, L.uc))) : 0.0;
+#pragma unroll
+        for (int k = 0; k < Cfg::KU; ++k) {
+          yr[Cfg::NC * (1 + k) + j] = C.active[k] ? dual_row(k) : 0.0;
+          yr[Cfg::NC * (1 + Cfg::KU + k) + j] = C.has_sb[k] ? dual_sb(k) : 0.0;
+        }
+      }
     } else {
       const int r = L.gl - Cfg::NC;
       if (ID && r >= Cfg::ND) {
@@ -780,6 +808,10 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
         io.out[b * io.sout.sb + j * io.sout.sk] = ok ? C.Dd[0] * L.b[0].xd : io.c_g[j * io.Bc + slot];
       }
       if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = C.has_sing[0] ? C.Dd[0] * L.b[0].xd : 0.0;
+      if (yr) {
+        yr[Cfg::NC * (1 + 2 * Cfg::KU) + r] = dual_row(0);
+        yr[Cfg::NC * (1 + 2 * Cfg::KU) + Cfg::NR + r] = C.has_sb[0] ? dual_sb(0) : 0.0;
+      }
     }
   });
 }

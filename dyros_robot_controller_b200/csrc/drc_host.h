@@ -49,7 +49,8 @@ struct drc_ctx {
   DrcParams prm;
   cudaStream_t stream;
   cudaStream_t side;      // EPA pass of the self-collision stage runs here, next to the state / QP-build kernel
-  cudaEvent_t ev_col, ev_epa;
+  cudaEvent_t ev_col, ev_epa, ev_build;
+  cudaStream_t prio_side; cudaEvent_t ev_prio_fk, ev_prio_build;   // priority pipeline: QP build next to the narrow phase
   // state cache (SoA, stride cap)
   double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
   double *c_Mact, *c_Minvact, *c_gact, *c_nleact;  // mobile manipulator only (actuated-space dynamics)
@@ -77,7 +78,17 @@ struct drc_ctx {
   bool timing;
   cudaEvent_t ev[4];
   float last_ms[4];
+  // stage trace of the last fused call (instrumentation only, drc_ctx_last_trace): named events on the streams of the pipelines
+  cudaEvent_t tr_ev[32]; const char* tr_name[32]; int tr_n;
+  // optional debug outputs of the QP solves (drc_ctx_enable_qp_debug): primal / dual vectors in structured order
+  double *dbg_x, *dbg_y;
 };
+static inline void mark(drc_ctx* c, const char* name, cudaStream_t s) {
+  if (!c->timing || c->tr_n >= 32) return;
+  if (!c->tr_ev[c->tr_n] && cudaEventCreate(&c->tr_ev[c->tr_n]) != cudaSuccess) { cudaGetLastError(); return; }
+  c->tr_name[c->tr_n] = name;
+  cudaEventRecord(c->tr_ev[c->tr_n++], s);
+}
 
 static DrcFrame frame_of(const drc_model* m, int fid) {
   DrcFrame f;
@@ -159,6 +170,23 @@ static int join_epa(drc_ctx* c, cudaStream_t s) {
   CU(cudaStreamWaitEvent(s, c->ev_epa, 0));
   return DRC_OK;
 }
+// The EPA pass (side stream) resolves the ~0.1 % of the robots with an overlapping cylinder / box pair; it is a long, nearly empty
+// kernel.  Instead of holding the whole ADMM launch back until it ends, the main launch skips those robots (SolveIO::skip =
+// epa_flag) and a second, small ADMM launch BEHIND the EPA pass on the side stream solves them.  `sio` is the main launch's
+// argument block; the caller's stream waits for ev_epa (recorded here after the small launch) at the end of the call.
+template <class Cfg, bool ID>
+static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask = (1u << Cfg::NC) - 1u, const double* gravity = nullptr,
+                       const Scratch* scp = nullptr);
+template <class Cfg, bool ID>
+static int solve_epa_robots(drc_ctx* c, SolveIO sio, cudaStream_t main, unsigned unit_mask, const double* gravity) {
+  CU(cudaEventRecord(c->ev_build, main));                  // the rest of their QP records (state / QP-build kernel)
+  CU(cudaStreamWaitEvent(c->side, c->ev_build, 0));
+  sio.order = c->epa_list; sio.count = c->epa_count; sio.order_off = nullptr; sio.skip = nullptr; sio.out_ids = nullptr;
+  int rc = launch_admm<Cfg, ID>(c, sio, c->side, unit_mask, gravity, nullptr);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->ev_epa, c->side));
+  return DRC_OK;
+}
 
 // ADMM schedule from the previous tick's iteration counts (k_sched_* in drc_kernels.cuh): c->order = robots by descending
 // count, *c->slow_count = how many of them reached kPrioIters (at most kPrioSlots).  Results do not depend on it.
@@ -176,14 +204,14 @@ static int launch_schedule(drc_ctx* c, int B, cudaStream_t s) {
 
 // io.B = slots to cover; io.order / order_off / out_ids / count select them (see SolveIO)
 template <class Cfg, bool ID>
-static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask = (1u << Cfg::NC) - 1u, const double* gravity = nullptr,
-                       const Scratch* scp = nullptr) {
+static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mask, const double* gravity, const Scratch* scp) {
   io.qp = scp ? scp->qp : c->qp;
   io.c_g = gravity ? gravity : (scp ? scp->c_g : c->c_g);
   io.Bc = scp ? scp->Bc : c->cap;
   const QpOptions o = qp_options(c->prm, unit_mask);
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
   io.iters_hint = c->prev_iters;
+  io.qp_x = c->dbg_x; io.qp_y = c->dbg_y;
   // one instantiation per QP shape (register cap 65536 / (128 * 3) = 168).  The dynamic shared-memory opt-in is a per-device
   // function attribute: set it for the context's device on every launch (cheap) so that contexts on several GPUs of one
   // process all get it.
@@ -194,6 +222,10 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   CU(cudaGetLastError());
   return DRC_OK;
 }
+
+// whole-body (tree-shaped) models behind the generic getters; defined in drc_moma.cu next to their kernel instantiations
+int moma_get_frame_full(drc_ctx* c, int B, int frame, double* pose12, double* J, double* Jdot, double* vel, int layout, cudaStream_t s);
+int moma_get_min_distance(drc_ctx* c, int B, int with_graddot, double* dist, double* grad, double* grad_dot, int* pair, int layout, cudaStream_t s);
 
 static int check_batch(const drc_ctx* c, int B) {
   if (!c) return fail(DRC_E_INVALID, "null context");

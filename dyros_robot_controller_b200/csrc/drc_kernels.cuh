@@ -20,13 +20,16 @@ using namespace drc;
 template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 __global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ DrcFrame frame, const __grid_constant__ JobIO io) {
+#ifndef DRC_SYNTAX_CHECK   // -DDRC_SYNTAX_CHECK: empty kernel bodies, for a host-code syntax pass in seconds (build.py --check)
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < io.B && (!io.count || b < *io.count)) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
+#endif
 }
 
 template <int NV, bool CHAIN, int MINB = 2>
 __global__ void __launch_bounds__(128, MINB) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ CollisionIO io) {
+#ifndef DRC_SYNTAX_CHECK
   // stage the geometry table in shared memory: the GJK pass indexes it with per-thread pair ids
   __shared__ GeomTable G;
   {
@@ -37,6 +40,7 @@ __global__ void __launch_bounds__(128, MINB) k_collision(const __grid_constant__
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < io.B && (!io.count || b < *io.count)) collision_job<NV, CHAIN>(m, G, prm, io, b);
+#endif
 }
 // ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar
 // epa_penetration (drc_geom.h: flood-fill horizon, uncommitted bad expansions, slot policy); the polytope lives in
@@ -171,6 +175,7 @@ constexpr int kEpaWarps = 2;
 template <int NV, bool CHAIN>
 __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                                    const __grid_constant__ CollisionIO io) {
+#ifndef DRC_SYNTAX_CHECK
   __shared__ EpaWarpSmem sm[kEpaWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   EpaWarpSmem& S = sm[warp];
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_c
     if (lane == 0) collision_finish<NV, CHAIN>(m, prm, io, b, best);
     __syncwarp();
   }
+#endif
 }
 
 #ifndef DRC_ADMM_WARPS
@@ -214,6 +220,7 @@ __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_c
 constexpr int kAdmmWarps = DRC_ADMM_WARPS;  // one warp per block: a finished warp frees its slot without waiting for block-mates
 template <class Cfg, bool ID, int MINB>
 __global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
+#ifndef DRC_SYNTAX_CHECK
   extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
   GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,12 +231,17 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_ad
   if (first >= nslot) return;  // no block-level barrier below: idle warps may leave
   int robots[Cfg::NG];
 #pragma unroll
-  for (int g = 0; g < Cfg::NG; ++g) robots[g] = first + g < nslot ? (io.order ? io.order[first + g] : first + g) : -1;
+  for (int g = 0; g < Cfg::NG; ++g) {
+    int r = first + g < nslot ? (io.order ? io.order[first + g] : first + g) : -1;
+    if (r >= 0 && io.skip && io.skip[r]) r = -1;   // its self-collision row is still being computed (EPA pass): solved by the launch behind that pass
+    robots[g] = r;
+  }
   WarpExec<Cfg> w;
   w.sh = sh + warp * Cfg::NG;
   w.lane = lane;
   lane_assign<Cfg>(w.L, lane);
   solve_and_emit<Cfg, ID>(w, robots, io, o);
+#endif
 }
 
 // ---- ADMM schedule.  The iteration count of a QP is not known in advance and spreads from 50 to max_iter (4000):

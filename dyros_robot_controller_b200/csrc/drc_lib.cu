@@ -39,13 +39,13 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     CU(cudaStreamWaitEvent(c->stream, c->ev_in, 0));
     s = c->stream;
   }
-  if (c->timing) cudaEventRecord(c->ev[0], s);
+  if (c->timing) { cudaEventRecord(c->ev[0], s); c->tr_n = 0; mark(c, "start", s); }
   int rc;
   const int qp_stride = id ? QpidCfg<NV>::STRIDE : QpikCfg<NV>::STRIDE;
   const int qp_row_off = (id ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (NV + 1);
   const bool sched = c->prm.schedule_hint != 0 && B >= 64;
   const bool prio = sched && fused && B >= kPrioMinBatch;
-  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; }
+  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; mark(c, "schedule", s); }
 
 #define J(FL, IO, ST) launch_job<NV, CHAIN, FL>(c, fr, IO, ST)
   // QPIK does not read the dynamics (M, M^-1, g, nle of updateState): in fused calls they leave the critical path -- the QP
@@ -67,13 +67,22 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     pio.B = kPrioSlots; pio.ids = c->order; pio.count = c->slow_count;
     bind_scratch(c->prio, pio);
     rc = J(F_STORE, pio, ps); if (rc) return rc;
+    mark(c, "prio_fk", ps);
+    // the QP-build kernel only needs the cached joint placements: it runs NEXT TO the narrow phase on a second high-priority
+    // stream (both are tiny, latency-bound launches here), and the solver waits for both
+    CU(cudaEventRecord(c->ev_prio_fk, ps));
+    CU(cudaStreamWaitEvent(c->prio_side, c->ev_prio_fk, 0));
+    if (c->late_pending) CU(cudaStreamWaitEvent(c->prio_side, c->ev_late, 0));   // x_target / xdot_target still uploading (host entry points)
+    rc = build(pio, c->prio_side); if (rc) return rc;
+    mark(c, "prio_build", c->prio_side);
+    CU(cudaEventRecord(c->ev_prio_build, c->prio_side));
     CollisionIO pc;
     std::memset(&pc, 0, sizeof pc);
     pc.B = kPrioSlots; pc.mode = id ? 2 : 1; pc.qp = c->prio.qp; pc.qp_stride = qp_stride; pc.qp_row_off = qp_row_off;
     pc.count = c->slow_count;
     rc = launch_collision<NV, CHAIN>(c, pc, ps, false, &c->prio); if (rc) return rc;
-    if (c->late_pending) CU(cudaStreamWaitEvent(ps, c->ev_late, 0));   // x_target / xdot_target still uploading (host entry points)
-    rc = build(pio, ps); if (rc) return rc;
+    mark(c, "prio_collision", ps);
+    CU(cudaStreamWaitEvent(ps, c->ev_prio_build, 0));
     SolveIO ps_io;
     std::memset(&ps_io, 0, sizeof ps_io);
     ps_io.B = kPrioSlots; ps_io.out = out; ps_io.sout = lay(layout, NV, B); ps_io.out2 = out2; ps_io.sout2 = ps_io.sout;
@@ -81,42 +90,51 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     rc = id ? launch_admm<QpidCfg<NV>, true>(c, ps_io, ps, (1u << NV) - 1u, nullptr, &c->prio)
             : launch_admm<QpikCfg<NV>, false>(c, ps_io, ps, (1u << NV) - 1u, nullptr, &c->prio);
     if (rc) return rc;
+    mark(c, "prio_admm", ps);
     CU(cudaEventRecord(c->ev_prio, ps));
   }
 
   // ---- main pipeline
   // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; its EPA pass goes to the side stream
-  if (fused) { rc = J(F_STORE, io, s); if (rc) return rc; }
+  if (fused) { rc = J(F_STORE, io, s); if (rc) return rc; mark(c, "fk", s); }
   if (split_dyn) CU(cudaEventRecord(c->ev_store, s));
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp; cio.qp_stride = qp_stride; cio.qp_row_off = qp_row_off;
   rc = launch_collision<NV, CHAIN>(c, cio, s, true);
   if (rc) return rc;
-  if (c->timing) cudaEventRecord(c->ev[1], s);
+  if (c->timing) { cudaEventRecord(c->ev[1], s); mark(c, "collision", s); }
   // stage 2 (next to the EPA pass)
   if (c->late_pending) { CU(cudaStreamWaitEvent(s, c->ev_late, 0)); c->late_pending = false; }
   rc = build(io, s);
   if (rc) return rc;
 #undef J
-  rc = join_epa(c, s);
-  if (rc) return rc;
+  mark(c, "build", s);
   if (c->timing) cudaEventRecord(c->ev[2], s);
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.out = out; sio.sout = lay(layout, NV, B); sio.out2 = out2; sio.sout2 = sio.sout; sio.status = status; sio.iters = iters;
+  // robots whose self-collision row is still in the EPA pass (side stream) are solved by a small launch behind that pass
+  rc = id ? solve_epa_robots<QpidCfg<NV>, true>(c, sio, s, (1u << NV) - 1u, nullptr) : solve_epa_robots<QpikCfg<NV>, false>(c, sio, s, (1u << NV) - 1u, nullptr);
+  if (rc) return rc;
+  sio.skip = c->epa_flag;
   if (sched) sio.order = c->order;
   if (prio) sio.order_off = c->slow_count;   // those robots are solved by the priority pipeline
   rc = id ? launch_admm<QpidCfg<NV>, true>(c, sio, s) : launch_admm<QpikCfg<NV>, false>(c, sio, s);
   if (rc) return rc;
+  mark(c, "admm", s);
   if (split_dyn) {  // enqueued behind the ADMM launch: its blocks are dispatched as the solver's grid drains
     CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_store, 0));
     rc = launch_job<NV, CHAIN, F_DYN | F_FROM_CACHE>(c, fr, io, c->dyn_stream); if (rc) return rc;
+    mark(c, "dynamics", c->dyn_stream);
     CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
     CU(cudaStreamWaitEvent(s, c->ev_dyn, 0));
   }
+  rc = join_epa(c, s);   // the EPA-pending robots' launch on the side stream
+  if (rc) return rc;
+  mark(c, "epa_robots", s);
   if (prio) CU(cudaStreamWaitEvent(s, c->ev_prio, 0));
-  if (c->timing) cudaEventRecord(c->ev[3], s);
+  if (c->timing) { cudaEventRecord(c->ev[3], s); mark(c, "end", s); }
   if (caller != s) {
     CU(cudaEventRecord(c->ev_out, s));
     CU(cudaStreamWaitEvent(caller, c->ev_out, 0));
@@ -241,6 +259,7 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
   CU(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_col, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_build, cudaEventDisableTiming));
   auto dalloc = [&](double** p, size_t cnt) { return cudaMalloc((void**)p, cnt * sizeof(double)); };
   CU(dalloc(&c->c_q, n * B)); CU(dalloc(&c->c_qd, n * B)); CU(dalloc(&c->c_oMi, 12 * n * B));
   CU(dalloc(&c->c_M, n * n * B)); CU(dalloc(&c->c_Minv, n * n * B)); CU(dalloc(&c->c_g, n * B)); CU(dalloc(&c->c_nle, n * B));
@@ -285,6 +304,9 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
     int lo = 0, hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi));
+    CU(cudaStreamCreateWithPriority(&c->prio_side, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&c->ev_prio_fk, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_prio_build, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
@@ -355,6 +377,10 @@ void drc_ctx_destroy(drc_ctx_t* c) {
       for (void* q : ps) if (q) cudaFree(q);
     }
     if (c->prio_stream) { cudaStreamSynchronize(c->prio_stream); cudaStreamDestroy(c->prio_stream); }
+    if (c->prio_side) { cudaStreamSynchronize(c->prio_side); cudaStreamDestroy(c->prio_side); }
+    if (c->ev_prio_fk) cudaEventDestroy(c->ev_prio_fk);
+    if (c->ev_prio_build) cudaEventDestroy(c->ev_prio_build);
+    if (c->ev_build) cudaEventDestroy(c->ev_build);
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
     if (c->ev_prio) cudaEventDestroy(c->ev_prio);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
@@ -369,6 +395,9 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   }
   if (c->stage_i) cudaFree(c->stage_i);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 32; ++i) if (c->tr_ev[i]) cudaEventDestroy(c->tr_ev[i]);
+  if (c->dbg_x) cudaFree(c->dbg_x);
+  if (c->dbg_y) cudaFree(c->dbg_y);
   if (c->ev_col) cudaEventDestroy(c->ev_col);
   if (c->ev_epa) cudaEventDestroy(c->ev_epa);
   if (c->side) cudaStreamDestroy(c->side);
@@ -415,6 +444,7 @@ int drc_ctx_synchronize(drc_ctx_t* c) {
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->side));
   CU(cudaStreamSynchronize(c->prio_stream));
+  CU(cudaStreamSynchronize(c->prio_side));
   CU(cudaStreamSynchronize(c->dyn_stream));
   return DRC_OK;
 }
@@ -431,6 +461,45 @@ int drc_ctx_last_timing(drc_ctx_t* c, float* ms) {
   return DRC_OK;
 }
 long long drc_ctx_launch_count(const drc_ctx_t* c) { return c ? c->launches : 0; }
+int drc_ctx_last_trace(drc_ctx_t* c, int max_marks, float* ms, char* names, int names_len) {
+  if (!c || !ms || !names || names_len <= 0) return fail(DRC_E_INVALID, "null argument");
+  if (!c->timing) return fail(DRC_E_INVALID, "timing is not enabled on this context");
+  std::string all;
+  int n = 0;
+  for (int i = 0; i < c->tr_n && n < max_marks; ++i) {
+    CU(cudaEventSynchronize(c->tr_ev[i]));
+    CU(cudaEventElapsedTime(&ms[n], c->tr_ev[0], c->tr_ev[i]));
+    all += c->tr_name[i]; all += ';';
+    ++n;
+  }
+  std::snprintf(names, (size_t)names_len, "%s", all.c_str());
+  return n;
+}
+int drc_ctx_enable_qp_debug(drc_ctx_t* c, int on) {
+  if (!c) return fail(DRC_E_INVALID, "null context");
+  CU(cudaSetDevice(c->device));
+  if (on && !c->dbg_x) {
+    const int n = c->model->hm.dev.nv;
+    CU(cudaMalloc((void**)&c->dbg_x, (size_t)c->cap * (6 * n + 2) * sizeof(double)));
+    CU(cudaMalloc((void**)&c->dbg_y, (size_t)c->cap * (11 * n + 4) * sizeof(double)));
+  } else if (!on && c->dbg_x) {
+    CU(cudaDeviceSynchronize());
+    cudaFree(c->dbg_x); cudaFree(c->dbg_y);
+    c->dbg_x = c->dbg_y = nullptr;
+  }
+  return DRC_OK;
+}
+int drc_host_get_qp_debug(drc_ctx_t* c, int B, int x_per_robot, int y_per_robot, double* x, double* y) {
+  int rc = check_batch(c, B); if (rc) return rc;
+  if (!c->dbg_x) return fail(DRC_E_INVALID, "QP debug outputs are not enabled on this context");
+  const int n = c->model->hm.dev.nv;
+  if (x_per_robot < 0 || x_per_robot > 6 * n + 2 || y_per_robot < 0 || y_per_robot > 11 * n + 4) return fail(DRC_E_INVALID, "debug vector size out of range");
+  CU(cudaSetDevice(c->device));
+  CU(cudaDeviceSynchronize());
+  if (x) CU(cudaMemcpy(x, c->dbg_x, (size_t)B * x_per_robot * sizeof(double), cudaMemcpyDeviceToHost));
+  if (y) CU(cudaMemcpy(y, c->dbg_y, (size_t)B * y_per_robot * sizeof(double), cudaMemcpyDeviceToHost));
+  return DRC_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ device entry points
 int drc_batch_update_state(drc_ctx_t* c, int B, const double* q, const double* qdot, int layout, void* stream) {
@@ -448,6 +517,7 @@ int drc_batch_get_frame(drc_ctx_t* c, int B, int frame, double* pose12, double* 
   int rc = check_batch(c, B); if (rc) return rc;
   rc = check_frame(c, frame); if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  if (c->model->hm.dev.drive_type != kNoBase) return moma_get_frame_full(c, B, frame, pose12, J, Jdot, vel, layout, pick(c, stream));
   const int n = c->model->hm.dev.nv;
   JobIO io; std::memset(&io, 0, sizeof io);
   io.B = B; bind_cache(c, io);
@@ -493,6 +563,7 @@ int drc_batch_get_manipulability(drc_ctx_t* c, int B, int frame, int with_graddo
 int drc_batch_get_min_distance(drc_ctx_t* c, int B, int with_graddot, double* dist, double* grad, double* grad_dot, int* pair, int layout, void* stream) {
   int rc = check_batch(c, B); if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  if (c->model->hm.dev.drive_type != kNoBase) return moma_get_min_distance(c, B, with_graddot, dist, grad, grad_dot, pair, layout, pick(c, stream));
   const int n = c->model->hm.dev.nv;
   CollisionIO io; std::memset(&io, 0, sizeof io);
   io.B = B; io.mode = 0; io.dist = dist; io.grad = grad; io.sgrad = lay(layout, n, B);

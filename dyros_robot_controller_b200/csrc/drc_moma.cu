@@ -69,17 +69,41 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   // stage 2 (next to the EPA pass): whole-body state update and QP record except the self-collision row
   rc = id ? launch_job<NV, false, K_ID, W>(c, fr, io, s) : launch_job<NV, false, K_IK, W>(c, fr, io, s);
   if (rc) return rc;
-  rc = join_epa(c, s);
-  if (rc) return rc;
   if (c->timing) cudaEventRecord(c->ev[2], s);
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.out = out; sio.sout = lay(layout, ACT, B); sio.out2 = out2; sio.sout2 = sio.sout; sio.status = status; sio.iters = iters;
-  if (sched) sio.order = c->order;
   const unsigned mani_mask = ((1u << MANI) - 1u) << d.act_mani_start;   // CBF unit rows exist on manipulator joints only
+  // robots whose self-collision row is still in the EPA pass are solved by a small launch behind that pass (side stream)
+  rc = id ? solve_epa_robots<MomaIdCfg<ACT>, true>(c, sio, s, mani_mask, c->c_gact) : solve_epa_robots<MomaIkCfg<ACT>, false>(c, sio, s, mani_mask, c->c_gact);
+  if (rc) return rc;
+  sio.skip = c->epa_flag;
+  if (sched) sio.order = c->order;
   rc = id ? launch_admm<MomaIdCfg<ACT>, true>(c, sio, s, mani_mask, c->c_gact) : launch_admm<MomaIkCfg<ACT>, false>(c, sio, s, mani_mask, c->c_gact);
+  if (rc) return rc;
+  rc = join_epa(c, s);
   if (c->timing) cudaEventRecord(c->ev[3], s);
   return rc;
+}
+
+// Full-dof getters of a whole-body model (MobileManipulator::RobotData inherits Manipulator::RobotData's getJacobian /
+// getJacobianTimeVariation / getPose / getVelocity / getMinDistance, mobile_manipulator/robot_data.h:42): the generic entry points
+// drc_batch_get_frame / drc_batch_get_min_distance forward here when the model has a mobile base.  J, Jdot are 6 x dof.
+int moma_get_frame_full(drc_ctx* c, int B, int frame, double* pose12, double* J, double* Jdot, double* vel, int layout, cudaStream_t s) {
+  const DrcModelDev& d = c->model->hm.dev;
+  JobIO io; std::memset(&io, 0, sizeof io);
+  io.B = B; bind_cache(c, io);
+  io.pose = pose12; io.spose = lay(layout, 12, B); io.J = J; io.sJ = lay(layout, 6 * d.nv, B); io.Jdot = Jdot; io.sJd = io.sJ;
+  io.vel = vel; io.svel = lay(layout, 6, B);
+  const DrcFrame fr = frame_of(c->model, frame);
+  DRC_DISPATCH_MOMA(d, return (launch_job<NV, false, F_FROM_CACHE | F_FRAME_OUT>(c, fr, io, s)));
+}
+int moma_get_min_distance(drc_ctx* c, int B, int with_graddot, double* dist, double* grad, double* grad_dot, int* pair, int layout, cudaStream_t s) {
+  const DrcModelDev& d = c->model->hm.dev;
+  CollisionIO io; std::memset(&io, 0, sizeof io);
+  io.B = B; io.mode = 0; io.dist = dist; io.grad = grad; io.sgrad = lay(layout, d.nv, B);
+  io.grad_dot = with_graddot ? grad_dot : nullptr; io.sgd = io.sgrad; io.pair_out = pair;
+  DRC_DISPATCH_MOMA(d, return (launch_collision<NV, false>(c, io, s)));
 }
 
 extern "C" {

@@ -88,12 +88,19 @@ class RobotController:
     def move_joint_velocity_cubic(self, q_target, qdot_target, q_init, qdot_init, current_time, init_time, duration):
         return _cubic(current_time, init_time, init_time + duration, q_init, q_target, qdot_init, qdot_target)[1]
 
-    def move_joint_torque_step(self, q_target, qdot_target=None):
-        if qdot_target is None:     # moveJointTorqueStep(qddot_target): M qddot + g  (robot_controller.cpp:108-113)
-            qdd = np.asarray(q_target, np.float64)
+    def move_joint_torque_step(self, q_target=None, qdot_target=None, qddot_target=None):
+        """the reference wrapper's three-keyword form (drc/manipulator/robot_controller.py:161-184): qddot_target -> M qddot + g
+        (robot_controller.cpp:108-113); (q_target, qdot_target) -> PD acceleration first (:115-125).  A single positional
+        argument is taken as qddot_target, like the C++ overload."""
+        if qddot_target is None and qdot_target is None and q_target is not None:
+            qddot_target, q_target = q_target, None
+        if qddot_target is not None:
+            qdd = np.asarray(qddot_target, np.float64)
             M, g = self._robot_data.get_mass_matrix(), self._robot_data.get_gravity()
             return np.einsum("...ij,...j->...i", M, qdd) + g
-        return self._sq(self._ctx.joint_torque_step(q_target, qdot_target))
+        if q_target is not None and qdot_target is not None:
+            return self._sq(self._ctx.joint_torque_step(q_target, qdot_target))
+        return None
 
     def move_joint_torque_cubic(self, q_target, qdot_target, q_init, qdot_init, current_time, init_time, duration):
         q_des, qd_des = _cubic(current_time, init_time, init_time + duration, q_init, q_target, qdot_init, qdot_target)

@@ -30,8 +30,8 @@ class RobotData:
             self._scratch = engine.Context(self._model, self._max_batch, self._device)
         return self._scratch
 
-    def _squeeze(self, a):
-        return a[0] if self._single else a
+    def _squeeze(self, a, single=None):
+        return a[0] if (self._single if single is None else single) else a
 
     def _link(self, ctx, link_name: str):
         fid = self._model.frame_id(link_name)
@@ -65,8 +65,10 @@ class RobotData:
     def get_joint_velocity_limit(self) -> Tuple[np.ndarray, np.ndarray]:
         return -self._model.v_limit, self._model.v_limit.copy()
 
-    def _dyn(self, ctx, key):
-        return self._squeeze(ctx.get_dynamics(want=(key,))[key])
+    def _dyn(self, ctx, key, single=None):
+        if isinstance(ctx, tuple):      # (scratch context, single) from _at(): stateless twins
+            ctx, single = ctx
+        return self._squeeze(ctx.get_dynamics(want=(key,))[key], single)
 
     def get_mass_matrix(self) -> np.ndarray:
         return self._dyn(self._ctx, "M")
@@ -83,14 +85,16 @@ class RobotData:
     def get_nonlinear_effects(self) -> np.ndarray:
         return self._dyn(self._ctx, "nle")
 
-    def _frame(self, ctx, link_name, key, neutral):
+    def _frame(self, ctx, link_name, key, neutral, single=None):
+        if isinstance(ctx, tuple):
+            ctx, single = ctx
         fid = self._link(ctx, link_name)
         if fid < 0:
             return neutral
         v = ctx.get_frame(fid, want=(key,))[key]
         if key == "pose":
             v = engine.pose44(v)
-        return self._squeeze(v)
+        return self._squeeze(v, single)
 
     def get_pose(self, link_name: str) -> np.ndarray:
         return self._frame(self._ctx, link_name, "pose", np.eye(4))
@@ -104,37 +108,41 @@ class RobotData:
     def get_velocity(self, link_name: str) -> np.ndarray:
         return self._frame(self._ctx, link_name, "vel", np.zeros(6))
 
-    def _min_distance(self, ctx, with_grad, with_graddot) -> MinDistResult:
+    def _min_distance(self, ctx, with_grad, with_graddot, single=None) -> MinDistResult:
+        if isinstance(ctx, tuple):
+            ctx, single = ctx
         d, g, gd, _ = ctx.get_min_distance(with_graddot=bool(with_graddot))
-        n = self._model.dof
         z = np.zeros_like(g)
-        r = MinDistResult(self._squeeze(d), self._squeeze(g if (with_grad or with_graddot) else z),
-                          self._squeeze(gd if with_graddot else z))
+        r = MinDistResult(self._squeeze(d, single), self._squeeze(g if (with_grad or with_graddot) else z, single),
+                          self._squeeze(gd if with_graddot else z, single))
         return r
 
     def get_min_distance(self, with_grad: bool, with_graddot: bool, verbose: bool = False) -> MinDistResult:
         return self._min_distance(self._ctx, with_grad, with_graddot)
 
-    def _manipulability(self, ctx, with_grad, with_graddot, link_name) -> ManipulabilityResult:
+    def _manipulability(self, ctx, with_grad, with_graddot, link_name, single=None) -> ManipulabilityResult:
+        if isinstance(ctx, tuple):
+            ctx, single = ctx
         fid = self._link(ctx, link_name)
         n = self._model.dof
         if fid < 0:
             return ManipulabilityResult(0.0, np.zeros(n), np.zeros(n))
         m, g, gd = ctx.get_manipulability(fid, with_graddot=bool(with_graddot))
         z = np.zeros_like(g)
-        return ManipulabilityResult(self._squeeze(m), self._squeeze(g if (with_grad or with_graddot) else z),
-                                    self._squeeze(gd if with_graddot else z))
+        return ManipulabilityResult(self._squeeze(m, single), self._squeeze(g if (with_grad or with_graddot) else z, single),
+                                    self._squeeze(gd if with_graddot else z, single))
 
     def get_manipulability(self, with_grad: bool, with_graddot: bool, link_name: str) -> ManipulabilityResult:
         return self._manipulability(self._ctx, with_grad, with_graddot, link_name)
 
     # ---- stateless twins (robot_data.cpp:128-374): evaluate at (q, qdot) without touching the cache
     def _at(self, q, qdot=None):
+        """(scratch context holding the state (q, qdot), single-robot flag of THIS call): the cached getters' flag, set by
+        update_state only, is left alone."""
         q = np.asarray(q, np.float64)
-        self._single = q.ndim == 1
         s = self._stateless()
         s.update_state(q, np.zeros_like(q) if qdot is None else qdot)
-        return s
+        return s, q.ndim == 1
 
     def compute_mass_matrix(self, q) -> np.ndarray:
         return self._dyn(self._at(q), "M")

@@ -54,6 +54,10 @@ class KinematicParam:
             self.wheel_offset = float(wheel_offset)
             self.base2wheel_positions = [np.asarray(p, np.float64) for p in base2wheel_positions]
 
+    def cpp(self):
+        """the reference returns the wrapped extension-module struct here (drc/type_define.py:53-54); this record IS that struct"""
+        return self
+
     def as_dict(self) -> dict:
         return dict(type=int(self.type), wheel_radius=self.wheel_radius, base_width=self.base_width,
                     wheel_offset=self.wheel_offset, max_lin_speed=self.max_lin_speed, max_ang_speed=self.max_ang_speed,
@@ -68,6 +72,9 @@ class JointIndex:
     def __init__(self, virtual_start: int, mani_start: int, mobi_start: int) -> None:
         self.virtual_start, self.mani_start, self.mobi_start = int(virtual_start), int(mani_start), int(mobi_start)
 
+    def cpp(self):
+        return self
+
     def as_dict(self) -> dict:
         return dict(virtual_start=self.virtual_start, mani_start=self.mani_start, mobi_start=self.mobi_start)
 
@@ -77,6 +84,9 @@ class ActuatorIndex:
 
     def __init__(self, mani_start: int, mobi_start: int) -> None:
         self.mani_start, self.mobi_start = int(mani_start), int(mobi_start)
+
+    def cpp(self):
+        return self
 
     def as_dict(self) -> dict:
         return dict(mani_start=self.mani_start, mobi_start=self.mobi_start)

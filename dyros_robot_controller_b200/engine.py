@@ -231,6 +231,37 @@ class Context:
         check(lib().drc_ctx_last_timing(self._h, ms), "drc_ctx_last_timing")
         return dict(collision_ms=ms[0], build_ms=ms[1], admm_ms=ms[2], total_ms=ms[3])
 
+    def last_trace(self):
+        """[(name, ms since the start of the call)] of the last fused cycle call (main and priority pipeline marks)."""
+        ms = (C.c_float * 32)()
+        names = C.create_string_buffer(1024)
+        n = lib().drc_ctx_last_trace(self._h, 32, ms, names, 1024)
+        if n < 0:
+            check(n, "drc_ctx_last_trace")
+        return list(zip(names.value.decode().split(";")[:n], [float(ms[i]) for i in range(n)]))
+
+    # QP shapes (NC core variables, KU unit bundles per variable, NR dense + equality rows) of the four formulations
+    def _qp_shape(self, kind: str):
+        moma = kind.startswith("moma")
+        nc = self.model.actuated_dof if moma else self.n
+        ident = kind.endswith("id")
+        return nc, (4 if ident else 2), (2 + nc if ident else 2)
+
+    def enable_qp_debug(self, on=True):
+        """keep the primal / dual vectors of every QP solve on the device (test instrumentation, see qp_debug)."""
+        check(lib().drc_ctx_enable_qp_debug(self._h, int(on)), "drc_ctx_enable_qp_debug")
+
+    def qp_debug(self, kind: str, B: Optional[int] = None):
+        """primal x and unscaled dual y of the last QP call of `kind` ("ik", "id", "moma_ik", "moma_id") in STRUCTURED order:
+        x = [core (NC) | unit slacks (KU, NC) | row singletons (NR)],
+        y = [core bound rows (NC) | unit rows (KU, NC) | unit-slack bound rows (KU, NC) | rows (NR) | row-singleton bound rows (NR)]."""
+        B = self._B if B is None else B
+        nc, ku, nr = self._qp_shape(kind)
+        nx, ny = nc * (1 + ku) + nr, nc * (1 + 2 * ku) + 2 * nr
+        x, y = np.zeros((B, nx)), np.zeros((B, ny))
+        check(lib().drc_host_get_qp_debug(self._h, B, nx, ny, self._p(x), self._p(y)), "drc_host_get_qp_debug")
+        return dict(x=x, y=y, nc=nc, ku=ku, nr=nr)
+
     @property
     def launch_count(self) -> int:
         return int(lib().drc_ctx_launch_count(self._h))

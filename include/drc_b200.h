@@ -273,6 +273,16 @@ int drc_host_mobile_ik(drc_mobile_t* h, int B, const double* wheel_pos, const do
  * it on a side stream)  [2] ADMM solve  [3] total; requires drc_ctx_enable_timing(c,1) */
 int drc_ctx_enable_timing(drc_ctx_t* c, int on);
 int drc_ctx_last_timing(drc_ctx_t* c, float* ms4);
+/* stage trace of the LAST fused cycle call: up to max_marks named events (names joined by ';'), times in ms relative to the first
+ * mark, recorded on the streams of the main and the priority pipeline; returns the number of marks; requires timing enabled */
+int drc_ctx_last_trace(drc_ctx_t* c, int max_marks, float* ms, char* names, int names_len);
+/* debug outputs of the QP solves (test instrumentation for the active-set gate; the reference exposes nothing comparable):
+ * after enabling, every QP call also stores, per robot, the primal vector [core x (NC) | unit slacks (KU*NC) | row singletons (NR)]
+ * and the UNSCALED dual vector [core bound rows (NC) | unit rows (KU*NC) | unit-slack bound rows (KU*NC) | dense/equality rows (NR)
+ * | row-singleton bound rows (NR)] of OSQP's final iterate (y = E y_scaled / c); rows that do not exist in a formulation hold 0.
+ * NC = core variables (dof / actuated dof), KU = 2 (QPIK) or 4 (QPID), NR = 2 (QPIK) or 2 + NC (QPID). */
+int drc_ctx_enable_qp_debug(drc_ctx_t* c, int on);
+int drc_host_get_qp_debug(drc_ctx_t* c, int B, int x_per_robot, int y_per_robot, double* x, double* y);
 /* number of kernels this library launched on the context since creation */
 long long drc_ctx_launch_count(const drc_ctx_t* c);
 /* measured FP64 FMA throughput of the device (TFLOP/s) -- the roofline denominator of this fp64 path */

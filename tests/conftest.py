@@ -95,3 +95,38 @@ def moma_workload(model_like, w, B, seed):
     q_t[:, 0:2] += 0.05 * rng.normal(size=(B, 2))
     xdot_t = 0.05 * rng.normal(size=(B, 6))
     return q, qd, q_t, xdot_t
+
+
+def struct_to_ref(kind, dbg, n_mani=None, am=0):
+    """Map the product's structured primal / dual vectors (Context.qp_debug) to the reference's QP order
+    (x as laid out by the QP classes, rows = [bounds; inequalities; equalities], QP_base.h:204-226).
+
+    kind "ik":      x = [qdot s_qmin s_qmax s_sing s_col]                          (QP_IK.cpp:12-34)
+    kind "id":      x = [qddot tau s_q- s_q+ s_v- s_v+ s_sing s_col]               (QP_ID.cpp:12-65)
+    kind "moma_ik": x = eta; rows = [free bounds (act); qmin, qmax (mani); sing; col]   (mobile_manipulator/QP_IK.cpp:14-28)
+    kind "moma_id": x = [etadot tau]; rows = [q-, q+, v-, v+ (mani); sing; col; dynamics (act)]   (QP_ID.cpp:14-36)
+    n_mani / am: manipulator dof and its first actuated index (whole-body QPs)."""
+    x, y, nc, ku, nr = dbg["x"], dbg["y"], dbg["nc"], dbg["ku"], dbg["nr"]
+    xc, xs, xr = x[:, :nc], x[:, nc:nc * (1 + ku)].reshape(-1, ku, nc), x[:, nc * (1 + ku):]
+    yb = y[:, :nc]
+    yu = y[:, nc:nc * (1 + ku)].reshape(-1, ku, nc)
+    ysb = y[:, nc * (1 + ku):nc * (1 + 2 * ku)].reshape(-1, ku, nc)
+    yr = y[:, nc * (1 + 2 * ku):nc * (1 + 2 * ku) + nr]
+    yrb = y[:, nc * (1 + 2 * ku) + nr:]
+    B = x.shape[0]
+    if kind == "ik":
+        xr_ = np.concatenate([xc, xs.reshape(B, -1), xr], axis=1)
+        yr_ = np.concatenate([yb, ysb.reshape(B, -1), yrb, yu.reshape(B, -1), yr], axis=1)
+    elif kind == "id":
+        tau, s2 = xr[:, 2:], xr[:, :2]
+        xr_ = np.concatenate([xc, tau, xs.reshape(B, -1), s2], axis=1)
+        yr_ = np.concatenate([yb, yrb[:, 2:], ysb.reshape(B, -1), yrb[:, :2], yu.reshape(B, -1), yr[:, :2], yr[:, 2:]], axis=1)
+    elif kind == "moma_ik":
+        m = n_mani
+        xr_ = xc
+        yr_ = np.concatenate([yb, yu[:, :, am:am + m].reshape(B, -1), yr], axis=1)
+    else:
+        m = n_mani
+        xr_ = np.concatenate([xc, xr[:, 2:]], axis=1)
+        yr_ = np.concatenate([yu[:, :, am:am + m].reshape(B, -1), yr[:, :2], yr[:, 2:]], axis=1)
+    return xr_, yr_

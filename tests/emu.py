@@ -121,6 +121,20 @@ class Emu:
             o["records"] = rec
         return o
 
+    def cycle_xy(self, mode, q, qd, x_target, xdot_target, frame):
+        """cycle() plus the dual vector: returns the same dictionary as engine.Context.qp_debug next to out / status / iters."""
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        xt = None if x_target is None else _c(x_target).reshape(B, 12)
+        xd = _c(xdot_target).reshape(B, 6)
+        ku, nr = (2, 2) if mode < 2 else (4, 2 + n)
+        o = dict(out=np.zeros((B, n)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
+                 x=np.zeros((B, n * (1 + ku) + nr)), y=np.zeros((B, n * (1 + 2 * ku) + 2 * nr)), nc=n, ku=ku, nr=nr)
+        rc = lib().emu_cycle_xy(self.h, C.c_int(mode), C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), _d(o["out"]),
+                                _i(o["status"]), _i(o["iters"]), _d(o["x"]), _d(o["y"]))
+        assert rc == 0
+        return o
+
     def taskspace(self, mode, q, qd, x_target, xdot_target, frame, aux=None, aux2=None):
         q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
         B, n = q.shape

@@ -193,7 +193,7 @@ int emu_min_distance(EmuHandle* h, int B, const double* q, const double* qd, dou
 }  // extern "C"
 template <int NV>
 static int emu_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
-              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records) {
+              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records, double* qp_y) {
   const int n = h->hm.dev.nv;
   const DrcFrame fr = make_frame(h->hm, frame_id);
   Cache c(n, B);
@@ -221,7 +221,7 @@ static int emu_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.qp = rec.data(); sio.out = out; sio.sout = aos(n); sio.status = status; sio.iters = iters;
-  sio.c_g = c.g.data(); sio.Bc = B; sio.qp_x = qp_x;
+  sio.c_g = c.g.data(); sio.Bc = B; sio.qp_x = qp_x; sio.qp_y = qp_y;
   if (ID) run_solve<QpidCfg<NV>, true>(h, sio, (1u << NV) - 1u);
   else run_solve<QpikCfg<NV>, false>(h, sio, (1u << NV) - 1u);
   return 0;
@@ -230,8 +230,16 @@ extern "C" {
 int emu_cycle(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
               const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records) {
   if (!h->hm.chain) return -1;
-  if (h->hm.dev.nv == 7) return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records);
-  if (h->hm.dev.nv == 6) return emu_cycle_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records);
+  if (h->hm.dev.nv == 7) return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records, nullptr);
+  if (h->hm.dev.nv == 6) return emu_cycle_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, qp_records, nullptr);
+  return -1;
+}
+// same, plus the unscaled dual vector in structured order (SolveIO::qp_y)
+int emu_cycle_xy(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                 const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_y) {
+  if (!h->hm.chain) return -1;
+  if (h->hm.dev.nv == 7) return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, nullptr, qp_y);
+  if (h->hm.dev.nv == 6) return emu_cycle_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, nullptr, qp_y);
   return -1;
 }
 int emu_qp_stride(int mode) { return mode >= 2 ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE; }  // FR3 records

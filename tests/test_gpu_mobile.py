@@ -180,7 +180,9 @@ def test_caster_moma_reference_api_mirror(pcv):
     f = o.frame_id(LINK)
     q, qd, q_t, xd = moma_workload(o.model, o.w, 16, 85)
     x_t = o.update_state(q_t, qd, f)["pose"]
+    o.set_task_gains(np.full(6, 400.0), np.full(6, 40.0))   # MobileManipulator::RobotController defaults (robot_controller.cpp:15-16)
     ref = o.moma_cycle(1, q, qd, x_t, xd, f)
+    o.set_task_gains(np.full(6, 100.0), np.full(6, 20.0))
     rd.update_state(q[0, :3], q[0, 3:7], q[0, 7:], qd[0, :3], qd[0, 3:7], qd[0, 7:])
     Jm, bv = o.mobile_state(q[0:1, 3:7], qd[0:1, 3:7])
     assert rd.get_FK_jacobian().shape == (3, 4) and rel(rd.get_FK_jacobian(), Jm[0]) < 1e-12

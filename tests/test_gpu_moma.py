@@ -101,26 +101,80 @@ def test_moma_reference_api_mirror(rig):
     qd = consistent(o, q, qd)
     w = o.w
     x_t = o.update_state(q_t, qd, f)["pose"]
-    ref = o.moma_cycle(1, q, qd, x_t, xd, f)
+    # the reference's MobileManipulator controller defaults to task gains 400 / 40 (mobile_manipulator/robot_controller.cpp:15-16)
+    o.set_task_gains(np.full(6, 400.0), np.full(6, 40.0))
+    try:
+        ref = o.moma_cycle(1, q, qd, x_t, xd, f)
+        ref3 = o.moma_cycle(3, q, qd, x_t, xd, f)
+    finally:
+        o.set_task_gains(np.full(6, 100.0), np.full(6, 20.0))
     # one robot, reference shapes
     assert rd.update_state(q[0, :3], q[0, 3:3 + w], q[0, 3 + w:], qd[0, :3], qd[0, 3:3 + w], qd[0, 3 + w:]) is True
     assert rd.get_pose(LINK).shape == (4, 4) and rd.get_jacobian_actuated(LINK).shape == (6, o.act)
     assert rd.get_mass_matrix_actuated().shape == (o.act, o.act) and rd.get_gravity_actuated().shape == (o.act,)
-    assert np.abs(rd.get_base_vel() - rd.get_FK_jacobian() @ qd[0, 3:3 + w]).max() < 1e-14
+    assert np.abs(rd.get_mobile_base_vel() - rd.get_mobile_FK_jacobian() @ qd[0, 3:3 + w]).max() < 1e-14
     mob, mani = rc.QPIK_step(c_oracle.pose44(x_t[0]), xd[0], LINK)
     assert mob.shape == (w,) and mani.shape == (7,)
     assert np.abs(np.concatenate([mob, mani]) - ref["out"][0]).max() < 1e-4
+    # full-dof getters inherited from Manipulator::RobotData (mobile_manipulator/robot_data.h:42) and the selection matrix
+    full, st = o.update_state(q[:1], qd[:1], f), o.moma_update_state(q[:1], qd[:1], f)
+    n = o.nv
+    assert rd.get_jacobian(LINK).shape == (6, n) and rel(rd.get_jacobian(LINK), full["J"][0]) < 1e-12
+    assert rel(rd.get_jacobian_time_variation(LINK), full["Jdot"][0]) < 1e-11
+    assert rel(rd.get_mass_matrix(), full["M"][0]) < 1e-9 and rel(rd.get_gravity(), full["g"][0]) < 1e-9
+    assert rel(rd.get_nonlinear_effects(), full["nle"][0]) < 1e-9 and rel(rd.get_coriolis(), full["nle"][0] - full["g"][0]) < 1e-8
+    # (PinvCOD with the reference's 1e-6 rank threshold, robot_data.cpp:118: the 14-dof model's M is numerically rank deficient,
+    # so M^-1 M = I is NOT expected; the oracle applies the same rule)
+    assert rel(rd.get_mass_matrix_inv(), full["Minv"][0]) < 1e-6
+    S = rd.get_selection_matrix()
+    assert S.shape == (n, o.act) and np.abs(S - st["S"][0]).max() < 1e-12
+    assert np.abs(rd.get_jacobian_actuated(LINK) - rd.get_jacobian(LINK) @ S).max() < 1e-10      # J~ = J S (robot_data.cpp:407-410)
+    md, mref = rd.get_min_distance(True, True), o.min_distance(q[:1], qd[:1], with_graddot=True)
+    assert abs(md.distance - mref["d"][0]) < 1e-8 and md.grad.shape == (n,) and np.abs(md.grad - mref["grad"][0]).max() < 1e-4
+    lo, hi = rd.get_joint_position_limit()
+    assert lo.shape == (n,) and np.abs(rd.get_manipulator_joint_position() - q[0, 3 + w:]).max() == 0
+    assert np.abs(rd.get_virtual_joint_velocity() - qd[0, :3]).max() == 0 and np.abs(rd.get_mobile_joint_position() - q[0, 3:3 + w]).max() == 0
+    # stateless twins: same values as the cached getters at the same state, cache untouched
+    args = (q[1, :3], q[1, 3:3 + w], q[1, 3 + w:])
+    vargs = (qd[1, :3], qd[1, 3:3 + w], qd[1, 3 + w:])
+    full1 = o.update_state(q[1:2], qd[1:2], f)
+    assert rel(rd.compute_mass_matrix(*args), full1["M"][0]) < 1e-9 and rel(rd.compute_gravity(*args), full1["g"][0]) < 1e-9
+    assert rel(rd.compute_nonlinear_effects(*args, *vargs), full1["nle"][0]) < 1e-9
+    assert rel(rd.compute_jacobian(*args, LINK), full1["J"][0]) < 1e-12
+    assert rel(rd.compute_jacobian_time_variation(*args, *vargs, LINK), full1["Jdot"][0]) < 1e-11
+    assert np.abs(rd.compute_pose(*args, LINK)[:3] - full1["pose"][0].reshape(3, 4)).max() < 1e-12
+    S1 = rd.compute_selection_matrix(q[1, :3], q[1, 3:3 + w])
+    assert np.abs(S1 - o.moma_update_state(q[1:2], qd[1:2], f)["S"][0]).max() < 1e-12
+    # the reference's actuated twins evaluate at q_virtual = 0 and multiply by S(q_virtual) (robot_data.cpp:185-232, 382-405)
+    q0 = q[1:2].copy(); q0[:, :3] = 0
+    f0 = o.update_state(q0, np.zeros_like(q0), f)
+    assert rel(rd.compute_jacobian_actuated(*args, LINK), f0["J"][0] @ S1) < 1e-11
+    assert rel(rd.compute_mass_matrix_actuated(*args), S1.T @ f0["M"][0] @ S1) < 1e-9
+    assert rel(rd.compute_gravity_actuated(*args), S1.T @ f0["g"][0]) < 1e-9
+    mm = rd.compute_manipulability(q[1, 3 + w:], qd[1, 3 + w:], True, True, LINK)
+    assert abs(mm.manipulability - o.moma_update_state(q[1:2], qd[1:2], f)["mani"][0]) < 1e-11 and mm.grad.shape == (7,)
+    assert np.abs(rd.get_pose(LINK)[:3] - full["pose"][0].reshape(3, 4)).max() < 1e-12            # cache still holds robot 0
+    # manipulator joint-space helpers (robot_controller.cpp:78-145): M_mani qddot + g_mani with the PD acceleration
+    ms = d["joint_idx"]["mani_start"]
+    qt, qdt = q[0, 3 + w:] + 0.05, 0.5 * qd[0, 3 + w:]
+    acc = 400.0 * (qt - q[0, 3 + w:]) + 40.0 * (qdt - qd[0, 3 + w:])
+    tau_ref = full["M"][0][ms:ms + 7, ms:ms + 7] @ acc + full["g"][0][ms:ms + 7]
+    assert rel(rc.move_manipulator_joint_torque_step(qt, qdt), tau_ref) < 1e-9
+    assert rel(rc.move_manipulator_joint_torque_step(qddot_mani_target=acc), tau_ref) < 1e-9
+    assert np.abs(rc.move_manipulator_joint_position_cubic(qt, qdt, q[0, 3 + w:], qd[0, 3 + w:], 2.0, 0.0, 1.0) - qt).max() == 0
+    with pytest.raises(RuntimeError):
+        rc.set_manipulator_joint_gain(np.ones(3), np.ones(7))
     # batch
     rd.update_state(q[:, :3], q[:, 3:3 + w], q[:, 3 + w:], qd[:, :3], qd[:, 3:3 + w], qd[:, 3 + w:])
     mob, mani = rc.QPIK_step(c_oracle.pose44(x_t), xd, LINK)
     same = rc.last_iters == ref["iters"]
     assert same.mean() > 0.9 and np.abs(np.concatenate([mob, mani], axis=1) - ref["out"])[same].max() < 1e-4
-    ref3 = o.moma_cycle(3, q, qd, x_t, xd, f)
     acc, tau = rc.QPID_step(c_oracle.pose44(x_t), xd, LINK)
     same = rc.last_iters == ref3["iters"]
     assert acc.shape == (32, w) and tau.shape == (32, 7)
     assert np.abs(tau - ref3["out"][:, w:])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out"]).max())
     assert np.abs(acc - ref3["out2"][:, :w])[same].max() < 1e-4 * max(1.0, np.abs(ref3["out2"]).max())
+    assert rd.get_jacobian(LINK).shape == (32, 6, n) and rd.get_selection_matrix().shape == (32, n, o.act)
 
 
 def test_moma_full_size_properties(rig):

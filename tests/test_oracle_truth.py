@@ -203,14 +203,18 @@ def test_qp_optimum_against_scipy_and_kkt(oracle):
             cons = [dict(type="ineq", fun=lambda x: (A @ x - l)[fin_l], jac=lambda x: A[fin_l]),
                     dict(type="ineq", fun=lambda x: (u - A @ x)[fin_u], jac=lambda x: -A[fin_u])]
             r = minimize(obj, ref["x"][b], jac=lambda x: P @ x + qv, constraints=cons, method="SLSQP", options=dict(ftol=1e-14, maxiter=500))
-            if r.success:
-                slsqp_gap.append(obj(r.x) - obj(xs))
-                # (SLSQP itself stops ~1e-2 short in qdot on these slack-weight-1000 problems: only its OBJECTIVE is used)
-                assert obj(r.x) >= obj(xs) - 1e-6 * (1.0 + abs(obj(xs)))
+            # SLSQP ends ~1e-6 infeasible on these slack-weight-1000 problems ("positive directional derivative"): by weak duality
+            # any point x satisfies obj(x) >= obj* - |y*|_1 * infeasibility(x), so it must not beat the certified optimum by more
+            Axr = A @ r.x
+            infeas = max((l - Axr).max(), (Axr - u).max(), 0.0)
+            if infeas < 1e-4:
+                slsqp_gap.append(np.abs(r.x[:7] - xs[:7]).max())
+                assert obj(r.x) >= obj(xs) - np.abs(ys).sum() * infeas - 1e-6 * (1.0 + abs(obj(xs)))
     dist_x, agree = np.array(dist_x), np.array(agree)
     print(f"QP truth over {len(dist_x)} QPs: |qdot_osqp - qdot_opt| median {np.median(dist_x):.2e}, p99 {np.quantile(dist_x, 0.99):.2e}, "
           f"max {dist_x.max():.2e}; active-set agreement of the eps=1e-3 iterate with the optimum: mean {agree.mean():.4f}, "
-          f"identical for {np.mean(agree == 1.0):.3f} of the QPs; mean active rows {np.mean(n_act):.1f}; SLSQP checked {len(slsqp_gap)}")
+          f"identical for {np.mean(agree == 1.0):.3f} of the QPs; mean active rows {np.mean(n_act):.1f}; SLSQP checked {len(slsqp_gap)} "
+          f"(median |qdot_slsqp - qdot_opt| {np.median(slsqp_gap):.1e})")
     assert len(dist_x) >= 950 and len(slsqp_gap) >= 80
     # OSQP at eps 1e-3 is OSQP-accurate, not exact: bounded distance, mostly the same active set
     assert np.median(dist_x) < 5e-2 and agree.mean() > 0.97

@@ -1,0 +1,32 @@
+#!/usr/bin/env python3
+"""Writes tests/golden/ref_api_surface.json: the public methods (name + positional argument names) of every class of the
+reference's Python package `drc` (/root/reference/drc/**/*.py), read with `ast` -- nothing is imported or executed.
+tests/test_api_surface_cpu.py compares the mirror package dyros_robot_controller_b200.drc with this list, so the fixture travels to
+machines that do not have the reference tree."""
+import ast
+import json
+import sys
+from pathlib import Path
+
+REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/drc")
+OUT = Path(__file__).resolve().parents[1] / "tests" / "golden" / "ref_api_surface.json"
+
+
+def main():
+    api = {}
+    for f in sorted(REF.rglob("*.py")):
+        mod = ".".join(f.relative_to(REF).with_suffix("").parts)
+        tree = ast.parse(f.read_text())
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef):
+                methods = {}
+                for item in node.body:
+                    if isinstance(item, ast.FunctionDef) and (not item.name.startswith("_") or item.name == "__init__"):
+                        methods[item.name] = [a.arg for a in item.args.args if a.arg != "self"]
+                api[f"{mod}.{node.name}"] = methods
+    OUT.write_text(json.dumps(api, indent=1, sort_keys=True) + "\n")
+    print("wrote", OUT, {k: len(v) for k, v in api.items()})
+
+
+if __name__ == "__main__":
+    main()
