@@ -81,6 +81,37 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+WRAP_SRC = PKG / "pywrap" / "py_wrapper.cpp"
+
+
+def wrapper_path() -> Path:
+    import sysconfig
+    return PKG / ("dyros_robot_controller_cpp_wrapper" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_wrapper(force: bool = False) -> Path:
+    """pybind11 extension module `dyros_robot_controller_cpp_wrapper` (the reference's module name, src/bindings.cpp:219) over the
+    C ABI: g++ only, linked against libdrc_b200.so next to it (rpath $ORIGIN)."""
+    import hashlib
+    import sysconfig
+    import pybind11
+    out = wrapper_path()
+    stamp = PKG / "dyros_robot_controller_cpp_wrapper.srchash"
+    h = hashlib.sha256(WRAP_SRC.read_bytes() + (PKG.parent / "include" / "drc_b200.h").read_bytes()).hexdigest()
+    if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == h:
+        return out
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    cmd = [cxx, "-O2", "-shared", "-fPIC", "-std=c++17", "-fvisibility=hidden", f"-I{sysconfig.get_paths()['include']}", f"-I{pybind11.get_include()}",
+           str(WRAP_SRC), "-o", str(out), f"-L{PKG}", "-ldrc_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed on py_wrapper.cpp:\n" + r.stdout + r.stderr)
+    stamp.write_text(h)
+    return out
+
+
 def check() -> None:
     """Host-code syntax pass in seconds: every translation unit with empty kernel bodies (-DDRC_SYNTAX_CHECK).  nvcc runs the
     device compilation (minutes for the real kernels) BEFORE the host compiler, so a typo in the C ABI otherwise shows up late."""
@@ -99,3 +130,4 @@ if __name__ == "__main__":
     else:
         build(force="--force" in sys.argv, verbose=True)
         print("built", LIB)
+        print("built", build_wrapper(force="--force" in sys.argv))

@@ -25,8 +25,32 @@ def test_mirror_has_every_reference_method(qual):
             continue
         params = [p for p in inspect.signature(f).parameters.values() if p.name != "self"]
         lead = [p.name for p in params[:len(args)]]
-        # same number of leading positional parameters (names may differ in spelling: kp vs Kp)
-        if len(lead) < len(args):
+        # same leading parameters, same NAMES: the reference's examples call with keywords (examples/python/fr3_controller.py:131-176)
+        if lead != args:
             wrong.append((name, args, lead))
     assert not missing, f"{qual} lacks {missing}"
-    assert not wrong, f"{qual}: fewer positional parameters than the reference: {wrong}"
+    assert not wrong, f"{qual}: parameters differ from the reference: {wrong}"
+
+
+def test_extension_module_surface():
+    """the pybind11 module `dyros_robot_controller_cpp_wrapper` exports every class and method of the reference's Boost.Python
+    module (src/bindings.cpp:219-447; fixture written by tools/dump_reference_api.py).  Import only -- no GPU needed."""
+    import sys
+    pkg = Path(__file__).resolve().parents[1] / "dyros_robot_controller_b200"
+    sys.path.insert(0, str(pkg))
+    try:
+        import dyros_robot_controller_cpp_wrapper as w
+    finally:
+        sys.path.remove(str(pkg))
+    ref = json.loads((Path(__file__).resolve().parent / "golden" / "ref_bindings_surface.json").read_text())
+    assert ref["module"] == w.__name__
+    for cls, members in ref["classes"].items():
+        C = getattr(w, cls, None)
+        assert C is not None, f"class {cls} missing"
+        missing = [mname for mname in members if not hasattr(C, mname)]
+        assert not missing, f"{cls} lacks {missing}"
+    # without a CUDA device construction fails loudly (no CPU fallback) -- and succeeds on the GPU box
+    import dyros_robot_controller_b200 as drc
+    if drc.device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            w.ManipulatorRobotData(drc.FR3_URDF, drc.FR3_SRDF, "")

@@ -28,5 +28,26 @@ def main():
     print("wrote", OUT, {k: len(v) for k, v in api.items()})
 
 
+def bindings_surface(src=Path("/root/reference/src/bindings.cpp")):
+    """module name, classes and their .def / .def_readwrite / enum .value names, read from the text of src/bindings.cpp"""
+    import re
+    text = src.read_text()
+    mod = re.search(r"BOOST_PYTHON_MODULE\((\w+)\)", text).group(1)
+    classes, cur = {}, None
+    for line in text.split("\n"):
+        m = re.search(r'bp::(?:class_|enum_)<[^"]*>\s*\(\s*"(\w+)"', line)
+        if m:
+            cur = m.group(1)
+            classes[cur] = []
+            continue
+        m = re.search(r'\.(?:def|def_readwrite|value)\(\s*"(\w+)"', line)
+        if m and cur and m.group(1) not in classes[cur]:
+            classes[cur].append(m.group(1))
+    out = OUT.parent / "ref_bindings_surface.json"
+    out.write_text(json.dumps({"module": mod, "classes": classes}, indent=1, sort_keys=True) + "\n")
+    print("wrote", out, {k: len(v) for k, v in classes.items()})
+
+
 if __name__ == "__main__":
     main()
+    bindings_surface()
