@@ -29,6 +29,7 @@ class DrcParams(C.Structure):
         ("adaptive_rho_tolerance", C.c_double), ("gjk_tol", C.c_double), ("epa_tol", C.c_double),
         ("gjk_max_iter", C.c_int), ("epa_max_iter", C.c_int), ("pinv_threshold", C.c_double),
         ("schedule_hint", C.c_int),
+        ("rollout_fused", C.c_int),
     ]
 
 

@@ -16,6 +16,11 @@
 #define DRC_HD_NOINLINE static inline
 #endif
 
+// phase markers for the flop-counting build of the kernel bodies (tools/flopcount); no-ops everywhere else
+#ifndef DRC_PHASE
+#define DRC_PHASE(x) ((void)0)
+#endif
+
 namespace drc {
 
 constexpr int kMaxV = 16;      // max model dof
@@ -48,6 +53,8 @@ struct DrcParams {
   double pinv_threshold = 1e-6;  // COD rank threshold (math_type_define.h:7)
   // scheduling only (no effect on results): order the ADMM launch by the previous tick's iteration counts
   int schedule_hint = 1;
+  // closed-loop rollouts: 0 = the multi-stream pipeline of the fused cycle per tick (fastest), 1 = two launches per tick (k_tick_front + k_admm)
+  int rollout_fused = 0;
 };
 
 // Collision primitives (kept as one block so a kernel can stage it into shared memory).

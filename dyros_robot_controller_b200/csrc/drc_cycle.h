@@ -102,6 +102,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     if (from_cache) { q[i] = io.c_q[i * io.Bc + b]; qd[i] = io.c_qd[i * io.Bc + b]; }
     else { q[i] = io.q[bi * io.sq.sb + i * io.sq.sk]; qd[i] = io.qd[bi * io.sqd.sb + i * io.sqd.sk]; }
   }
+  DRC_PHASE(PH_KIN);
   KinState<NV> k;
   k.origin = v3(0, 0, 0);
   forward_kinematics<NV, CHAIN>(m, q, k);
@@ -122,6 +123,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     }
   }
 
+  DRC_PHASE(PH_DYN);
   double M[NV * NV], g[NV], Minv[NV * NV];
   constexpr bool need_dyn_vals = (FLAGS & (F_QPID | F_OSF | F_TORQUE)) != 0;
   if (FLAGS & F_DYN) {
@@ -196,6 +198,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     for (int i = 0; i < ACT; ++i) { io.c_gact[i * io.Bc + b] = gact[i]; io.c_nleact[i * io.Bc + b] = nleact[i]; }
   }
 
+  DRC_PHASE(PH_BUILD);
   if (FLAGS & F_TORQUE) {  // tau = M (Kp (q_t - q) + Kv (qd_t - qd)) + g
     double acc[NV];
 #pragma unroll
@@ -214,6 +217,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   constexpr bool need_frame = (FLAGS & (F_FRAME_OUT | F_MANIP_OUT | F_QPIK | F_QPID | F_CLIK | F_OSF)) != 0;
   if (!need_frame) return;
 
+  DRC_PHASE(PH_KIN);
   Mat3 Rf;
   Vec3 pf;
   frame_pose<NV>(k, frame, Rf, pf);
@@ -270,6 +274,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   }
 
   // manipulability
+  DRC_PHASE(PH_MANI);
   double mani = 0, mgrad[NV], mgraddot[NV];
   if (FLAGS & (F_MANIP_OUT | F_QPIK | F_QPID)) {
     constexpr bool gd = (FLAGS & (F_QPID | F_GRADDOT)) != 0;
@@ -285,6 +290,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   }
 
   // desired task-space signal
+  DRC_PHASE(PH_BUILD);
   double des[6];
   if (FLAGS & (F_QPIK | F_QPID | F_CLIK | F_OSF)) {
     double xd_t[6];
@@ -761,11 +767,17 @@ struct SolveIO {
   const int* out_ids;           // optional: outputs / hints of QP slot i go to robot out_ids[i] (priority launch: records are compact)
   const int* count;             // optional (device): number of slots (null = B)
   const int* skip;              // optional: robots (QP slots) with skip[slot] != 0 are left to another launch (EPA-pending robots)
+  // closed-loop rollout (drc_batch_rollout_qpik): the solver launch also performs the caller's integrate step
+  // q += dt * qdot*, qdot = qdot* (examples/C++/src/fr3_controller.cpp:129-131, ideal tracking) and the per-robot tallies
+  double* roll_q; double* roll_qd; Strided sroll; double roll_dt;
+  int* fail_ticks; int* iters_total;
+  int* hist_next; int* offs_next; int* sched_ticket;   // next tick's schedule (device only, see k_admm)
 };
 
 template <class Cfg, bool ID, class W>
 DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpOptions& o) {
   admm_solve<Cfg>(w, io.qp, robots, o);
+  DRC_PHASE(PH_QP_EMIT);
   w.each([&](Lane<Cfg>& L, GroupShared<Cfg>& S) {
     const int slot = S.robot;  // index of the QP record / state-cache entry
     if (slot < 0) return;
@@ -775,6 +787,8 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
       if (io.status) io.status[b] = S.status;
       if (io.iters) io.iters[b] = S.iters;
       if (io.iters_hint) io.iters_hint[b] = S.iters;
+      if (io.fail_ticks) io.fail_ticks[b] += ok ? 0 : 1;
+      if (io.iters_total) io.iters_total[b] += S.iters;
     }
     const ColdLane<Cfg>& C = S.cold[L.gl];
     constexpr int NY = Cfg::NC * (1 + 2 * Cfg::KU) + 2 * Cfg::NR;
@@ -785,8 +799,14 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
     if (L.is_core) {
       const int j = L.gl;
       const double xc = C.D * L.x;
-      if (!ID) io.out[b * io.sout.sb + j * io.sout.sk] = ok ? xc : 0.0;
-      else if (io.out2) io.out2[b * io.sout2.sb + j * io.sout2.sk] = ok ? xc : 0.0;
+      if (!ID) {
+        const double cmd = ok ? xc : 0.0;
+        if (io.out) io.out[b * io.sout.sb + j * io.sout.sk] = cmd;
+        if (io.roll_q) {   // rollout: integrate in place
+          io.roll_q[b * io.sroll.sb + j * io.sroll.sk] += io.roll_dt * cmd;
+          io.roll_qd[b * io.sroll.sb + j * io.sroll.sk] = cmd;
+        }
+      } else if (io.out2) io.out2[b * io.sout2.sb + j * io.sout2.sk] = ok ? xc : 0.0;
       if (io.qp_x) {
         double* xr = io.qp_x + (long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR);
         xr[j] = xc;

@@ -60,7 +60,7 @@ struct drc_ctx {
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
-  double* roll; int* roll_i;             // rollout scratch (command, cubic profile; status, iterations), allocated on first use
+  double* roll; int* roll_i;             // rollout scratch (cubic profile; next tick's schedule histogram / offsets / ticket), allocated on first use
   int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
@@ -82,6 +82,8 @@ struct drc_ctx {
   cudaEvent_t tr_ev[32]; const char* tr_name[32]; int tr_n;
   // optional debug outputs of the QP solves (drc_ctx_enable_qp_debug): primal / dual vectors in structured order
   double *dbg_x, *dbg_y;
+  // rollout in progress (pipeline variant): every solver launch of the tick integrates the state in place and keeps the tallies
+  double *roll_q, *roll_qd; Strided sroll; double roll_dt; int *roll_fail, *roll_iters;
 };
 static inline void mark(drc_ctx* c, const char* name, cudaStream_t s) {
   if (!c->timing || c->tr_n >= 32) return;
@@ -212,6 +214,7 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
   io.iters_hint = c->prev_iters;
   io.qp_x = c->dbg_x; io.qp_y = c->dbg_y;
+  if (c->roll_q && !io.roll_q) { io.roll_q = c->roll_q; io.roll_qd = c->roll_qd; io.sroll = c->sroll; io.roll_dt = c->roll_dt; io.fail_ticks = c->roll_fail; io.iters_total = c->roll_iters; }
   // one instantiation per QP shape (register cap 65536 / (128 * 3) = 168).  The dynamic shared-memory opt-in is a per-device
   // function attribute: set it for the context's device on every launch (cheap) so that contexts on several GPUs of one
   // process all get it.

@@ -171,6 +171,39 @@ static __device__ void epa_warp(EpaWarpSmem& S, const Prim& A, const Prim& B, co
   __syncwarp();
 }
 
+// one flagged robot, handled by one warp: resolve its overlapping GJK-type pairs with EPA, then gradients / QP row
+template <int NV, bool CHAIN>
+static __device__ void epa_robot_warp(EpaWarpSmem& S, const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b, int lane) {
+  unsigned long long deferred = io.cand_mask[b];
+  BestPair best;
+  best.d = io.dist[b]; best.id = io.pair_out[b];
+  best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
+  best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
+  best.ja = -1; best.jb = -1;
+  for (int k = 0; k < m.npair; ++k)
+    if (m.geom.pair_id[k] == best.id) { best.ja = m.geom.parent[m.geom.pair_a[k]]; best.jb = m.geom.parent[m.geom.pair_b[k]]; }
+  while (deferred) {
+    const int bit = __ffsll((long long)deferred) - 1;
+    deferred &= deferred - 1ull;
+    const int k = m.gjk_pair[bit];
+    const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
+    const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
+    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+    const Mat3 Rab = tmul(FA.R, FB.R);
+    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
+    GjkOut g;
+    gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+    PairResult r;
+    r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
+    if (g.intersect) epa_warp(S, A, Bp, g, prm.epa_tol, prm.epa_max_iter, r, lane);
+    consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
+  }
+  __syncwarp();
+  if (lane == 0) collision_finish<NV, CHAIN>(m, prm, io, b, best);
+  __syncwarp();
+}
+
 constexpr int kEpaWarps = 2;
 template <int NV, bool CHAIN>
 __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
@@ -178,42 +211,17 @@ __global__ void __launch_bounds__(kEpaWarps * 32) k_collision_epa(const __grid_c
 #ifndef DRC_SYNTAX_CHECK
   __shared__ EpaWarpSmem sm[kEpaWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  EpaWarpSmem& S = sm[warp];
   const int count = *io.epa_count;
-  for (int i = blockIdx.x * kEpaWarps + warp; i < count; i += gridDim.x * kEpaWarps) {
-    const int b = io.epa_list[i];
-    unsigned long long deferred = io.cand_mask[b];
-    BestPair best;
-    best.d = io.dist[b]; best.id = io.pair_out[b];
-    best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
-    best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
-    best.ja = -1; best.jb = -1;
-    for (int k = 0; k < m.npair; ++k)
-      if (m.geom.pair_id[k] == best.id) { best.ja = m.geom.parent[m.geom.pair_a[k]]; best.jb = m.geom.parent[m.geom.pair_b[k]]; }
-    while (deferred) {
-      const int bit = __ffsll((long long)deferred) - 1;
-      deferred &= deferred - 1ull;
-      const int k = m.gjk_pair[bit];
-      const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
-      const int ja = m.geom.parent[ga], jb = m.geom.parent[gb];
-      const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
-      const Mat3 Rab = tmul(FA.R, FB.R);
-      const Vec3 pab = tmul(FA.R, FB.p - FA.p);
-      const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
-      GjkOut g;
-      gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
-      PairResult r;
-      r.d = g.dist; r.pa = g.pa; r.pb = g.pb;
-      if (g.intersect) epa_warp(S, A, Bp, g, prm.epa_tol, prm.epa_max_iter, r, lane);
-      consider(best, r.d, m.geom.pair_id[k], ja, jb, r.pa, r.pb);
-    }
-    __syncwarp();
-    if (lane == 0) collision_finish<NV, CHAIN>(m, prm, io, b, best);
-    __syncwarp();
-  }
+  for (int i = blockIdx.x * kEpaWarps + warp; i < count; i += gridDim.x * kEpaWarps) epa_robot_warp<NV, CHAIN>(sm[warp], m, prm, io, io.epa_list[i], lane);
 #endif
 }
 
+// schedule bucket of an iteration count (descending: slow robots get the small buckets); used by k_admm and the k_sched_* kernels
+constexpr int kSchedBuckets = 256;
+static __device__ __forceinline__ int sched_bucket_of(int iters) {
+  const int k = iters / 25;
+  return kSchedBuckets - 1 - (k < kSchedBuckets ? k : kSchedBuckets - 1);
+}
 #ifndef DRC_ADMM_WARPS
 #define DRC_ADMM_WARPS 1
 #endif
@@ -228,7 +236,6 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_ad
   const int off = io.order_off ? *io.order_off : 0;
   const int nslot = io.count ? (*io.count < io.B ? *io.count : io.B) : io.B;
   const int first = off + (blockIdx.x * kAdmmWarps + warp) * Cfg::NG;
-  if (first >= nslot) return;  // no block-level barrier below: idle warps may leave
   int robots[Cfg::NG];
 #pragma unroll
   for (int g = 0; g < Cfg::NG; ++g) {
@@ -238,9 +245,38 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_ad
   }
   WarpExec<Cfg> w;
   w.sh = sh + warp * Cfg::NG;
-  w.lane = lane;
-  lane_assign<Cfg>(w.L, lane);
-  solve_and_emit<Cfg, ID>(w, robots, io, o);
+  if (first < nslot) {   // no block-level barrier below: idle warps skip the solve
+    w.lane = lane;
+    lane_assign<Cfg>(w.L, lane);
+    solve_and_emit<Cfg, ID>(w, robots, io, o);
+  }
+  if (io.hist_next) {
+    // rollout ticks: histogram of this tick's iteration counts = the schedule buckets of the next tick; the LAST warp of the
+    // launch turns it into the exclusive offsets the next tick's front kernel scatters with (no extra launch, no host sync)
+    int mine = -1;
+#pragma unroll
+    for (int g = 0; g < Cfg::NG; ++g) if (lane == g) mine = robots[g];
+    if (first < nslot && mine >= 0) atomicAdd(&io.hist_next[sched_bucket_of(w.sh[lane].iters)], 1);
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(io.sched_ticket, 1) == (int)(gridDim.x * kAdmmWarps) - 1;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      constexpr int PER = kSchedBuckets / 32;
+      int v[PER], sum = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { v[i] = __ldcg(&io.hist_next[lane * PER + i]); sum += v[i]; }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+      int run = incl - sum;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { io.offs_next[lane * PER + i] = run; run += v[i]; io.hist_next[lane * PER + i] = 0; }
+      if (lane == 0) *io.sched_ticket = 0;
+    }
+  }
 #endif
 }
 
@@ -250,11 +286,7 @@ __global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_ad
 // solve nearly the same QP, so the PREVIOUS tick's iteration count is an excellent predictor: robots are ordered by
 // descending previous count (counting sort over count/25), i.e. longest first and warps of similar length.  Only the
 // robot -> warp assignment changes; every robot's arithmetic, and therefore its result, is unaffected.
-constexpr int kSchedBuckets = 256;
-static __device__ __forceinline__ int sched_bucket(int iters) {
-  const int k = iters / 25;
-  return kSchedBuckets - 1 - (k < kSchedBuckets ? k : kSchedBuckets - 1);  // descending: slow robots get the small buckets
-}
+static __device__ __forceinline__ int sched_bucket(int iters) { return sched_bucket_of(iters); }
 static __global__ void k_sched_hist(const int* prev, int B, int* hist) {
   __shared__ int h[kSchedBuckets];
   for (int i = threadIdx.x; i < kSchedBuckets; i += blockDim.x) h[i] = 0;
@@ -328,9 +360,7 @@ static __device__ Mat3 so3_exp(Vec3 w) {
   sincos(th, &s, &c);
   return rot_axis((1.0 / th) * w, s, c);
 }
-static __global__ void k_task_cubic(const __grid_constant__ CubicIO io) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= io.B) return;
+static __device__ __forceinline__ void task_cubic_job(const CubicIO& io, int b) {
   auto ld12 = [&](const double* p, int k) { return p[b * io.s12.sb + k * io.s12.sk]; };
   auto ld6 = [&](const double* p, int k) { return p[b * io.s6.sb + k * io.s6.sk]; };
   const double tf = io.t0 + io.dur;
@@ -361,6 +391,52 @@ static __global__ void k_task_cubic(const __grid_constant__ CubicIO io) {
   io.xdot_des[b * io.s6.sb + 3 * io.s6.sk] = rd.x;
   io.xdot_des[b * io.s6.sb + 4 * io.s6.sk] = rd.y;
   io.xdot_des[b * io.s6.sb + 5 * io.s6.sk] = rd.z;
+}
+static __global__ void k_task_cubic(const __grid_constant__ CubicIO io) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < io.B) task_cubic_job(io, b);
+}
+
+// ---- one control tick of a closed-loop rollout, front half: per robot, in ONE launch,
+//   [schedule scatter for this tick's solver launch] -> [cubic profile] -> joint placements -> self-collision narrow phase
+//   -> QPIK record;  the block's EPA-flagged robots (~0.1 %) are then resolved by warp 0 with the warp-parallel EPA.
+// The solver launch (k_admm with SolveIO::roll_*) integrates the state and prepares the next tick's schedule: 2 launches per tick.
+struct TickIO {
+  JobIO job;            // q / qdot: the rollout state (read), x_target / xdot_target: the tick's desired pose / twist
+  CollisionIO col;
+  CubicIO cubic;        // B == 0: no profile (QPIKStep on the given target)
+  const int* prev;      // previous tick's iteration counts; null: the schedule of this tick has been prepared by k_sched_*
+  int* offs;            // exclusive bucket offsets (k_admm's last block, previous tick)
+  int* order;
+};
+constexpr int kTickThreads = 128;
+template <int NV, bool CHAIN>
+__global__ void __launch_bounds__(kTickThreads) k_tick_front(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+                                                             const __grid_constant__ DrcFrame frame, const __grid_constant__ TickIO io) {
+#ifndef DRC_SYNTAX_CHECK
+  __shared__ GeomTable G;
+  __shared__ EpaWarpSmem epa;
+  __shared__ int n_flag, flagged[kTickThreads];
+  {
+    const int* src = reinterpret_cast<const int*>(&m.geom);
+    int* dst = reinterpret_cast<int*>(&G);
+    for (int i = threadIdx.x; i < (int)(sizeof(GeomTable) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) n_flag = 0;
+  }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < io.job.B) {
+    if (io.prev) io.order[atomicAdd(&io.offs[sched_bucket(io.prev[b])], 1)] = b;
+    if (io.cubic.B > 0) task_cubic_job(io.cubic, b);
+    robot_job<NV, CHAIN, F_STORE>(m, prm, frame, io.job, b);
+    collision_job<NV, CHAIN>(m, G, prm, io.col, b);
+    if (io.col.epa_flag[b]) flagged[atomicAdd(&n_flag, 1)] = b;
+    robot_job<NV, CHAIN, F_FROM_CACHE | F_QPIK | F_STEP>(m, prm, frame, io.job, b);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+    for (int i = 0; i < n_flag; ++i) epa_robot_warp<NV, CHAIN>(epa, m, prm, io.col, flagged[i], threadIdx.x);
+#endif
 }
 
 // cache (SoA [K][Bc]) -> user array; `sub` != null writes src - sub (coriolis = nle - g)

@@ -58,8 +58,12 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     return step ? J(F_FROM_CACHE | F_QPID | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPID, jio, st);
   };
 
+  if (prio) CU(cudaEventRecord(c->ev_sched, s));
+  // stage 1a (main pipeline): joint placements -> cache.  Enqueued before the priority pipeline so that every read of the INPUT
+  // state arrays by the main pipeline precedes the priority solver launch, which may update them in place (rollouts)
+  if (fused) { rc = J(F_STORE, io, s); if (rc) return rc; mark(c, "fk", s); }
+  if (fused) CU(cudaEventRecord(c->ev_store, s));
   if (prio) {
-    CU(cudaEventRecord(c->ev_sched, s));
     // ---- priority pipeline: slots [0, *slow_count) of the compact scratch hold robots order[slot]
     CU(cudaStreamWaitEvent(c->prio_stream, c->ev_sched, 0));
     cudaStream_t ps = c->prio_stream;
@@ -83,6 +87,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     rc = launch_collision<NV, CHAIN>(c, pc, ps, false, &c->prio); if (rc) return rc;
     mark(c, "prio_collision", ps);
     CU(cudaStreamWaitEvent(ps, c->ev_prio_build, 0));
+    CU(cudaStreamWaitEvent(ps, c->ev_store, 0));
     SolveIO ps_io;
     std::memset(&ps_io, 0, sizeof ps_io);
     ps_io.B = kPrioSlots; ps_io.out = out; ps_io.sout = lay(layout, NV, B); ps_io.out2 = out2; ps_io.sout2 = ps_io.sout;
@@ -95,9 +100,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   }
 
   // ---- main pipeline
-  // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; its EPA pass goes to the side stream
-  if (fused) { rc = J(F_STORE, io, s); if (rc) return rc; mark(c, "fk", s); }
-  if (split_dyn) CU(cudaEventRecord(c->ev_store, s));
+  // stage 1b: self-collision narrow phase; its EPA pass goes to the side stream
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp; cio.qp_stride = qp_stride; cio.qp_row_off = qp_row_off;
@@ -142,27 +145,77 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   return rc;
 }
 
-// Closed-loop rollout: the caller's integrate step between control ticks,
-// q_desired = q + qdot_desired * dt (examples/C++/src/fr3_controller.cpp:129-131), with ideal tracking of the command
-// (q <- q_desired, qdot <- qdot_desired) standing in for the simulator.  One thread per robot.
-struct RolloutIO {
-  int B, nv;
-  double dt;
-  double *q, *qd; Strided sq;
-  const double* cmd; Strided sc;
-  const int *status, *iters;
-  int *fail_ticks, *iters_total;
-};
-static __global__ void __launch_bounds__(128) k_rollout_integrate(const RolloutIO io) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= io.B) return;
-  for (int i = 0; i < io.nv; ++i) {
-    const double v = io.cmd[b * io.sc.sb + i * io.sc.sk];
-    io.q[b * io.sq.sb + i * io.sq.sk] += io.dt * v;
-    io.qd[b * io.sq.sb + i * io.sq.sk] = v;
+// Closed-loop rollout: T control ticks of updateState + QPIKCubic / QPIKStep + the caller's integrate step
+// (examples/C++/src/fr3_controller.cpp:116-131), TWO launches per tick:
+//   k_tick_front  [schedule scatter] -> [cubic profile] -> joint placements -> narrow phase (+ EPA for the block's flagged robots)
+//                 -> QPIK record
+//   k_admm        solve -> command -> q += dt qdot*, qdot = qdot* in place -> tallies -> histogram + offsets of the next tick's schedule
+// The robot -> warp schedule of tick k is tick k-1's iteration counts (tick 0: the context's previous call), results unaffected.
+template <int NV, bool CHAIN>
+static int run_rollout(drc_ctx* c, int B, int T, double dt, double* q, double* qdot, const double* x_target, const double* xdot_target,
+                       const double* x_init, const double* xdot_init, double t_start, double t0, double duration, int frame,
+                       int* fail_ticks, int* iters_total, int layout, cudaStream_t s) {
+  const bool cubic = duration > 0;
+  if (!c->roll) {
+    CU(cudaMalloc((void**)&c->roll, (size_t)c->cap * (12 + 6) * sizeof(double)));
+    CU(cudaMalloc((void**)&c->roll_i, (size_t)(2 * kSchedBuckets + 1) * sizeof(int)));
+    CU(cudaMemset(c->roll_i, 0, (size_t)(2 * kSchedBuckets + 1) * sizeof(int)));
   }
-  if (io.fail_ticks) io.fail_ticks[b] += io.status[b] != kQpSolved ? 1 : 0;
-  if (io.iters_total) io.iters_total[b] += io.iters[b];
+  double *x_des = c->roll, *xd_des = c->roll + (size_t)c->cap * 12;
+  int *hist_next = c->roll_i, *offs_next = c->roll_i + kSchedBuckets, *ticket = c->roll_i + 2 * kSchedBuckets;
+  if (fail_ticks) CU(cudaMemsetAsync(fail_ticks, 0, (size_t)B * sizeof(int), s));
+  if (iters_total) CU(cudaMemsetAsync(iters_total, 0, (size_t)B * sizeof(int), s));
+  if (!c->prm.rollout_fused) {
+    // pipeline variant: per tick [cubic profile kernel] + the multi-stream pipeline of the fused cycle (run_qp), whose solver launches
+    // (priority, main, EPA-pending) integrate the state in place -- the slow robots' solves overlap the other robots' front stages
+    c->roll_q = q; c->roll_qd = qdot; c->sroll = lay(layout, NV, B); c->roll_dt = dt; c->roll_fail = fail_ticks; c->roll_iters = iters_total;
+    int rc = DRC_OK;
+    for (int k = 0; k < T && rc == DRC_OK; ++k) {
+      const double *xt = x_target, *xd = xdot_target;
+      if (cubic) {
+        rc = drc_batch_task_space_cubic(c, B, x_target, xdot_target, x_init, xdot_init, t_start + k * dt, t0, duration, x_des, xd_des, layout, s);
+        xt = x_des; xd = xd_des;
+      }
+      if (rc == DRC_OK) rc = run_qp<NV, CHAIN>(c, B, false, true, q, qdot, xt, xd, frame, nullptr, nullptr, nullptr, nullptr, layout, s);
+    }
+    c->roll_q = c->roll_qd = nullptr; c->roll_fail = c->roll_iters = nullptr;
+    return rc;
+  }
+  const bool sched = c->prm.schedule_hint != 0 && B >= 64;
+  if (sched) { int rc = launch_schedule(c, B, s); if (rc) return rc; }
+  const DrcFrame fr = frame_of(c->model, frame);
+  const Scratch sc = main_scratch(c);
+  for (int k = 0; k < T; ++k) {
+    TickIO io;
+    std::memset(&io, 0, sizeof io);
+    JobIO& j = io.job;
+    j.B = B; j.q = q; j.qd = qdot; j.sq = lay(layout, NV, B); j.sqd = j.sq;
+    j.x_target = cubic ? x_des : x_target; j.sxt = lay(layout, 12, B);
+    j.xdot_target = cubic ? xd_des : xdot_target; j.sxd = lay(layout, 6, B);
+    j.qp = c->qp;
+    bind_cache(c, j);
+    CollisionIO& col = io.col;
+    col.B = B; col.mode = 1; col.qp = c->qp; col.qp_stride = QpikCfg<NV>::STRIDE; col.qp_row_off = QpikCfg<NV>::OFF_ROW + (NV + 1);
+    col.c_q = sc.c_q; col.c_qd = sc.c_qd; col.c_oMi = sc.c_oMi; col.Bc = sc.Bc;
+    col.epa_flag = sc.epa_flag; col.cand_mask = sc.cand_mask; col.dist = sc.col_dist; col.pair_out = sc.col_pair; col.witness = sc.col_wit;
+    if (cubic) {  // DyrosMath::getTaskSpaceCubic at the tick's time (QPIKCubic, robot_controller.cpp:302-317)
+      CubicIO& cb = io.cubic;
+      cb.B = B; cb.x_target = x_target; cb.xdot_target = xdot_target; cb.x_init = x_init; cb.xdot_init = xdot_init;
+      cb.s12 = lay(layout, 12, B); cb.s6 = lay(layout, 6, B); cb.t = t_start + k * dt; cb.t0 = t0; cb.dur = duration; cb.x_des = x_des; cb.xdot_des = xd_des;
+    }
+    if (sched) { io.order = c->order; io.offs = offs_next; io.prev = k > 0 ? c->prev_iters : nullptr; }
+    k_tick_front<NV, CHAIN><<<(B + kTickThreads - 1) / kTickThreads, kTickThreads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
+    c->launches++;
+    CU(cudaGetLastError());
+    SolveIO sio;
+    std::memset(&sio, 0, sizeof sio);
+    sio.B = B; sio.sout = lay(layout, NV, B);
+    sio.roll_q = q; sio.roll_qd = qdot; sio.sroll = lay(layout, NV, B); sio.roll_dt = dt; sio.fail_ticks = fail_ticks; sio.iters_total = iters_total;
+    if (sched) { sio.order = c->order; sio.hist_next = hist_next; sio.offs_next = offs_next; sio.sched_ticket = ticket; }
+    int rc = launch_admm<QpikCfg<NV>, false>(c, sio, s);
+    if (rc) return rc;
+  }
+  return DRC_OK;
 }
 
 extern "C" {
@@ -416,7 +469,7 @@ int drc_ctx_get_params(const drc_ctx_t* c, drc_params_t* p) {
   p->check_termination = s.check_termination; p->scaling = s.scaling; p->adaptive_rho = s.adaptive_rho;
   p->adaptive_rho_interval = s.adaptive_rho_interval; p->adaptive_rho_tolerance = s.adaptive_rho_tolerance;
   p->gjk_tol = s.gjk_tol; p->epa_tol = s.epa_tol; p->gjk_max_iter = s.gjk_max_iter; p->epa_max_iter = s.epa_max_iter;
-  p->pinv_threshold = s.pinv_threshold; p->schedule_hint = s.schedule_hint;
+  p->pinv_threshold = s.pinv_threshold; p->schedule_hint = s.schedule_hint; p->rollout_fused = s.rollout_fused;
   return DRC_OK;
 }
 int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
@@ -434,7 +487,7 @@ int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
   s.check_termination = p->check_termination; s.scaling = p->scaling; s.adaptive_rho = p->adaptive_rho;
   s.adaptive_rho_interval = p->adaptive_rho_interval; s.adaptive_rho_tolerance = p->adaptive_rho_tolerance;
   s.gjk_tol = p->gjk_tol; s.epa_tol = p->epa_tol; s.gjk_max_iter = p->gjk_max_iter; s.epa_max_iter = p->epa_max_iter;
-  s.pinv_threshold = p->pinv_threshold; s.schedule_hint = p->schedule_hint;
+  s.pinv_threshold = p->pinv_threshold; s.schedule_hint = p->schedule_hint; s.rollout_fused = p->rollout_fused;
   return DRC_OK;
 }
 int drc_ctx_max_batch(const drc_ctx_t* c) { return c ? c->cap : DRC_E_INVALID; }
@@ -610,36 +663,12 @@ int drc_batch_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, dou
   rc = check_frame(c, frame); if (rc) return rc;
   if (!q || !qdot || !x_target || !xdot_target) return fail(DRC_E_INVALID, "null argument");
   if (T <= 0 || !(dt > 0)) return fail(DRC_E_INVALID, "rollout needs T > 0 ticks and dt > 0");
-  const bool cubic = duration > 0;
-  if (cubic && (!x_init || !xdot_init)) return fail(DRC_E_INVALID, "a cubic profile needs x_init and xdot_init");
+  if (duration > 0 && (!x_init || !xdot_init)) return fail(DRC_E_INVALID, "a cubic profile needs x_init and xdot_init");
   CU(cudaSetDevice(c->device));
-  const int n = c->model->hm.dev.nv;
-  if (!c->roll) {  // command / profile scratch, allocated on first use
-    CU(cudaMalloc((void**)&c->roll, (size_t)c->cap * (n + 12 + 6) * sizeof(double)));
-    CU(cudaMalloc((void**)&c->roll_i, (size_t)c->cap * 2 * sizeof(int)));
-  }
-  double *cmd = c->roll, *x_des = c->roll + (size_t)c->cap * n, *xd_des = x_des + (size_t)c->cap * 12;
-  int *st = c->roll_i, *it = c->roll_i + c->cap;
   cudaStream_t s = pick(c, stream);
-  if (fail_ticks) CU(cudaMemsetAsync(fail_ticks, 0, (size_t)B * sizeof(int), s));
-  if (iters_total) CU(cudaMemsetAsync(iters_total, 0, (size_t)B * sizeof(int), s));
-  for (int k = 0; k < T; ++k) {
-    const double *xt = x_target, *xd = xdot_target;
-    if (cubic) {  // DyrosMath::getTaskSpaceCubic at the tick's time (QPIKCubic, robot_controller.cpp:302-317)
-      rc = drc_batch_task_space_cubic(c, B, x_target, xdot_target, x_init, xdot_init, t_start + k * dt, t0, duration, x_des, xd_des, layout, s);
-      if (rc) return rc;
-      xt = x_des; xd = xd_des;
-    }
-    rc = drc_batch_cycle_qpik_step(c, B, q, qdot, xt, xd, frame, cmd, st, it, layout, s);
-    if (rc) return rc;
-    RolloutIO io;
-    io.B = B; io.nv = n; io.dt = dt; io.q = q; io.qd = qdot; io.sq = lay(layout, n, B); io.cmd = cmd; io.sc = io.sq;
-    io.status = st; io.iters = it; io.fail_ticks = fail_ticks; io.iters_total = iters_total;
-    k_rollout_integrate<<<(B + 127) / 128, 128, 0, s>>>(io);
-    c->launches++;
-    CU(cudaGetLastError());
-  }
-  return DRC_OK;
+  DRC_DISPATCH_NV(c->model->hm.dev.nv, c->model->hm.chain,
+                  return (run_rollout<NV, CHAIN>(c, B, T, dt, q, qdot, x_target, xdot_target, x_init, xdot_init, t_start, t0, duration, frame,
+                                                 fail_ticks, iters_total, layout, s)));
 }
 
 static int taskspace(drc_ctx_t* c, int B, int kind, const double* x_target, const double* xdot, const double* aux, const double* aux2,

@@ -208,6 +208,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
   const double sigma = o.sigma, alpha = o.alpha, oma = 1.0 - o.alpha;
 
   // ---------------------------------------------------------------- load
+  DRC_PHASE(PH_QP_LOAD);
   w.each([&](LaneT& L, GS& S) {
     const int rb = robots[L.grp];
     Cold& C = S.cold[L.gl];
@@ -279,6 +280,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
   // (|c| = e = beta = 1, cost = slack weight) and every scaling factor depends on magnitudes only, so they stay
   // identical through all passes: bundle 0 is scaled as their representative and copied to the others afterwards.
   // The cost normalisation of a pass (c_temp) is applied at the start of the next one (apply_cost), which saves a phase.
+  DRC_PHASE(PH_QP_SCALE);
   auto apply_cost = [&](LaneT& L, GS& S) {
     // c_temp = 1 / limit(max(mean_j ||P_j||_inf, limit(||q||_inf))) from the per-lane values published by phase Y
     double sum = 0, qm = 0;
@@ -394,6 +396,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
 
   // ---------------------------------------------------------------- factorisation (setup and rho updates)
   auto factor = [&]() {
+    DRC_PHASE(PH_QP_FACTOR);
     // (a) rho vector, per-bundle constants, Schur complement S = P + sigma I + diag(...) + sum_r omega_r a_r a_r'
     w.each([&](LaneT& L, GS& S) {
       if (!S.need_factor) return;
@@ -621,6 +624,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
       for (int g = 0; g < NG; ++g) nf = nf || (w.group(g).need_factor != 0 && w.group(g).done == 0);
       if (nf) factor();
     }
+    DRC_PHASE(PH_QP_ITER);
     // plain iterations up to (excluding) the next event: nothing but the two hot phases
     int nplain = to_check < to_adapt ? to_check : to_adapt;
     if (nplain > o.max_iter - iter) nplain = o.max_iter - iter;
@@ -642,6 +646,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     w.each(phase_b_keep);
 
     // ---------------- OSQP update_info + check_termination + adapt_rho
+    DRC_PHASE(PH_QP_CHECK);
     // C1: per-lane partial reductions (registers; published once at the end).  Group totals:
     //   rows:      0 pri_u | 1 max(ax_u, z_u) | 2 pri_s | 3 max(ax_s, z_s) | 4 ||E dy|| | 5 sum(u dy+ + l dy-)
     //              6 max Adx over rows with a finite u | 7 max -Adx over rows with a finite l

@@ -51,6 +51,10 @@ typedef struct drc_params {
   /* scheduling only, results unaffected: order the ADMM launch by each robot's iteration count of the previous call on
    * this context (longest first, similar counts share a warp) -- consecutive control ticks solve nearly the same QP */
   int schedule_hint;
+  /* drc_batch_rollout_qpik: 0 (default) = per tick, the multi-stream pipeline of drc_batch_cycle_qpik_step (priority pipeline for the
+   * predicted-slow robots, integrate step fused into the solver launches); 1 = TWO launches per tick (k_tick_front: schedule
+   * scatter + cubic profile + FK + narrow phase + EPA + QPIK record; k_admm: solve + integrate + next tick's schedule).  Same results. */
+  int rollout_fused;
 } drc_params_t;
 
 const char* drc_last_error(void);

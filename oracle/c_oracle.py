@@ -99,6 +99,11 @@ class Oracle:
     def set_threads(self, t: int):
         lib().orc_set_threads(self.h, C.c_int(int(t)))
 
+    def set_fresh_workspace(self, on: bool):
+        """CPU-baseline mode: allocate and release the whole workspace every control cycle, as the reference does (a new
+        OsqpEigen::Solver per solveQP, QP_base.h:143-177; a new pinocchio::Data per getManipulability, robot_data.cpp:542)."""
+        lib().orc_set_fresh_workspace(self.h, C.c_int(int(on)))
+
     def set_task_gains(self, kp, kv):
         lib().orc_set_task_gains(self.h, _d(_c(kp)), _d(_c(kv)))
 

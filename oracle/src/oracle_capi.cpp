@@ -5,6 +5,7 @@
 //
 // All batch arrays are batch-major ("AoS"): element (b, k) of a (B, K) array sits at [b*K + k].
 // Poses are 12 doubles: the top three rows of the 4x4 homogeneous matrix, row-major.
+#include <memory>
 #include <omp.h>
 
 #include "omoma.h"
@@ -17,6 +18,10 @@ struct OrcHandle {
   GeomParams gp;
   QpSettings qs;
   int threads = 1;
+  // CPU-baseline mode: 1 = a fresh workspace (solver data, scratch vectors) is heap-allocated and released EVERY control cycle, as
+  // the reference does (new OsqpEigen::Solver per solveQP, QP_base.h:143-177; new pinocchio::Data per getManipulability,
+  // robot_data.cpp:542); 0 = one preallocated workspace per thread (optimistic)
+  int fresh_workspace = 0;
 };
 
 static SE3 pose_from12(const double* a) {
@@ -81,6 +86,7 @@ OrcHandle* orc_model_create(int nv, const int* parent, const int* jtype, const d
 }
 void orc_model_destroy(OrcHandle* h) { delete h; }
 void orc_set_threads(OrcHandle* h, int t) { h->threads = t > 0 ? t : 1; }
+void orc_set_fresh_workspace(OrcHandle* h, int on) { h->fresh_workspace = on != 0; }
 void orc_set_task_gains(OrcHandle* h, const double* kp, const double* kv) {
   for (int i = 0; i < 6; ++i) { h->cp.Kp_task[i] = kp[i]; h->cp.Kv_task[i] = kv[i]; }
 }
@@ -255,9 +261,11 @@ void orc_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* 
   const int n = m.nv;
 #pragma omp parallel num_threads(h->threads)
   {
-    Workspace ws;
+    std::unique_ptr<Workspace> keep(new Workspace);
 #pragma omp for schedule(dynamic, 16)
     for (int b = 0; b < B; ++b) {
+      std::unique_ptr<Workspace> fresh(h->fresh_workspace ? new Workspace : nullptr);
+      Workspace& ws = fresh ? *fresh : *keep;
       update_state(m, ws.s, q + b * n, qd + b * n);
       double des[6];
       if (mode == 0 || mode == 2) std::copy(xdot_target + 6 * b, xdot_target + 6 * b + 6, des);
@@ -457,10 +465,12 @@ void orc_moma_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const dou
   const int n = m.nv;
 #pragma omp parallel num_threads(h->threads)
   {
-    Workspace ws;
+    std::unique_ptr<Workspace> keep(new Workspace);
     MomaState ms;
 #pragma omp for schedule(dynamic, 16)
     for (int b = 0; b < B; ++b) {
+      std::unique_ptr<Workspace> fresh(h->fresh_workspace ? new Workspace : nullptr);
+      Workspace& ws = fresh ? *fresh : *keep;
       update_state(m, ws.s, q + b * n, qd + b * n);
       moma_update(m, ws.s, ms);
       const int act = ms.act;

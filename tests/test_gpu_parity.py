@@ -146,6 +146,30 @@ def test_device_pointer_path(gpu_ctx, oracle):
     assert np.abs(d["out"].cpu().numpy() - h["out"]).max() < 1e-12
 
 
+def test_streams_are_ordered_between_calls(gpu_ctx, oracle):
+    """torch inputs run on the caller's (torch) stream, the numpy getters on the context's own non-blocking stream: a getter
+    issued right after a torch update_state must see the NEW state (cross-stream ordering of consecutive calls)."""
+    import torch
+    model, ctx = gpu_ctx
+    dev = torch.device("cuda", 0)
+    f = oracle.frame_id(LINK)
+    B = 65536
+    for seed in (41, 42, 43):
+        q, qd, _, _ = workload(oracle.model, B, seed)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):           # a user stream, with work queued in front of the update
+            tq, tqd = torch.from_numpy(q).to(dev, non_blocking=True), torch.from_numpy(qd).to(dev, non_blocking=True)
+            junk = torch.randn(4096, 4096, device=dev) @ torch.randn(4096, 4096, device=dev)
+            ctx.update_state(tq, tqd)
+        fr = ctx.get_frame(LINK, want=("pose", "J"))     # host path, context stream
+        dy = ctx.get_dynamics(want=("M",))
+        idx = np.arange(0, B, 257)
+        ref = oracle.update_state(q[idx], qd[idx], f)
+        assert rel(fr["pose"][idx], ref["pose"]) < 1e-12 and rel(fr["J"][idx], ref["J"]) < 1e-12 and rel(dy["M"][idx], ref["M"]) < 1e-9
+        torch.cuda.synchronize()
+        del junk
+
+
 def test_taskspace_controllers(gpu_ctx, oracle):
     model, ctx = gpu_ctx
     B = 1500

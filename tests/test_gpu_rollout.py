@@ -31,8 +31,17 @@ def oracle_rollout(oracle, q, qd, x_t, xd_t, T, dt, x_i=None, xd_i=None, t_start
     return q, qd, fail, its
 
 
+@pytest.fixture(params=[0, 1], ids=["pipeline", "two_launches_per_tick"])
+def variant(request, gpu_ctx):
+    """both rollout variants (drc_params_t::rollout_fused): the multi-stream pipeline per tick, and two launches per tick"""
+    model, ctx = gpu_ctx
+    ctx.set_params(rollout_fused=request.param)
+    yield request.param
+    ctx.set_params(rollout_fused=0)
+
+
 @pytest.mark.parametrize("cubic", [False, True])
-def test_rollout_matches_tick_by_tick_oracle(gpu_ctx, oracle, cubic):
+def test_rollout_matches_tick_by_tick_oracle(gpu_ctx, oracle, cubic, variant):
     model, ctx = gpu_ctx
     B, T, dt = 160, 12, 1e-3
     q, qd, q_t, xd_t = workload(oracle.model, B, 91)
@@ -52,7 +61,7 @@ def test_rollout_matches_tick_by_tick_oracle(gpu_ctx, oracle, cubic):
     assert (r["fail_ticks"] <= T).all() and (r["iters_total"] >= 25 * T).all() and (r["iters_total"] % 25 == 0).all()
 
 
-def test_rollout_equals_repeated_cycles_on_the_device(gpu_ctx, oracle):
+def test_rollout_equals_repeated_cycles_on_the_device(gpu_ctx, oracle, variant):
     """device tensors, in place: one rollout call == T fused cycles + integrate on the caller's side (same iteration counts, states equal to rounding)"""
     import torch
     model, ctx = gpu_ctx
@@ -68,8 +77,11 @@ def test_rollout_equals_repeated_cycles_on_the_device(gpu_ctx, oracle):
         a_q = a_q + dt * r["out"]
         a_qd = r["out"].clone()
         its += r["iters"]
+    l0 = ctx.launch_count
     b = ctx.rollout_qpik(tq, tqd, txt, txd, LINK, T, dt)
     torch.cuda.synchronize()
+    if variant == 1:   # two launches per tick (+ the three schedule kernels of tick 0)
+        assert ctx.launch_count - l0 <= 2 * T + 3
     assert b["q"].data_ptr() == tq.data_ptr()                 # in place
     assert torch.equal(b["iters_total"], its)
     # the integrate kernel fuses q + dt * qdot into one FMA (torch rounds twice): equal up to that rounding
