@@ -48,9 +48,12 @@ def stale() -> bool:
     return HASH.read_text().strip() != _source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every translation unit for sm_100a (in parallel), link libdrc_b200.so in-tree."""
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, only: str | None = None, defines: tuple = ()) -> Path:
+    """Compile every translation unit for sm_100a (in parallel), link libdrc_b200.so in-tree.
+    `only` / `defines` are for kernel development (python -m ...build --dev): recompile ONE translation unit (the other objects
+    are reused as they are -- valid while the shared struct layouts are unchanged), optionally with -DDRC_DEV_FR3_ONLY (7-dof
+    instantiations only).  Such a build leaves the source hash stale, so the next plain build() is a full one."""
+    if not force and not only and not stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     src_hash = _source_hash()   # of the sources as they are NOW (edits made while nvcc runs must leave the library stale)
@@ -61,7 +64,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> Path:
         obj = OBJDIR / (src.stem + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src)]
+        if only and src.stem != only and obj.exists():
+            return obj
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -77,7 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                        capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
-    HASH.write_text(src_hash)
+    HASH.write_text("dev build" if only or defines else src_hash)
     return LIB
 
 
@@ -127,6 +132,9 @@ def check() -> None:
 if __name__ == "__main__":
     if "--check" in sys.argv:
         check()
+    elif "--dev" in sys.argv:
+        build(force=True, verbose="-v" in sys.argv, only="drc_lib", defines=("DRC_DEV_FR3_ONLY",))
+        print("dev build (drc_lib.cu, 7-dof instantiations only)", LIB)
     else:
         build(force="--force" in sys.argv, verbose=True)
         print("built", LIB)

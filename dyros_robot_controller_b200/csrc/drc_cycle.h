@@ -617,19 +617,34 @@ DRC_HD void collision_finish(const DrcModelDev& m, const DrcParams& prm, const C
   }
 }
 
-// Main self-distance pass.  Closed-form pairs are evaluated exactly in a loop that is uniform across
-// threads (model indices are warp-uniform -> constant-bank broadcasts); GJK-type pairs get their
-// certified lower bound there, and only those that can still win run GJK afterwards, each thread on
-// ITS OWN candidate (divergent model indices -> `G` is the shared-memory copy of the geometry table).
-// Pairs that overlap are deferred to the EPA kernel through cand_mask / epa_flag.
-template <int NV, bool CHAIN>
-DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io, int b) {
+// Main self-distance pass, in stages so that the device can run the GJK stage with the lanes of a block compacted onto the
+// robots that need it (drc_kernels.cuh `collision_block`); `collision_job` below is the same sequence for ONE robot.
+//   narrow_closed_phase  closed-form pairs exactly, in a loop that is uniform across threads (model indices are warp-uniform ->
+//                        constant-bank broadcasts); GJK-type pairs get their certified lower bound there
+//   narrow_pick          best first: the live candidate with the smallest lower bound, or -1 when none can still win
+//   narrow_gjk_item      GJK on one (robot, candidate) item -- any thread may run it (divergent model indices -> `G` is the
+//                        shared-memory copy of the geometry table)
+//   narrow_apply         the owner folds the item's result into its running minimum
+//   narrow_finish        overlapping pairs -> hand-over to the EPA kernel (cand_mask / epa_flag), else gradients + QP row
+struct NarrowState {
   BestPair best;
+  unsigned long long cand;      // bit i: i-th GJK-type pair whose bound beats the best exact distance so far
+  unsigned long long deferred;  // bit i: that pair overlaps -> EPA
+  float lbs[64];                // certified lower bounds (rounded DOWN to float: still lower bounds)
+};
+struct GjkItemResult {
+  double d;
+  Vec3 pa, pb;
+  int state;  // 0 culled by the exact re-test of the bound, 1 separated (d, pa, pb valid), 2 overlapping
+};
+
+template <int NV, bool CHAIN>
+DRC_HD void narrow_closed_phase(const DrcModelDev& m, const CollisionIO& io, int b, NarrowState& st) {
+  BestPair& best = st.best;
   best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
-  int best_k = -1;                 // closed-form pass: only (distance, reference order, pair index) of the running minimum travel
-                                   // through the loop; the witness points of the winner are re-evaluated once afterwards
-  unsigned long long cand = 0ull;  // bit i: i-th GJK-type pair whose bound beats the best exact distance so far
-  float lbs[64];                   // its certified lower bound (rounded DOWN to float: still a lower bound)
+  int best_k = -1;  // only (distance, reference order, pair index) of the running minimum travel through the loop; the witness
+                    // points of the winner are re-evaluated once afterwards
+  st.cand = 0ull; st.deferred = 0ull;
   int gi = 0;
   for (int grp = 0; grp < m.ngroup; ++grp) {
     const int ja = m.group_ja[grp], jb = m.group_jb[grp];
@@ -646,10 +661,10 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
         if (d < best.d || (d == best.d && id < best.id)) { best.d = d; best.id = id; best_k = k; }
       } else {
         const double lb = pair_lower_bound(A, Bp);
-        if (lb <= best.d) cand |= 1ull << gi;
+        if (lb <= best.d) st.cand |= 1ull << gi;
         float lf = (float)lb;
         if ((double)lf > lb) lf = lf - fabsf(lf) * 1.2e-7f - 1e-30f;
-        lbs[gi] = lf;
+        st.lbs[gi] = lf;
         ++gi;
       }
     }
@@ -664,38 +679,58 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
     const PairResult r = closed_form_distance(A, Bp);
     best.ja = ja; best.jb = jb; best.pa = r.pa; best.pb = r.pb;
   }
-  // GJK pass, best first: every thread resolves ITS most promising candidate (smallest lower bound) first, so that
-  // the improving minimum culls most of the others before they cost a GJK run (and the warp's lanes stay in step)
-  unsigned long long deferred = 0ull;
-  while (cand) {
-    int bit = -1;
-    float blb = 3.0e38f;
-    for (unsigned long long rem = cand; rem; rem &= rem - 1ull) {
+}
+
+// the most promising live candidate (smallest lower bound), removed from the candidate set; -1: none can still win
+// (ties with the running minimum are resolved by the exact re-test in narrow_gjk_item)
+DRC_HD int narrow_pick(NarrowState& st) {
+  int bit = -1;
+  float blb = 3.0e38f;
+  for (unsigned long long rem = st.cand; rem; rem &= rem - 1ull) {
 #if defined(__CUDA_ARCH__)
-      const int i = __ffsll((long long)rem) - 1;
+    const int i = __ffsll((long long)rem) - 1;
 #else
-      int i = 0;
-      while (!((rem >> i) & 1ull)) ++i;
+    int i = 0;
+    while (!((rem >> i) & 1ull)) ++i;
 #endif
-      if (lbs[i] < blb) { blb = lbs[i]; bit = i; }
-    }
-    if ((double)blb > best.d) break;  // no remaining candidate can win (ties are resolved by the exact re-test below)
-    cand &= ~(1ull << bit);
+    if (st.lbs[i] < blb) { blb = st.lbs[i]; bit = i; }
+  }
+  if (bit < 0 || (double)blb > st.best.d) { st.cand = 0ull; return -1; }
+  st.cand &= ~(1ull << bit);
+  return bit;
+}
+
+DRC_HD void narrow_gjk_item(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io, int b, int bit,
+                            double best_d, GjkItemResult& res) {
+  const int k = m.gjk_pair[bit];
+  const int ga = G.pair_a[k], gb = G.pair_b[k];
+  const int ja = G.parent[ga], jb = G.parent[gb];
+  const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
+  const Mat3 Rab = tmul(FA.R, FB.R);
+  const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+  const Prim A = place_prim(G, ga, Rab, pab, true), Bp = place_prim(G, gb, Rab, pab, false);
+  res.state = 0;
+  if (pair_lower_bound(A, Bp) > best_d) return;
+  GjkOut g;
+  gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
+  res.state = g.intersect ? 2 : 1;
+  res.d = g.dist; res.pa = g.pa; res.pb = g.pb;
+}
+
+DRC_HD void narrow_apply(const DrcModelDev& m, const GeomTable& G, NarrowState& st, int bit, const GjkItemResult& res) {
+  if (res.state == 2) st.deferred |= 1ull << bit;
+  else if (res.state == 1) {
     const int k = m.gjk_pair[bit];
     const int ga = G.pair_a[k], gb = G.pair_b[k];
-    const int ja = G.parent[ga], jb = G.parent[gb];
-    const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
-    const Mat3 Rab = tmul(FA.R, FB.R);
-    const Vec3 pab = tmul(FA.R, FB.p - FA.p);
-    const Prim A = place_prim(G, ga, Rab, pab, true), Bp = place_prim(G, gb, Rab, pab, false);
-    if (pair_lower_bound(A, Bp) > best.d) continue;
-    GjkOut g;
-    gjk_distance(A, Bp, prm.gjk_tol, prm.gjk_max_iter, g);
-    if (g.intersect) deferred |= 1ull << bit;
-    else consider(best, g.dist, G.pair_id[k], ja, jb, g.pa, g.pb);
+    consider(st.best, res.d, G.pair_id[k], G.parent[ga], G.parent[gb], res.pa, res.pb);
   }
-  if (deferred) {
-    io.cand_mask[b] = deferred;
+}
+
+template <int NV, bool CHAIN>
+DRC_HD void narrow_finish(const DrcModelDev& m, const DrcParams& prm, const CollisionIO& io, int b, const NarrowState& st) {
+  const BestPair& best = st.best;
+  if (st.deferred) {
+    io.cand_mask[b] = st.deferred;
     io.epa_flag[b] = 1;
     if (io.epa_list) {
 #if defined(__CUDA_ARCH__)
@@ -713,6 +748,18 @@ DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcPar
   }
   io.epa_flag[b] = 0;
   collision_finish<NV, CHAIN>(m, prm, io, b, best);
+}
+
+template <int NV, bool CHAIN>
+DRC_HD void collision_job(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io, int b) {
+  NarrowState st;
+  narrow_closed_phase<NV, CHAIN>(m, io, b, st);
+  for (int bit = narrow_pick(st); bit >= 0; bit = narrow_pick(st)) {
+    GjkItemResult res;
+    narrow_gjk_item(m, G, prm, io, b, bit, st.best.d, res);
+    narrow_apply(m, G, st, bit, res);
+  }
+  narrow_finish<NV, CHAIN>(m, prm, io, b, st);
 }
 
 // EPA pass: only robots flagged by collision_job.

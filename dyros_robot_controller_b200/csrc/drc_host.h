@@ -121,10 +121,16 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
 
 // dispatch on the compile-time robot shape; extend the list to add robots (serial chains of 7 / 6 revolute joints:
 // FR3 class, UR5e class)
+#ifdef DRC_DEV_FR3_ONLY  // kernel development builds (build.py --dev): half the compile time
+#define DRC_DISPATCH_NV(nv, chain, CALL)                                         \
+  if ((nv) == 7 && (chain)) { constexpr int NV = 7; constexpr bool CHAIN = true; CALL; } \
+  else return fail(DRC_E_UNSUPPORTED, "development build: 7-dof serial chains only");
+#else
 #define DRC_DISPATCH_NV(nv, chain, CALL)                                         \
   if ((nv) == 7 && (chain)) { constexpr int NV = 7; constexpr bool CHAIN = true; CALL; } \
   else if ((nv) == 6 && (chain)) { constexpr int NV = 6; constexpr bool CHAIN = true; CALL; } \
   else return fail(DRC_E_UNSUPPORTED, "no kernel instantiation for this robot (dof / topology)");
+#endif
 
 template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
