@@ -38,7 +38,7 @@ SYMBOLS = [
     "drc_last_error", "drc_version", "drc_device_count",
     "drc_model_create_from_urdf", "drc_model_create_from_text", "drc_model_destroy", "drc_model_dof",
     "drc_model_frame_id", "drc_model_num_frames", "drc_model_frame_name", "drc_model_joint_name", "drc_model_limits",
-    "drc_model_info", "drc_model_verbose",
+    "drc_model_info", "drc_model_mesh_info", "drc_model_verbose",
     "drc_ctx_create", "drc_ctx_destroy", "drc_ctx_get_params", "drc_ctx_set_params", "drc_ctx_max_batch",
     "drc_ctx_synchronize", "drc_ctx_stream",
     "drc_batch_update_state", "drc_batch_get_frame", "drc_batch_get_dynamics", "drc_batch_get_manipulability",

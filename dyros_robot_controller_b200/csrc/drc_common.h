@@ -29,7 +29,7 @@ constexpr int kMaxPair = 512;  // enabled collision pairs
 constexpr int kMaxGroup = 64;  // (jointA, jointB) groups of pairs
 
 enum JointType : int { kRevolute = 0, kPrismatic = 1 };
-enum GeomType : int { kSphere = 0, kCylinder = 1, kBox = 2, kCapsule = 3 };
+enum GeomType : int { kSphere = 0, kCylinder = 1, kBox = 2, kCapsule = 3, kConvex = 4 };  // kConvex: convex hull of a mesh (vertex set)
 enum DriveType : int { kNoBase = -1, kDifferential = 0, kMecanum = 1, kCaster = 2 };
 
 // QP solver / formulation constants.  Defaults are the reference's hard-coded values
@@ -66,6 +66,11 @@ struct GeomTable {
   double p[kMaxGeom][3];
   unsigned char pair_a[kMaxPair], pair_b[kMaxPair];  // geometry indices of the enabled pairs, sorted by group
   short pair_id[kMaxPair];                           // index in the reference's pair order (tie-break)
+  // mesh collision geometry (robot_data.cpp:24-34, packages_path branch): the convex hull's vertices, in the geometry's own
+  // frame about its placement point `p`; `hull` is host memory in the host model and device memory in a context's copy
+  double brad[kMaxGeom];                             // bounding radius about p (every type)
+  int vert_off[kMaxGeom], vert_n[kMaxGeom];          // kConvex: vertices hull[3*vert_off ..], vert_n of them
+  const double* hull;
 };
 
 // Flat, fixed-topology robot model.  Passed to kernels BY VALUE as a __grid_constant__ parameter

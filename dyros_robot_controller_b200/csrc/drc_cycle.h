@@ -519,8 +519,10 @@ DRC_HD Prim place_prim(const GeomTable& G, int g, const Mat3& R, Vec3 p, bool id
   const Vec3 al = v3(G.R[g][2], G.R[g][5], G.R[g][8]);
   if (identity) { s.c = cl; s.a = al; }
   else { s.c = mul(R, cl) + p; s.a = mul(R, al); }
-  if (s.type == kBox) s.R = identity ? mat3_from(G.R[g]) : mul(R, mat3_from(G.R[g]));
+  if (s.type == kBox || s.type == kConvex) s.R = identity ? mat3_from(G.R[g]) : mul(R, mat3_from(G.R[g]));
   else s.R = identity3();
+  s.verts = nullptr; s.nvert = 0;
+  if (s.type == kConvex) { s.verts = G.hull + 3 * G.vert_off[g]; s.nvert = G.vert_n[g]; s.r = G.brad[g]; }
   return s;
 }
 

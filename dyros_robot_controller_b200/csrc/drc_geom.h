@@ -20,7 +20,9 @@ struct Prim {
   Vec3 hb;       // box half extents
   Vec3 c;        // centre
   Vec3 a;        // cylinder / capsule axis (unit); box: unused
-  Mat3 R;        // box orientation (only valid for boxes)
+  Mat3 R;        // box / convex orientation (only valid for those)
+  const double* verts;  // convex: hull vertices in the shape's frame (about c), nvert of them; r = bounding radius
+  int nvert;
 };
 
 struct PairResult {
@@ -134,6 +136,16 @@ DRC_HD Vec3 support(const Prim& S, Vec3 d) {
       const Vec3 dl = tmul(S.R, d);
       return mul(S.R, v3(dl.x >= 0 ? S.hb.x : -S.hb.x, dl.y >= 0 ? S.hb.y : -S.hb.y, dl.z >= 0 ? S.hb.z : -S.hb.z)) + S.c;
     }
+    case kConvex: {  // convex hull of a mesh: the vertex furthest along d (brute force over the hull's vertex set)
+      const Vec3 dl = tmul(S.R, d);
+      int bi = 0;
+      double bv = -1e300;
+      for (int i = 0; i < S.nvert; ++i) {
+        const double t = dl.x * S.verts[3 * i] + dl.y * S.verts[3 * i + 1] + dl.z * S.verts[3 * i + 2];
+        if (t > bv) { bv = t; bi = i; }
+      }
+      return mul(S.R, v3(S.verts[3 * bi], S.verts[3 * bi + 1], S.verts[3 * bi + 2])) + S.c;
+    }
     case kCylinder: {
       // radial part of d, orthogonalised twice: for d (nearly) along the axis the first difference is rounding noise
       // with an axial component, which would push the rim point out of the cylinder by up to r
@@ -156,6 +168,7 @@ DRC_HD Vec3 support(const Prim& S, Vec3 d) {
 DRC_HD double support_width(const Prim& S, Vec3 n) {  // max over the shape of n.(x - c), |n| = 1
   switch (S.type) {
     case kSphere: return S.r;
+    case kConvex: return S.r;  // bounding radius: an upper bound of the width keeps the pair bound a certified lower bound
     case kBox: {
       const Vec3 dl = tmul(S.R, n);
       return S.hb.x * fabs(dl.x) + S.hb.y * fabs(dl.y) + S.hb.z * fabs(dl.z);
@@ -171,10 +184,11 @@ DRC_HD double support_width(const Prim& S, Vec3 n) {  // max over the shape of n
 // Certified lower bound of the signed distance between two convex primitives, at least one of
 // which is a cylinder (the other a cylinder, capsule or box).
 DRC_HD double pair_lower_bound(const Prim& A, const Prim& B) {
-  // inner segments (a box is reduced to its centre with its circumscribed radius)
-  const double hA = A.type == kBox ? 0.0 : A.h, hB = B.type == kBox ? 0.0 : B.h;
+  // inner segments (a box / a convex hull / a sphere is reduced to its centre with its circumscribed radius)
+  const bool blobA = A.type == kBox || A.type == kConvex || A.type == kSphere, blobB = B.type == kBox || B.type == kConvex || B.type == kSphere;
+  const double hA = blobA ? 0.0 : A.h, hB = blobB ? 0.0 : B.h;
   const double rA = A.type == kBox ? norm(A.hb) : A.r, rB = B.type == kBox ? norm(B.hb) : B.r;
-  const Vec3 aA = A.type == kBox ? v3(0, 0, 1) : A.a, aB = B.type == kBox ? v3(0, 0, 1) : B.a;
+  const Vec3 aA = blobA ? v3(0, 0, 1) : A.a, aB = blobB ? v3(0, 0, 1) : B.a;
   double s, t;
   segment_segment(A.c - hA * aA, (2 * hA) * aA, B.c - hB * aB, (2 * hB) * aB, s, t);
   const Vec3 pA = A.c + ((2 * s - 1) * hA) * aA, pB = B.c + ((2 * t - 1) * hB) * aB;
@@ -473,6 +487,7 @@ DRC_HD_NOINLINE void epa_penetration(const Prim& A, const Prim& B, const GjkOut&
 
 // ---------------------------------------------------------------- exact closed-form dispatcher
 DRC_HD bool has_closed_form(int ta, int tb) {
+  if (ta == kConvex || tb == kConvex) return false;  // mesh hulls always go through GJK / EPA
   return ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule);
 }
 DRC_HD PairResult closed_form_distance(const Prim& A, const Prim& B) {

@@ -45,6 +45,8 @@ constexpr int kPrioIters = 300;         // previous-tick iteration count from wh
 
 struct drc_ctx {
   const drc_model* model;
+  DrcModelDev mdev;   // the model as the kernels of THIS context get it: a snapshot taken at creation, mesh hull vertices in device memory
+  double* hull_dev;
   int device, cap;
   DrcParams prm;
   cudaStream_t stream;
@@ -136,7 +138,7 @@ template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
   constexpr int threads = 64;
   const int blocks = (io.B + threads - 1) / threads;
-  k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
+  k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->mdev, c->prm, fr, io);
   c->launches++;
   CU(cudaGetLastError());
   return DRC_OK;
@@ -155,7 +157,7 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   const int blocks = (io.B + threads - 1) / threads;
   // (register budgets of 168 / 128 registers were measured too: 3 blocks/SM is slower, 4 blocks/SM saves 0.1 ms here and loses it
   // again in the ADMM stage -- profiles/README.md)
-  k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->model->hm.dev, c->prm, io);
+  k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
   CU(cudaGetLastError());
   // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it
   // on the side stream, concurrently with the state / QP-build kernel (disjoint parts of the QP record), and join
@@ -167,7 +169,7 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
     es = c->side;
   }
   const int epa_blocks = scp ? 16 : c->sm_count;
-  k_collision_epa<NV, CHAIN><<<epa_blocks, kEpaWarps * 32, 0, es>>>(c->model->hm.dev, c->prm, io);
+  k_collision_epa<NV, CHAIN><<<epa_blocks, kEpaWarps * 32, 0, es>>>(c->mdev, c->prm, io);
   CU(cudaGetLastError());
   if (epa_on_side_stream) CU(cudaEventRecord(c->ev_epa, c->side));
   c->launches += 2;

@@ -204,7 +204,7 @@ static int run_rollout(drc_ctx* c, int B, int T, double dt, double* q, double* q
       cb.s12 = lay(layout, 12, B); cb.s6 = lay(layout, 6, B); cb.t = t_start + k * dt; cb.t0 = t0; cb.dur = duration; cb.x_des = x_des; cb.xdot_des = xd_des;
     }
     if (sched) { io.order = c->order; io.offs = offs_next; io.prev = k > 0 ? c->prev_iters : nullptr; }
-    k_tick_front<NV, CHAIN><<<(B + kTickThreads - 1) / kTickThreads, kTickThreads, 0, s>>>(c->model->hm.dev, c->prm, fr, io);
+    k_tick_front<NV, CHAIN><<<(B + kTickThreads - 1) / kTickThreads, kTickThreads, 0, s>>>(c->mdev, c->prm, fr, io);
     c->launches++;
     CU(cudaGetLastError());
     SolveIO sio;
@@ -239,6 +239,7 @@ static int finish_model(std::unique_ptr<drc_model>& m, drc_model_t** out) {
     v += line;
   }
   m->verbose = v;
+  m->hm.bind_hull();
   *out = m.release();
   return DRC_OK;
 }
@@ -252,8 +253,11 @@ int drc_model_create_from_text(const char* urdf_text, const char* srdf_text, drc
     return fail(DRC_E_PARSE, e.what());
   }
 }
+static std::string dir_of(const std::string& path) {
+  const size_t sl = path.find_last_of('/');
+  return sl == std::string::npos ? std::string(".") : path.substr(0, sl);
+}
 int drc_model_create_from_urdf(const char* urdf_path, const char* srdf_path, const char* packages_path, drc_model_t** out) {
-  (void)packages_path;
   if (!urdf_path || !out) return fail(DRC_E_INVALID, "null argument");
   std::string urdf, srdf;
   try {
@@ -264,7 +268,17 @@ int drc_model_create_from_urdf(const char* urdf_path, const char* srdf_path, con
   if (srdf_path && srdf_path[0]) {
     try { srdf = read_text_file(srdf_path); } catch (const std::exception&) { srdf.clear(); }  // all pairs stay enabled
   }
-  return drc_model_create_from_text(urdf.c_str(), srdf.c_str(), out);
+  try {
+    // mesh collision elements: package:// under packages_path (robot_data.cpp:24-28), relative names next to the URDF
+    MeshSource ms;
+    ms.urdf_dir = dir_of(urdf_path);
+    ms.packages_path = packages_path ? packages_path : "";
+    std::unique_ptr<drc_model> m(new drc_model);
+    m->hm = compile_model(urdf, srdf, ms);
+    return finish_model(m, out);
+  } catch (const std::exception& e) {
+    return fail(DRC_E_PARSE, e.what());
+  }
 }
 void drc_model_destroy(drc_model_t* m) { delete m; }
 int drc_model_dof(const drc_model_t* m) { return m ? m->hm.dev.nv : DRC_E_INVALID; }
@@ -292,12 +306,24 @@ int drc_model_info(const drc_model_t* m, int* s) {
   s[0] = d.nv; s[1] = d.ngeom; s[2] = d.npair; s[3] = d.ngroup; s[4] = (int)m->hm.frames.size(); s[5] = m->hm.skipped_geoms;
   return DRC_OK;
 }
+int drc_model_mesh_info(const drc_model_t* m, int* s) {
+  if (!m || !s) return fail(DRC_E_INVALID, "null argument");
+  s[0] = m->hm.mesh_geoms; s[1] = (int)m->hm.hull.size() / 3;
+  return DRC_OK;
+}
 const char* drc_model_verbose(const drc_model_t* m) { return m ? m->verbose.c_str() : ""; }
 
 // ------------------------------------------------------------------------------------------------ context
 // allocations of drc_ctx_create; on any failure the caller releases whatever was created so far (drc_ctx_destroy skips nulls)
 static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max_batch) {
   c->model = m; c->device = device; c->cap = max_batch;
+  c->mdev = m->hm.dev;
+  c->mdev.geom.hull = nullptr;
+  if (!m->hm.hull.empty()) {  // mesh hull vertices (kConvex geometry) live in device memory of this context's GPU
+    CU(cudaMalloc((void**)&c->hull_dev, m->hm.hull.size() * sizeof(double)));
+    CU(cudaMemcpy(c->hull_dev, m->hm.hull.data(), m->hm.hull.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->mdev.geom.hull = c->hull_dev;
+  }
   c->prm = DrcParams();
   for (int i = 0; i < kMaxV; ++i) { c->prm.Kp_joint[i] = 400; c->prm.Kv_joint[i] = 40; }
   const int n = m->hm.dev.nv;
@@ -411,6 +437,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   double* ds[] = {c->c_q, c->c_qd, c->c_oMi, c->c_M, c->c_Minv, c->c_g, c->c_nle, c->qp, c->col_dist, c->col_wit, c->stage,
                   c->c_Mact, c->c_Minvact, c->c_gact, c->c_nleact};
   for (double* p : ds) if (p) cudaFree(p);
+  if (c->hull_dev) cudaFree(c->hull_dev);
   if (c->epa_flag) cudaFree(c->epa_flag);
   if (c->cand_mask) cudaFree(c->cand_mask);
   if (c->col_pair) cudaFree(c->col_pair);

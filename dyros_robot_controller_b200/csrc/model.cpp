@@ -11,6 +11,7 @@
 #include <sstream>
 #include <stdexcept>
 
+#include "mesh_hull.h"
 #include "xml_mini.h"
 
 namespace drc {
@@ -81,6 +82,7 @@ Tf origin_of(const xml::Node* parent) {
 
 struct Builder {
   HostModel hm;
+  MeshSource meshes;
   std::map<std::string, const xml::Node*> links;
   std::map<std::string, std::vector<const xml::Node*>> child_joints;
   // accumulated body inertia about each joint origin
@@ -126,7 +128,7 @@ struct Builder {
       const xml::Node* geo = c->child("geometry");
       if (!geo || geo->children.empty()) continue;
       const xml::Node* g = geo->children[0].get();
-      int type;
+      int type = -1;
       double prm[3] = {0, 0, 0};
       if (g->tag == "sphere") { type = kSphere; prm[0] = number(g, "radius", 0, true); }
       else if (g->tag == "cylinder") { type = kCylinder; prm[0] = number(g, "radius", 0, true); prm[1] = 0.5 * number(g, "length", 0, true); }
@@ -136,11 +138,34 @@ struct Builder {
         if (s.size() != 3) throw std::runtime_error("urdf: malformed <box size>");
         type = kBox;
         for (int a = 0; a < 3; ++a) prm[a] = 0.5 * s[a];
-      } else { ++hm.skipped_geoms; continue; }  // meshes: SURVEY 8(f) rank 4
+      }
+      mesh::Hull hull;
+      if (g->tag == "mesh") {  // the convex hull of the mesh's vertices
+        const std::string path = mesh::resolve(g->attr_or("filename", ""), meshes.urdf_dir, meshes.packages_path);
+        std::vector<double> pts = mesh::read_vertices(path, read_text_file(path));
+        std::vector<double> sc = numbers(g->attr_or("scale", "1 1 1"));
+        if (sc.size() != 3) throw std::runtime_error("urdf: malformed <mesh scale>");
+        for (size_t i = 0; i < pts.size(); ++i) pts[i] *= sc[i % 3];
+        hull = mesh::convex_hull(pts);
+        type = kConvex;
+        ++hm.mesh_geoms;
+      } else if (g->tag != "sphere" && g->tag != "cylinder" && g->tag != "capsule" && g->tag != "box") { ++hm.skipped_geoms; continue; }
       DrcModelDev& d = hm.dev;
       if (d.ngeom >= kMaxGeom) throw std::runtime_error("urdf: too many collision primitives (max 64)");
-      const Tf Tg = tf_mul(T, origin_of(c));
+      Tf Tg = tf_mul(T, origin_of(c));
       const int gi = d.ngeom++;
+      d.geom.vert_off[gi] = 0; d.geom.vert_n[gi] = 0;
+      if (type == kConvex) {  // vertices are kept about the hull's box centre: move the placement point there
+        double off[3];
+        rot_apply(Tg.R, hull.centre, off);
+        for (int a = 0; a < 3; ++a) Tg.p[a] += off[a];
+        d.geom.vert_off[gi] = (int)hm.hull.size() / 3;
+        d.geom.vert_n[gi] = (int)hull.verts.size() / 3;
+        hm.hull.insert(hm.hull.end(), hull.verts.begin(), hull.verts.end());
+        prm[0] = hull.radius;
+      }
+      d.geom.brad[gi] = type == kSphere ? prm[0] : type == kCylinder ? std::sqrt(prm[0] * prm[0] + prm[1] * prm[1])
+                        : type == kCapsule ? prm[0] + prm[1] : type == kBox ? std::sqrt(prm[0] * prm[0] + prm[1] * prm[1] + prm[2] * prm[2]) : hull.radius;
       d.geom.type[gi] = type;
       d.geom.parent[gi] = j;
       std::memcpy(d.geom.prm[gi], prm, sizeof prm);
@@ -200,10 +225,11 @@ std::string read_text_file(const std::string& path) {
   return ss.str();
 }
 
-HostModel compile_model(const std::string& urdf_text, const std::string& srdf_text) {
+HostModel compile_model(const std::string& urdf_text, const std::string& srdf_text, const MeshSource& meshes) {
   std::unique_ptr<xml::Node> root = xml::parse(urdf_text);
   if (root->tag != "robot") throw std::runtime_error("urdf: root element is not <robot>");
   Builder B;
+  B.meshes = meshes;
   std::memset(&B.hm.dev, 0, sizeof(DrcModelDev));
   B.hm.name = root->attr_or("name", "");
   std::vector<std::string> order;
@@ -264,10 +290,10 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
       if (disabled.count({B.geom_link[i], B.geom_link[j]})) continue;
       pairs.push_back({i, j, id++});
       const int ta = d.geom.type[i], tb = d.geom.type[j];
-      if (!(ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule))) ++ngjk;
+      if (!has_closed_form(ta, tb)) ++ngjk;
     }
   if ((int)pairs.size() > kMaxPair) throw std::runtime_error("model: too many collision pairs (max 512)");
-  if (ngjk > 64) throw std::runtime_error("model: more than 64 collision pairs need GJK (cylinder/box vs cylinder/box)");
+  if (ngjk > 64) throw std::runtime_error("model: more than 64 collision pairs need GJK (cylinder / box / mesh hull against each other)");
   // group by (parent joint A, parent joint B), stable in reference order
   std::stable_sort(pairs.begin(), pairs.end(), [&](const P& x, const P& y) {
     const int xa = d.geom.parent[x.a], xb = d.geom.parent[x.b], ya = d.geom.parent[y.a], yb = d.geom.parent[y.b];
@@ -291,8 +317,9 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
   d.ngjk = 0;
   for (int k = 0; k < d.npair; ++k) {
     const int ta = d.geom.type[d.geom.pair_a[k]], tb = d.geom.type[d.geom.pair_b[k]];
-    if (!(ta == kSphere || tb == kSphere || (ta == kCapsule && tb == kCapsule))) d.gjk_pair[d.ngjk++] = (unsigned short)k;
+    if (!has_closed_form(ta, tb)) d.gjk_pair[d.ngjk++] = (unsigned short)k;
   }
+  B.hm.bind_hull();
   return B.hm;
 }
 

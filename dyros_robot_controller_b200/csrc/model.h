@@ -25,15 +25,23 @@ struct HostModel {
   std::vector<std::string> geom_names;
   std::vector<double> effort;
   bool chain = true;  // parent[i] == i-1 for every joint
-  int skipped_geoms = 0;  // mesh collision elements (out of scope)
+  int skipped_geoms = 0;  // collision elements that are not geometry this library knows (none of the URDF primitive / mesh tags)
+  int mesh_geoms = 0;     // <mesh> collision elements, turned into convex hulls (kConvex)
+  std::vector<double> hull;  // their hull vertices (xyz triples, geometry frame); dev.geom.hull points here on the host
+  void bind_hull() { dev.geom.hull = hull.empty() ? nullptr : hull.data(); }  // call after the model has reached its final address
   int frame_id(const std::string& n) const {
     for (size_t i = 0; i < frames.size(); ++i) if (frames[i].name == n) return (int)i;
     return -1;
   }
 };
 
+// Where <mesh filename="..."> collision elements are looked up (robot_data.cpp:24-34): `package://` under packages_path,
+// relative names under the URDF's directory.
+struct MeshSource {
+  std::string urdf_dir, packages_path;
+};
 // Throws std::runtime_error with a readable message on malformed or unsupported input.
-HostModel compile_model(const std::string& urdf_text, const std::string& srdf_text);
+HostModel compile_model(const std::string& urdf_text, const std::string& srdf_text, const MeshSource& meshes = MeshSource());
 
 // Mobile-base extension (reference MobileManipulator::RobotData ctor, mobile_manipulator/robot_data.cpp:7-44
 // and Mobile::RobotData, mobile/robot_data.cpp:7-32,138-177).

@@ -15,6 +15,7 @@ struct Node {
   std::string tag;
   std::vector<std::pair<std::string, std::string>> attrs;
   std::vector<std::unique_ptr<Node>> children;
+  std::string text;  // character data directly inside the element (COLLADA float arrays; unused by URDF / SRDF)
 
   const std::string* attr(const std::string& k) const {
     for (auto& a : attrs) if (a.first == k) return &a.second;
@@ -115,6 +116,7 @@ class Parser {
     for (;;) {
       size_t lt = s_.find('<', i_);
       if (lt == std::string::npos) throw std::runtime_error("xml: missing </" + n->tag + ">");
+      if (lt > i_) n->text.append(s_, i_, lt - i_);
       i_ = lt;
       if (starts("<!--")) { skip_until("-->"); continue; }
       if (starts("<![CDATA[")) { skip_until("]]>"); continue; }

@@ -53,7 +53,10 @@ class Model:
         self.dof = lib().drc_model_dof(h)
         s = (C.c_int * 6)()
         check(lib().drc_model_info(h, s), "drc_model_info")
-        self.info = dict(dof=s[0], geoms=s[1], pairs=s[2], groups=s[3], frames=s[4], skipped_meshes=s[5])
+        self.info = dict(dof=s[0], geoms=s[1], pairs=s[2], groups=s[3], frames=s[4], skipped_geoms=s[5], skipped_meshes=0)
+        s2 = (C.c_int * 2)()
+        check(lib().drc_model_mesh_info(h, s2), "drc_model_mesh_info")
+        self.info.update(mesh_geoms=s2[0], hull_vertices=s2[1])
         n = self.dof
         lo, hi, vl, ef = (np.zeros(n) for _ in range(4))
         check(lib().drc_model_limits(h, lo.ctypes.data_as(_D), hi.ctypes.data_as(_D), vl.ctypes.data_as(_D),

@@ -65,7 +65,11 @@ int drc_device_count(void);
 /* ---- model: replaces Manipulator::RobotData::RobotData (src/manipulator/robot_data.cpp:7-70), i.e.
  * pinocchio::urdf::buildModel/buildGeom + addAllCollisionPairs + srdf::removeCollisionPairs.  A missing
  * URDF is an error code here (the reference calls std::exit, :15-19); a missing SRDF enables every pair
- * (:45-49).  packages_path is accepted for signature parity; mesh collision geometry is not supported. */
+ * (:45-49).  <mesh> collision elements (:24-34): `package://pkg/file` is looked up under packages_path, other names next
+ * to the URDF; STL / OBJ / DAE vertices become the mesh's CONVEX HULL (GJK / EPA support set) -- exact for convex meshes,
+ * a lower bound of the distance for non-convex ones (hpp-fcl walks the triangles of a BVH model).  A mesh that cannot be
+ * read is an error code.  drc_model_create_from_text has no file context: relative mesh names resolve against the
+ * working directory and package:// names are errors. */
 int drc_model_create_from_urdf(const char* urdf_path, const char* srdf_path, const char* packages_path,
                                drc_model_t** out);
 int drc_model_create_from_text(const char* urdf_text, const char* srdf_text, drc_model_t** out);
@@ -77,8 +81,10 @@ const char* drc_model_frame_name(const drc_model_t* m, int frame);
 const char* drc_model_joint_name(const drc_model_t* m, int joint);
 /* getJointPositionLimit / getJointVelocityLimit (robot_data.cpp:59-62); any pointer may be NULL */
 int drc_model_limits(const drc_model_t* m, double* q_lo, double* q_hi, double* v_lim, double* effort);
-/* sizes: [0] dof [1] collision primitives [2] enabled pairs [3] link-pair groups [4] frames [5] skipped meshes */
+/* sizes: [0] dof [1] collision geometries [2] enabled pairs [3] link-pair groups [4] frames [5] skipped (unknown) geometry tags */
 int drc_model_info(const drc_model_t* m, int* sizes6);
+/* mesh collision geometry: [0] geometries built from <mesh> elements [1] hull vertices kept in total */
+int drc_model_mesh_info(const drc_model_t* m, int* sizes2);
 /* getVerbose() (robot_data.cpp:72-89); returns a string owned by the model */
 const char* drc_model_verbose(const drc_model_t* m);
 

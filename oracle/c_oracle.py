@@ -69,8 +69,8 @@ def pose44(p12) -> np.ndarray:
 class Oracle:
     """CPU restatement of the reference hot path for one robot model."""
 
-    def __init__(self, urdf_path: str, srdf_path: str = "", threads: int = 1):
-        self.model = m = urdf_model.load(urdf_path, srdf_path)
+    def __init__(self, urdf_path: str, srdf_path: str = "", threads: int = 1, packages_path: str = ""):
+        self.model = m = urdf_model.load(urdf_path, srdf_path, packages_path)
         self.nv = m.nv
         L = lib()
         self._keep = [_c(m.parent, np.int32), _c(m.jtype, np.int32), _c(m.axis), _c(m.jR), _c(m.jp), _c(m.mass),
@@ -85,6 +85,9 @@ class Oracle:
             C.c_int(len(m.pairs)), _i(k[19]), _d(k[20])))
         if not self.h:
             raise RuntimeError("orc_model_create failed")
+        if len(m.hull):  # mesh collision geometry: hull vertices per geometry
+            hv, ho, hn = _c(m.hull), _c(m.hull_off, np.int32), _c(m.hull_n, np.int32)
+            L.orc_model_set_hulls(self.h, C.c_int(len(hv)), _d(hv), _i(ho), _i(hn))
         self.set_threads(threads)
 
     def __del__(self):

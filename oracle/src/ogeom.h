@@ -16,7 +16,15 @@ struct Shape {
   int type;
   V3 prm;  // sphere: r | cylinder/capsule: r, half length (axis = local z) | box: half extents
   SE3 T;   // world placement
+  const double* verts = nullptr;  // GEOM_CONVEX: hull vertices (geometry frame), nvert of them
+  int nvert = 0;
 };
+inline Shape make_shape(const Model& m, int g, const SE3& T) {
+  Shape s;
+  s.type = m.geom_type[g]; s.prm = m.geom_param[g]; s.T = T;
+  if (s.type == GEOM_CONVEX) { s.verts = m.hull.data() + 3 * m.hull_off[g]; s.nvert = m.hull_n[g]; }
+  return s;
+}
 struct DistResult {
   double d;
   V3 pa, pb;
@@ -137,6 +145,15 @@ inline V3 support(const Shape& S, const V3& d) {
     case GEOM_BOX:
       s = V3(dl.x >= 0 ? S.prm.x : -S.prm.x, dl.y >= 0 ? S.prm.y : -S.prm.y, dl.z >= 0 ? S.prm.z : -S.prm.z);
       break;
+    case GEOM_CONVEX: {  // mesh hull: the vertex furthest along the direction
+      double bv = -1e300;
+      for (int i = 0; i < S.nvert; ++i) {
+        const V3 v(S.verts[3 * i], S.verts[3 * i + 1], S.verts[3 * i + 2]);
+        const double t = dot(dl, v);
+        if (t > bv) { bv = t; s = v; }
+      }
+      break;
+    }
     case GEOM_CYLINDER: {
       double sg = std::sqrt(dl.x * dl.x + dl.y * dl.y);
       double k = sg > 0 ? S.prm.x / sg : 0.0;
@@ -430,7 +447,8 @@ inline DistResult epa(const Shape& A, const Shape& B, const GjkResult& g, const 
 inline DistResult swap_ab(DistResult r) { std::swap(r.pa, r.pb); return r; }
 
 inline DistResult shape_distance(const Shape& A, const Shape& B, const GeomParams& gp) {
-  if (A.type == GEOM_SPHERE) {
+  const bool hull = A.type == GEOM_CONVEX || B.type == GEOM_CONVEX;  // mesh hulls: always GJK / EPA
+  if (!hull && A.type == GEOM_SPHERE) {
     switch (B.type) {
       case GEOM_SPHERE: return sphere_sphere(A.T.p, A.prm.x, B.T.p, B.prm.x);
       case GEOM_CYLINDER: return sphere_cylinder(A.T.p, A.prm.x, B.T, B.prm.x, B.prm.y);
@@ -438,7 +456,7 @@ inline DistResult shape_distance(const Shape& A, const Shape& B, const GeomParam
       default: return sphere_capsule(A.T.p, A.prm.x, B.T, B.prm.x, B.prm.y);
     }
   }
-  if (B.type == GEOM_SPHERE) return swap_ab(shape_distance(B, A, gp));
+  if (!hull && B.type == GEOM_SPHERE) return swap_ab(shape_distance(B, A, gp));
   if (A.type == GEOM_CAPSULE && B.type == GEOM_CAPSULE)
     return capsule_capsule(A.T, A.prm.x, A.prm.y, B.T, B.prm.x, B.prm.y);
   GjkResult g = gjk(A, B, gp);
@@ -468,11 +486,7 @@ inline void min_distance(const Model& m, const State& s, bool with_grad, bool wi
   for (int i = 0; i < MAXV; ++i) out.grad[i] = out.grad_dot[i] = 0;
   // updateGeometryPlacements
   std::vector<Shape> sh(m.ng);
-  for (int g = 0; g < m.ng; ++g) {
-    sh[g].type = m.geom_type[g];
-    sh[g].prm = m.geom_param[g];
-    sh[g].T = m.geom_parent[g] < 0 ? m.geom_place[g] : s.oMi[m.geom_parent[g]] * m.geom_place[g];
-  }
+  for (int g = 0; g < m.ng; ++g) sh[g] = make_shape(m, g, m.geom_parent[g] < 0 ? m.geom_place[g] : s.oMi[m.geom_parent[g]] * m.geom_place[g]);
   DistResult best;
   for (size_t k = 0; k < m.pair_a.size(); ++k) {
     DistResult r = shape_distance(sh[m.pair_a[k]], sh[m.pair_b[k]], gp);

@@ -84,6 +84,13 @@ OrcHandle* orc_model_create(int nv, const int* parent, const int* jtype, const d
   for (int k = 0; k < npairs; ++k) { m.pair_a.push_back(pairs[2 * k]); m.pair_b.push_back(pairs[2 * k + 1]); }
   return h;
 }
+// mesh geometry (GEOM_CONVEX): hull vertices per geometry, from the Python loader (scipy / Qhull)
+void orc_model_set_hulls(OrcHandle* h, int nvert_total, const double* verts, const int* off, const int* n) {
+  Model& m = h->m;
+  m.hull.assign(verts, verts + 3 * (size_t)nvert_total);
+  m.hull_off.assign(off, off + m.ng);
+  m.hull_n.assign(n, n + m.ng);
+}
 void orc_model_destroy(OrcHandle* h) { delete h; }
 void orc_set_threads(OrcHandle* h, int t) { h->threads = t > 0 ? t : 1; }
 void orc_set_fresh_workspace(OrcHandle* h, int on) { h->fresh_workspace = on != 0; }
@@ -178,12 +185,9 @@ void orc_pair_distances(OrcHandle* h, const double* q, double* d_out, double* pa
   std::vector<double> qd(m.nv, 0.0);
   update_state(m, s, q, qd.data());
   for (size_t k = 0; k < m.pair_a.size(); ++k) {
-    Shape A, Bs;
     int ga = m.pair_a[k], gb = m.pair_b[k];
-    A.type = m.geom_type[ga]; A.prm = m.geom_param[ga];
-    A.T = m.geom_parent[ga] < 0 ? m.geom_place[ga] : s.oMi[m.geom_parent[ga]] * m.geom_place[ga];
-    Bs.type = m.geom_type[gb]; Bs.prm = m.geom_param[gb];
-    Bs.T = m.geom_parent[gb] < 0 ? m.geom_place[gb] : s.oMi[m.geom_parent[gb]] * m.geom_place[gb];
+    Shape A = make_shape(m, ga, m.geom_parent[ga] < 0 ? m.geom_place[ga] : s.oMi[m.geom_parent[ga]] * m.geom_place[ga]);
+    Shape Bs = make_shape(m, gb, m.geom_parent[gb] < 0 ? m.geom_place[gb] : s.oMi[m.geom_parent[gb]] * m.geom_place[gb]);
     DistResult r = shape_distance(A, Bs, h->gp);
     d_out[k] = r.d;
     if (pa) { pa[3 * k] = r.pa.x; pa[3 * k + 1] = r.pa.y; pa[3 * k + 2] = r.pa.z; }

@@ -13,7 +13,7 @@ namespace orc {
 
 constexpr int MAXV = 16;
 enum { JOINT_REVOLUTE = 0, JOINT_PRISMATIC = 1 };
-enum { GEOM_SPHERE = 0, GEOM_CYLINDER = 1, GEOM_BOX = 2, GEOM_CAPSULE = 3 };
+enum { GEOM_SPHERE = 0, GEOM_CYLINDER = 1, GEOM_BOX = 2, GEOM_CAPSULE = 3, GEOM_CONVEX = 4 };
 
 struct Motion { V3 lin, ang; };
 struct Force { V3 lin, ang; };
@@ -90,6 +90,8 @@ struct Model {
   std::vector<int> geom_type, geom_parent;
   std::vector<V3> geom_param;
   std::vector<SE3> geom_place;
+  std::vector<double> hull;             // GEOM_CONVEX: hull vertices of mesh geometry (xyz triples, geometry frame)
+  std::vector<int> hull_off, hull_n;   // per geometry: first vertex / vertex count
   std::vector<int> pair_a, pair_b;
   // mobile-manipulator extension (filled by orc_model_set_moma)
   int drive_type = -1;  // 0 differential, 1 mecanum, 2 caster

@@ -28,6 +28,8 @@ import xml.etree.ElementTree as ET
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+from pathlib import Path
+
 import numpy as np
 
 GEOM_SPHERE, GEOM_CYLINDER, GEOM_BOX, GEOM_CAPSULE = 0, 1, 2, 3
@@ -93,7 +95,59 @@ class FlatModel:
         return self.frame_names.index(name) if name in self.frame_names else -1
 
 
-def load(urdf_path: str, srdf_path: str = "") -> FlatModel:
+
+GEOM_CONVEX = 4
+
+
+def resolve_mesh(filename: str, urdf_dir: str, packages_path: str) -> str:
+    """package://pkg/rest -> packages_path/pkg/rest; file://abs; otherwise relative to the URDF (pinocchio's lookup)."""
+    if filename.startswith("package://"):
+        return str(Path(packages_path) / filename[len("package://"):])
+    if filename.startswith("file://"):
+        return filename[len("file://"):]
+    return filename if filename.startswith("/") else str(Path(urdf_dir) / filename)
+
+
+def read_mesh_vertices(path: str) -> np.ndarray:
+    """(n,3) vertex coordinates of an STL (binary / ASCII), OBJ or COLLADA file."""
+    raw = Path(path).read_bytes()
+    ext = path.rsplit(".", 1)[-1].lower()
+    if ext == "stl":
+        if len(raw) >= 84:
+            n = int(np.frombuffer(raw[80:84], "<u4")[0])
+            if len(raw) == 84 + 50 * n:
+                rec = np.frombuffer(raw[84:], np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+                return rec["v"].reshape(-1, 3).astype(np.float64)
+        tok = raw.decode(errors="ignore").split()
+        v = [tok[i + 1:i + 4] for i, t in enumerate(tok) if t == "vertex"]
+        return np.array(v, np.float64)
+    if ext == "obj":
+        v = [ln.split()[1:4] for ln in raw.decode(errors="ignore").splitlines() if ln.startswith("v ")]
+        return np.array(v, np.float64)
+    if ext == "dae":
+        root = ET.fromstring(raw)
+        strip = lambda t: t.split("}")[-1]
+        unit = 1.0
+        out = []
+        src = {}
+        for el in root.iter():
+            tag = strip(el.tag)
+            if tag == "unit" and el.get("meter"):
+                unit = float(el.get("meter"))
+            if tag == "source":
+                fa = [c for c in el if strip(c.tag) == "float_array"]
+                if fa and fa[0].text:
+                    src[el.get("id")] = np.array(fa[0].text.split(), np.float64)
+        for el in root.iter():
+            if strip(el.tag) == "vertices":
+                for inp in el:
+                    if strip(inp.tag) == "input" and inp.get("semantic") == "POSITION":
+                        out.append(src[inp.get("source").lstrip("#")].reshape(-1, 3))
+        return unit * np.concatenate(out)
+    raise ValueError(f"unsupported mesh format: {path}")
+
+
+def load(urdf_path: str, srdf_path: str = "", packages_path: str = "") -> FlatModel:
     root = ET.parse(urdf_path).getroot()
     links = {l.get("name"): l for l in root.findall("link")}
     link_order = [l.get("name") for l in root.findall("link")]
@@ -112,6 +166,8 @@ def load(urdf_path: str, srdf_path: str = "") -> FlatModel:
     qlo, qhi, vl, ef = [], [], [], []
     fn, fpar, fR, fp = [], [], [], []
     gn, gl, gt, gpar_, gparam, gR, gp = [], [], [], [], [], [], []
+    hull_pts, hull_off = [], {}
+    urdf_dir = str(Path(urdf_path).resolve().parent)
 
     def add_body(jidx, R, p, link):
         """Lump `link`'s inertia (placed at (R,p) in joint jidx's frame) into that joint's body."""
@@ -147,8 +203,17 @@ def load(urdf_path: str, srdf_path: str = "") -> FlatModel:
                 t, prm = GEOM_BOX, list(0.5 * s)
             elif g.tag == "capsule":
                 t, prm = GEOM_CAPSULE, [float(g.get("radius")), 0.5 * float(g.get("length")), 0]
+            elif g.tag == "mesh":
+                # robot_data.cpp:24-34 (buildGeom with packages_path): the mesh's vertices -> convex hull (scipy / Qhull here,
+                # independent of the product's GJK-based hull selection); vertices stay in the mesh's own frame
+                pts = read_mesh_vertices(resolve_mesh(g.get("filename"), urdf_dir, packages_path)) * _vec(g.get("scale"), 3, 1.0)
+                from scipy.spatial import ConvexHull
+                hv = pts[ConvexHull(pts).vertices]
+                t, prm = GEOM_CONVEX, [float(np.linalg.norm(hv, axis=1).max()), 0, 0]
+                hull_off[len(gn)] = (len(hull_pts), len(hv))
+                hull_pts.extend(hv.tolist())
             else:
-                continue  # meshes are out of scope
+                continue
             gn.append(f"{lname}_{k}"); gl.append(lname); gt.append(t); gparam.append(prm)
             gpar_.append(jidx); gR.append(R @ Rc); gp.append(R @ pc + p)
 
@@ -211,6 +276,9 @@ def load(urdf_path: str, srdf_path: str = "") -> FlatModel:
     m.geom_R = np.array(gR).reshape(ng, 3, 3)
     m.geom_p = np.array(gp).reshape(ng, 3)
     m.gravity = np.array([0.0, 0.0, -9.81])
+    m.hull = np.array(hull_pts, np.float64).reshape(-1, 3)
+    m.hull_off = np.array([hull_off.get(g, (0, 0))[0] for g in range(ng)], np.int32)
+    m.hull_n = np.array([hull_off.get(g, (0, 0))[1] for g in range(ng)], np.int32)
 
     disabled = set()
     if srdf_path:

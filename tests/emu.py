@@ -18,6 +18,7 @@ def lib():
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
         _LIB = C.CDLL(str(_HERE / "libdrc_emu.so"))
         _LIB.emu_create.restype = C.c_void_p
+        _LIB.emu_create2.restype = C.c_void_p
         _LIB.emu_shape_distance.restype = C.c_double
         _LIB.emu_pair_lower_bound.restype = C.c_double
     return _LIB
@@ -36,12 +37,12 @@ def _c(a, dt=np.float64):
 
 
 class Emu:
-    def __init__(self, urdf_path: str, srdf_path: str = ""):
+    def __init__(self, urdf_path: str, srdf_path: str = "", packages_path: str = ""):
         L = lib()
         urdf = Path(urdf_path).read_text()
         srdf = Path(srdf_path).read_text() if srdf_path else ""
         err = C.create_string_buffer(512)
-        h = L.emu_create(urdf.encode(), srdf.encode(), err, 512)
+        h = L.emu_create2(urdf.encode(), srdf.encode(), str(Path(urdf_path).resolve().parent).encode(), str(packages_path).encode(), err, 512)
         if not h:
             raise RuntimeError(err.value.decode())
         self.h = C.c_void_p(h)
@@ -63,6 +64,15 @@ class Emu:
         nbytes = lib().emu_model_sizes(self.h, _i(out))
         return dict(nv=int(out[0]), ngeom=int(out[1]), npair=int(out[2]), ngroup=int(out[3]), nframes=int(out[4]),
                     skipped=int(out[5]), dev_bytes=int(nbytes))
+
+    def mesh_info(self):
+        ng = self.sizes()["ngeom"]
+        out, vn = np.zeros(2, np.int32), np.zeros(ng, np.int32)
+        lib().emu_mesh_info(self.h, _i(out), _i(vn), None)
+        hull = np.zeros((int(out[1]), 3))
+        if out[1]:
+            lib().emu_mesh_info(self.h, _i(out), _i(vn), _d(hull))
+        return dict(mesh_geoms=int(out[0]), hull_vertices=int(out[1]), vert_n=vn, hull=hull)
 
     def model_arrays(self):
         s = self.sizes()

@@ -72,16 +72,23 @@ static void run_solve(const EmuHandle* h, const SolveIO& io, unsigned unit_mask)
 
 extern "C" {
 
-EmuHandle* emu_create(const char* urdf_text, const char* srdf_text, char* err, int errlen) {
+// urdf_dir / packages_path: where <mesh> collision elements are looked up (may be null)
+EmuHandle* emu_create2(const char* urdf_text, const char* srdf_text, const char* urdf_dir, const char* packages_path, char* err, int errlen) {
   try {
     std::unique_ptr<EmuHandle> h(new EmuHandle);
-    h->hm = compile_model(urdf_text, srdf_text ? srdf_text : "");
+    MeshSource ms;
+    ms.urdf_dir = urdf_dir ? urdf_dir : ""; ms.packages_path = packages_path ? packages_path : "";
+    h->hm = compile_model(urdf_text, srdf_text ? srdf_text : "", ms);
+    h->hm.bind_hull();
     for (int i = 0; i < kMaxV; ++i) { h->prm.Kp_joint[i] = 400; h->prm.Kv_joint[i] = 40; }
     return h.release();
   } catch (const std::exception& e) {
     if (err && errlen > 0) { std::strncpy(err, e.what(), errlen - 1); err[errlen - 1] = 0; }
     return nullptr;
   }
+}
+EmuHandle* emu_create(const char* urdf_text, const char* srdf_text, char* err, int errlen) {
+  return emu_create2(urdf_text, srdf_text, nullptr, nullptr, err, errlen);
 }
 void emu_destroy(EmuHandle* h) { delete h; }
 int emu_nv(EmuHandle* h) { return h->hm.dev.nv; }
@@ -91,6 +98,13 @@ int emu_model_sizes(EmuHandle* h, int* out) {
   const DrcModelDev& d = h->hm.dev;
   out[0] = d.nv; out[1] = d.ngeom; out[2] = d.npair; out[3] = d.ngroup; out[4] = (int)h->hm.frames.size(); out[5] = h->hm.skipped_geoms;
   return (int)sizeof(DrcModelDev);
+}
+// mesh geometry: out[0] = mesh geometries, out[1] = hull vertices in total; per geometry vertex counts in vert_n (ngeom ints);
+// hull (optional): the vertices (3 * out[1] doubles, geometry frames about the placement points)
+void emu_mesh_info(EmuHandle* h, int* out, int* vert_n, double* hull) {
+  out[0] = h->hm.mesh_geoms; out[1] = (int)h->hm.hull.size() / 3;
+  for (int g = 0; g < h->hm.dev.ngeom; ++g) vert_n[g] = h->hm.dev.geom.vert_n[g];
+  if (hull) std::copy(h->hm.hull.begin(), h->hm.hull.end(), hull);
 }
 // flat copy of the compiled model for comparison with the oracle's independent loader
 void emu_model_arrays(EmuHandle* h, int* parent, int* jtype, double* axis, double* jR, double* jp, double* mass, double* com,

@@ -226,6 +226,7 @@ FcHandle* fc_create(const char* urdf_text, const char* srdf_text) {
   try {
     std::unique_ptr<FcHandle> h(new FcHandle);
     h->hm = compile_model(urdf_text, srdf_text ? srdf_text : "");
+    h->hm.bind_hull();
     for (int i = 0; i < kMaxV; ++i) { h->prm.Kp_joint[i] = 400; h->prm.Kv_joint[i] = 40; }
     return h.release();
   } catch (const std::exception& e) {
