@@ -50,8 +50,8 @@ def stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False, only: str | None = None, defines: tuple = ()) -> Path:
     """Compile every translation unit for sm_100a (in parallel), link libdrc_b200.so in-tree.
-    `only` / `defines` are for kernel development (python -m ...build --dev): recompile ONE translation unit (the other objects
-    are reused as they are -- valid while the shared struct layouts are unchanged), optionally with -DDRC_DEV_FR3_ONLY (7-dof
+    `only` / `defines` are for kernel development (python -m ...build --dev): recompile everything but drc_moma.cu (its object
+    is reused as it is -- valid while the shared struct layouts are unchanged), optionally with -DDRC_DEV_FR3_ONLY (7-dof
     instantiations only).  Such a build leaves the source hash stale, so the next plain build() is a full one."""
     if not force and not only and not stale():
         return LIB
@@ -64,8 +64,8 @@ def build(force: bool = False, verbose: bool = False, only: str | None = None, d
 
     def compile_one(src: Path) -> Path:
         obj = OBJDIR / (src.stem + ".o")
-        if only and src.stem != only and obj.exists():
-            return obj
+        if only and src.stem == "drc_moma" and only != "drc_moma" and obj.exists():
+            return obj   # the slow unit that kernel development on the manipulator path does not touch
         cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-c", "-o", str(obj), str(src)]
         if verbose:
             print(" ".join(cmd), flush=True)

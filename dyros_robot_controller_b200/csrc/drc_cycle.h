@@ -492,6 +492,9 @@ struct CollisionIO {
   unsigned long long* cand_mask;     // per robot: bit i = GJK-type pair i must be resolved by EPA
   int* epa_list; int* epa_count;     // compacted list of flagged robots (device: atomic append), may be null
   const int* count;                  // number of slots in use (device memory; null = B)
+  // hand-over from the closed-form kernel to the GJK kernel (device, split narrow phase): winner's pair index, candidate
+  // lower bounds [i][Bc]; the running minimum travels in dist / pair_out / witness, the candidate set in cand_mask
+  int* nar_k; float* nar_lb;
 };
 
 struct JointFrame {
@@ -641,7 +644,7 @@ struct GjkItemResult {
 };
 
 template <int NV, bool CHAIN>
-DRC_HD void narrow_closed_phase(const DrcModelDev& m, const CollisionIO& io, int b, NarrowState& st) {
+DRC_HD void narrow_closed_phase(const DrcModelDev& m, const CollisionIO& io, int b, NarrowState& st, int* best_k_out = nullptr) {
   BestPair& best = st.best;
   best.d = 1e300; best.id = 1 << 30; best.ja = -1; best.jb = -1; best.pa = v3(0, 0, 0); best.pb = v3(0, 0, 0);
   int best_k = -1;  // only (distance, reference order, pair index) of the running minimum travel through the loop; the witness
@@ -653,19 +656,31 @@ DRC_HD void narrow_closed_phase(const DrcModelDev& m, const CollisionIO& io, int
     const JointFrame FA = load_joint_frame(io.c_oMi, io.Bc, b, ja), FB = load_joint_frame(io.c_oMi, io.Bc, b, jb);
     const Mat3 Rab = tmul(FA.R, FB.R);
     const Vec3 pab = tmul(FA.R, FB.p - FA.p);
+    int placed = -1;  // pairs are sorted by the second geometry inside a group: it is placed once for all its partners
+    Prim Bp;
     for (int t = 0; t < m.group_count[grp]; ++t) {
       const int k = m.group_first[grp] + t;
       const int ga = m.geom.pair_a[k], gb = m.geom.pair_b[k];
-      const Prim A = place_prim(m.geom, ga, Rab, pab, true), Bp = place_prim(m.geom, gb, Rab, pab, false);
-      if (has_closed_form(A.type, Bp.type)) {
+      if (gb != placed) { Bp = place_prim(m.geom, gb, Rab, pab, false); placed = gb; }
+      const int ta = m.geom.type[ga];
+      if (has_closed_form(ta, Bp.type)) {
+        const Prim A = place_prim(m.geom, ga, Rab, pab, true);
         const double d = closed_form_distance(A, Bp).d;
         const int id = m.geom.pair_id[k];
         if (d < best.d || (d == best.d && id < best.id)) { best.d = d; best.id = id; best_k = k; }
       } else {
-        const double lb = pair_lower_bound(A, Bp);
-        if (lb <= best.d) st.cand |= 1ull << gi;
-        float lf = (float)lb;
-        if ((double)lf > lb) lf = lf - fabsf(lf) * 1.2e-7f - 1e-30f;
+        // bounding spheres first: a pair whose spheres are further apart than the running minimum cannot win, now or later (the
+        // minimum only decreases) -- it is no candidate, and the costlier certified bound is skipped
+        const Vec3 dc = Bp.c - v3(m.geom.p[ga][0], m.geom.p[ga][1], m.geom.p[ga][2]);
+        const double reach = best.d + m.geom.brad[ga] + m.geom.brad[gb];
+        float lf = 3.0e38f;
+        if (!(reach >= 0.0 && dot(dc, dc) > reach * reach * (1.0 + 1e-12))) {
+          const Prim A = place_prim(m.geom, ga, Rab, pab, true);
+          const double lb = pair_lower_bound(A, Bp);
+          if (lb <= best.d) st.cand |= 1ull << gi;
+          lf = (float)lb;
+          if ((double)lf > lb) lf = lf - fabsf(lf) * 1.2e-7f - 1e-30f;
+        }
         st.lbs[gi] = lf;
         ++gi;
       }
@@ -681,6 +696,7 @@ DRC_HD void narrow_closed_phase(const DrcModelDev& m, const CollisionIO& io, int
     const PairResult r = closed_form_distance(A, Bp);
     best.ja = ja; best.jb = jb; best.pa = r.pa; best.pb = r.pb;
   }
+  if (best_k_out) *best_k_out = best_k;
 }
 
 // the most promising live candidate (smallest lower bound), removed from the candidate set; -1: none can still win

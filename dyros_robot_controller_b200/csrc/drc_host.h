@@ -38,6 +38,7 @@ struct Scratch {
   double* qp;
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
+  int* nar_k; float* nar_lb;   // split narrow phase: hand-over from the closed-form kernel to the GJK kernel
 };
 constexpr int kPrioSlots = 2048;        // capacity of the priority sub-batch
 constexpr int kPrioMinBatch = 8192;     // batches below this run as one pipeline
@@ -61,6 +62,7 @@ struct drc_ctx {
   int qp_stride_max;
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
+  int* nar_k; float* nar_lb;
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
   double* roll; int* roll_i;             // rollout scratch (cubic profile; next tick's schedule histogram / offsets / ticket), allocated on first use
   int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
@@ -109,6 +111,7 @@ static Scratch main_scratch(const drc_ctx* c) {
   sc.c_q = c->c_q; sc.c_qd = c->c_qd; sc.c_oMi = c->c_oMi; sc.c_M = c->c_M; sc.c_Minv = c->c_Minv; sc.c_g = c->c_g; sc.c_nle = c->c_nle;
   sc.Bc = c->cap; sc.qp = c->qp; sc.epa_flag = c->epa_flag; sc.cand_mask = c->cand_mask; sc.col_dist = c->col_dist;
   sc.col_pair = c->col_pair; sc.col_wit = c->col_wit; sc.epa_list = c->epa_list; sc.epa_count = c->epa_count;
+  sc.nar_k = c->nar_k; sc.nar_lb = c->nar_lb;
   return sc;
 }
 static void bind_scratch(const Scratch& sc, JobIO& io) {
@@ -157,8 +160,12 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   const int blocks = (io.B + threads - 1) / threads;
   // (register budgets of 168 / 128 registers were measured too: 3 blocks/SM is slower, 4 blocks/SM saves 0.1 ms here and loses it
   // again in the ADMM stage -- profiles/README.md)
-  k_collision<NV, CHAIN, 2><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
+  io.nar_k = sc.nar_k; io.nar_lb = sc.nar_lb;
+  k_collision_closed<NV, CHAIN><<<blocks, threads, 0, s>>>(c->mdev, io);
   CU(cudaGetLastError());
+  k_collision<NV, CHAIN, true, 2><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
+  CU(cudaGetLastError());
+  c->launches++;
   // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it
   // on the side stream, concurrently with the state / QP-build kernel (disjoint parts of the QP record), and join
   // before the ADMM launch (join_epa).

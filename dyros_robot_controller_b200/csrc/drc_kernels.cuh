@@ -39,13 +39,30 @@ struct NarrowBlockSmem {
   double best_d[T];
   GjkItemResult res[T];
 };
-template <int NV, bool CHAIN, int T>
+template <int NV, bool CHAIN, int T, bool LOAD>
 static __device__ __forceinline__ void collision_block(const DrcModelDev& m, const GeomTable& G, const DrcParams& prm, const CollisionIO& io,
                                                        int b0, bool valid, NarrowBlockSmem<T>& S) {
   const int tid = threadIdx.x;
   NarrowState st;
   st.cand = 0ull;
-  if (valid) narrow_closed_phase<NV, CHAIN>(m, io, b0 + tid, st);
+  if (valid) {
+    if (LOAD) {  // the closed-form stage ran in its own launch (k_collision_closed): pick its result up
+      const int b = b0 + tid;
+      BestPair& best = st.best;
+      best.d = io.dist[b]; best.id = io.pair_out[b];
+      best.pa = v3(io.witness[6 * b + 0], io.witness[6 * b + 1], io.witness[6 * b + 2]);
+      best.pb = v3(io.witness[6 * b + 3], io.witness[6 * b + 4], io.witness[6 * b + 5]);
+      const int k = io.nar_k[b];
+      best.ja = k >= 0 ? m.geom.parent[m.geom.pair_a[k]] : -1; best.jb = k >= 0 ? m.geom.parent[m.geom.pair_b[k]] : -1;
+      st.cand = io.cand_mask[b]; st.deferred = 0ull;
+      for (unsigned long long rem = st.cand; rem; rem &= rem - 1ull) {
+        const int i = __ffsll((long long)rem) - 1;
+        st.lbs[i] = io.nar_lb[(long long)i * io.Bc + b];
+      }
+    } else {
+      narrow_closed_phase<NV, CHAIN>(m, io, b0 + tid, st);
+    }
+  }
   for (;;) {
     const int bit = valid ? narrow_pick(st) : -1;
     if (bit >= 0) {
@@ -68,7 +85,24 @@ static __device__ __forceinline__ void collision_block(const DrcModelDev& m, con
 }
 
 constexpr int kColThreads = 128;
-template <int NV, bool CHAIN, int MINB = 2>
+// The narrow phase as TWO launches: the closed-form stage is straight-line FP64 code that lives on latency hiding -- on its own it
+// fits a 128-register budget (16 warps / SM instead of the 8 the GJK code's 255 registers allow); the GJK stage + gradients follow.
+template <int NV, bool CHAIN>
+__global__ void __launch_bounds__(kColThreads, 4) k_collision_closed(const __grid_constant__ DrcModelDev m, const __grid_constant__ CollisionIO io) {
+#ifndef DRC_SYNTAX_CHECK
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!(b < io.B && (!io.count || b < *io.count))) return;
+  NarrowState st;
+  int best_k;
+  narrow_closed_phase<NV, CHAIN>(m, io, b, st, &best_k);
+  io.dist[b] = st.best.d; io.pair_out[b] = st.best.id; io.nar_k[b] = best_k;
+  io.witness[6 * b + 0] = st.best.pa.x; io.witness[6 * b + 1] = st.best.pa.y; io.witness[6 * b + 2] = st.best.pa.z;
+  io.witness[6 * b + 3] = st.best.pb.x; io.witness[6 * b + 4] = st.best.pb.y; io.witness[6 * b + 5] = st.best.pb.z;
+  io.cand_mask[b] = st.cand;
+  for (int i = 0; i < m.ngjk; ++i) io.nar_lb[(long long)i * io.Bc + b] = st.lbs[i];
+#endif
+}
+template <int NV, bool CHAIN, bool LOAD, int MINB = 2>
 __global__ void __launch_bounds__(kColThreads, MINB) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ CollisionIO io) {
 #ifndef DRC_SYNTAX_CHECK
@@ -83,7 +117,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_collision(const __grid_co
   }
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  collision_block<NV, CHAIN, kColThreads>(m, G, prm, io, blockIdx.x * blockDim.x, b < io.B && (!io.count || b < *io.count), S);
+  collision_block<NV, CHAIN, kColThreads, LOAD>(m, G, prm, io, blockIdx.x * blockDim.x, b < io.B && (!io.count || b < *io.count), S);
 #endif
 }
 // ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar
@@ -476,7 +510,7 @@ __global__ void __launch_bounds__(kTickThreads) k_tick_front(const __grid_consta
     if (io.cubic.B > 0) task_cubic_job(io.cubic, b);
     robot_job<NV, CHAIN, F_STORE>(m, prm, frame, io.job, b);
   }
-  collision_block<NV, CHAIN, kTickThreads>(m, G, prm, io.col, blockIdx.x * blockDim.x, valid, S);
+  collision_block<NV, CHAIN, kTickThreads, false>(m, G, prm, io.col, blockIdx.x * blockDim.x, valid, S);
   if (valid) {
     if (io.col.epa_flag[b]) flagged[atomicAdd(&n_flag, 1)] = b;
     robot_job<NV, CHAIN, F_FROM_CACHE | F_QPIK | F_STEP>(m, prm, frame, io.job, b);

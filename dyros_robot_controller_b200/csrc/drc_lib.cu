@@ -356,6 +356,8 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
   CU(dalloc(&c->col_dist, B));
   CU(cudaMalloc((void**)&c->col_pair, B * sizeof(int)));
   CU(dalloc(&c->col_wit, 6 * B));
+  CU(cudaMalloc((void**)&c->nar_k, B * sizeof(int)));
+  CU(cudaMalloc((void**)&c->nar_lb, 64 * B * sizeof(float)));
   CU(cudaMalloc((void**)&c->epa_list, B * sizeof(int)));
   CU(cudaMalloc((void**)&c->epa_count, sizeof(int)));
   CU(cudaMalloc((void**)&c->prev_iters, B * sizeof(int)));
@@ -375,6 +377,8 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
       CU(dalloc(&p.col_dist, P));
       CU(cudaMalloc((void**)&p.col_pair, P * sizeof(int)));
       CU(dalloc(&p.col_wit, 6 * P));
+      CU(cudaMalloc((void**)&p.nar_k, P * sizeof(int)));
+      CU(cudaMalloc((void**)&p.nar_lb, 64 * P * sizeof(float)));
       CU(cudaMalloc((void**)&p.epa_list, P * sizeof(int)));
       CU(cudaMalloc((void**)&p.epa_count, sizeof(int)));
       return DRC_OK;
@@ -441,6 +445,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->epa_flag) cudaFree(c->epa_flag);
   if (c->cand_mask) cudaFree(c->cand_mask);
   if (c->col_pair) cudaFree(c->col_pair);
+  if (c->nar_k) cudaFree(c->nar_k);
+  if (c->nar_lb) cudaFree(c->nar_lb);
   if (c->epa_list) cudaFree(c->epa_list);
   if (c->epa_count) cudaFree(c->epa_count);
   if (c->prev_iters) cudaFree(c->prev_iters);
@@ -453,7 +459,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     for (Scratch* sp : {&c->prio}) {
       Scratch& p = *sp;
       void* ps[] = {p.c_q, p.c_qd, p.c_oMi, p.c_M, p.c_Minv, p.c_g, p.c_nle, p.qp, p.epa_flag, p.cand_mask, p.col_dist, p.col_pair, p.col_wit,
-                    p.epa_list, p.epa_count};
+                    p.epa_list, p.epa_count, p.nar_k, p.nar_lb};
       for (void* q : ps) if (q) cudaFree(q);
     }
     if (c->prio_stream) { cudaStreamSynchronize(c->prio_stream); cudaStreamDestroy(c->prio_stream); }

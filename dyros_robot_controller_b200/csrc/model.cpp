@@ -295,9 +295,12 @@ HostModel compile_model(const std::string& urdf_text, const std::string& srdf_te
   if ((int)pairs.size() > kMaxPair) throw std::runtime_error("model: too many collision pairs (max 512)");
   if (ngjk > 64) throw std::runtime_error("model: more than 64 collision pairs need GJK (cylinder / box / mesh hull against each other)");
   // group by (parent joint A, parent joint B), stable in reference order
+  // ... and inside a group by the second geometry, so that the narrow phase places it once for all its partners
   std::stable_sort(pairs.begin(), pairs.end(), [&](const P& x, const P& y) {
     const int xa = d.geom.parent[x.a], xb = d.geom.parent[x.b], ya = d.geom.parent[y.a], yb = d.geom.parent[y.b];
-    return xa != ya ? xa < ya : xb < yb;
+    if (xa != ya) return xa < ya;
+    if (xb != yb) return xb < yb;
+    return x.b < y.b;
   });
   d.npair = (int)pairs.size();
   d.ngroup = 0;
