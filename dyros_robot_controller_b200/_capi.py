@@ -30,6 +30,7 @@ class DrcParams(C.Structure):
         ("gjk_max_iter", C.c_int), ("epa_max_iter", C.c_int), ("pinv_threshold", C.c_double),
         ("schedule_hint", C.c_int),
         ("rollout_fused", C.c_int),
+        ("rollout_warm_start", C.c_int),
     ]
 
 

@@ -133,7 +133,8 @@ if __name__ == "__main__":
     if "--check" in sys.argv:
         check()
     elif "--dev" in sys.argv:
-        build(force=True, verbose="-v" in sys.argv, only="drc_lib", defines=("DRC_DEV_FR3_ONLY",))
+        extra = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+        build(force=True, verbose="-v" in sys.argv, only="drc_lib", defines=("DRC_DEV_FR3_ONLY",) + extra)
         print("dev build (drc_lib.cu, 7-dof instantiations only)", LIB)
     else:
         build(force="--force" in sys.argv, verbose=True)

@@ -55,6 +55,9 @@ struct DrcParams {
   int schedule_hint = 1;
   // closed-loop rollouts: 0 = the multi-stream pipeline of the fused cycle per tick (fastest), 1 = two launches per tick (k_tick_front + k_admm)
   int rollout_fused = 0;
+  // closed-loop rollouts: 1 = warm start every tick's QP from the previous tick's primal / dual solution (osqp_warm_start
+  // semantics).  An extension: the reference never warm starts (fresh solver per cycle, QP_base.h:146), so 0 = its iterates.
+  int rollout_warm_start = 0;
 };
 
 // Collision primitives (kept as one block so a kernel can stage it into shared memory).

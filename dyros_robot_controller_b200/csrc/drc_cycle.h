@@ -837,17 +837,23 @@ struct SolveIO {
   double* roll_q; double* roll_qd; Strided sroll; double roll_dt;
   int* fail_ticks; int* iters_total;
   int* hist_next; int* offs_next; int* sched_ticket;   // next tick's schedule (device only, see k_admm)
+  // optional warm start (rollouts with drc_params_t::rollout_warm_start): a previous solve's qp_x / qp_y, indexed by robot
+  const double* warm_x; const double* warm_y;
 };
 
 template <class Cfg, bool ID, class W>
 DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpOptions& o) {
-  admm_solve<Cfg>(w, io.qp, robots, o);
+  WarmStart ws;
+  ws.x = io.warm_x; ws.y = io.warm_y; ws.ids = io.out_ids;
+  admm_solve<Cfg>(w, io.qp, robots, o, ws);
   DRC_PHASE(PH_QP_EMIT);
   w.each([&](Lane<Cfg>& L, GroupShared<Cfg>& S) {
     const int slot = S.robot;  // index of the QP record / state-cache entry
     if (slot < 0) return;
     const long long b = io.out_ids ? io.out_ids[slot] : slot;  // robot index in the output arrays
     const bool ok = S.status == kQpSolved;
+    // warm-started rollouts: an infeasible / non-convex solve leaves zeros, i.e. the next tick of that robot starts cold
+    const double wk = (!io.warm_x || S.status == kQpSolved || S.status == kQpMaxIter || S.status == kQpSolvedInaccurate) ? 1.0 : 0.0;
     if (L.gl == 0) {
       if (io.status) io.status[b] = S.status;
       if (io.iters) io.iters[b] = S.iters;
@@ -859,8 +865,8 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
     constexpr int NY = Cfg::NC * (1 + 2 * Cfg::KU) + 2 * Cfg::NR;
     double* yr = io.qp_y ? io.qp_y + (long long)b * NY : nullptr;
     // OSQP unscale_solution: y = E y_scaled / c, y_scaled = rho (v - Proj(v))
-    auto dual_row = [&](int k) { return S.cinv * C.E[k] * (L.rho_r * (L.b[k].v - proj_row(L, L.b[k].v, L.b[k].l))); };
-    auto dual_sb = [&](int k) { return S.cinv * C.Eb[k] * (L.rho_b * (L.b[k].vb - proj_sb(L, L.b[k].vb))); };
+    auto dual_row = [&](int k) { return wk * S.cinv * C.E[k] * (L.rho_r * (L.b[k].v - proj_row(L, L.b[k].v, L.b[k].l))); };
+    auto dual_sb = [&](int k) { return wk * S.cinv * C.Eb[k] * (L.rho_b * (L.b[k].vb - proj_sb(L, L.b[k].vb))); };
     if (L.is_core) {
       const int j = L.gl;
       const double xc = C.D * L.x;
@@ -874,12 +880,12 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
       } else if (io.out2) io.out2[b * io.sout2.sb + j * io.sout2.sk] = ok ? xc : 0.0;
       if (io.qp_x) {
         double* xr = io.qp_x + (long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR);
-        xr[j] = xc;
+        xr[j] = wk * xc;
 #pragma unroll
-        for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = C.has_sing[k] ? C.Dd[k] * L.b[k].xd : 0.0;
+        for (int k = 0; k < Cfg::KU; ++k) xr[Cfg::NC * (1 + k) + j] = C.has_sing[k] ? wk * (C.Dd[k] * L.b[k].xd) : 0.0;
       }
       if (yr) {
-        yr[j] = Cfg::BOUNDS ? S.cinv * C.Ecb * (L.rhoc * (L.vc - clampd(L.vc, L.lc, L.uc))) : 0.0;
+        yr[j] = Cfg::BOUNDS ? wk * S.cinv * C.Ecb * (L.rhoc * (L.vc - clampd(L.vc, L.lc, L.uc))) : 0.0;
 #pragma unroll
         for (int k = 0; k < Cfg::KU; ++k) {
           yr[Cfg::NC * (1 + k) + j] = C.active[k] ? dual_row(k) : 0.0;
@@ -892,7 +898,7 @@ DRC_HD void solve_and_emit(W& w, const int* robots, const SolveIO& io, const QpO
         const int j = r - Cfg::ND;
         io.out[b * io.sout.sb + j * io.sout.sk] = ok ? C.Dd[0] * L.b[0].xd : io.c_g[j * io.Bc + slot];
       }
-      if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = C.has_sing[0] ? C.Dd[0] * L.b[0].xd : 0.0;
+      if (io.qp_x) io.qp_x[(long long)b * (Cfg::NC * (1 + Cfg::KU) + Cfg::NR) + Cfg::NC * (1 + Cfg::KU) + r] = C.has_sing[0] ? wk * (C.Dd[0] * L.b[0].xd) : 0.0;
       if (yr) {
         yr[Cfg::NC * (1 + 2 * Cfg::KU) + r] = dual_row(0);
         yr[Cfg::NC * (1 + 2 * Cfg::KU) + Cfg::NR + r] = C.has_sb[0] ? dual_sb(0) : 0.0;

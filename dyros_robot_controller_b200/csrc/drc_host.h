@@ -88,6 +88,8 @@ struct drc_ctx {
   double *dbg_x, *dbg_y;
   // rollout in progress (pipeline variant): every solver launch of the tick integrates the state in place and keeps the tallies
   double *roll_q, *roll_qd; Strided sroll; double roll_dt; int *roll_fail, *roll_iters;
+  // warm-started rollout in progress: previous tick's primal / dual solution per robot (structured order of SolveIO::qp_x / qp_y)
+  double *ws_x, *ws_y; bool warm_on;
 };
 static inline void mark(drc_ctx* c, const char* name, cudaStream_t s) {
   if (!c->timing || c->tr_n >= 32) return;
@@ -147,6 +149,9 @@ static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStrea
   return DRC_OK;
 }
 
+#ifndef DRC_GJK_MINB
+#define DRC_GJK_MINB 2
+#endif
 template <int NV, bool CHAIN>
 static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa_on_side_stream = false, const Scratch* scp = nullptr) {
   const Scratch sc = scp ? *scp : main_scratch(c);
@@ -163,7 +168,7 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   io.nar_k = sc.nar_k; io.nar_lb = sc.nar_lb;
   k_collision_closed<NV, CHAIN><<<blocks, threads, 0, s>>>(c->mdev, io);
   CU(cudaGetLastError());
-  k_collision<NV, CHAIN, true, 2><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
+  k_collision<NV, CHAIN, true, DRC_GJK_MINB><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
   CU(cudaGetLastError());
   c->launches++;
   // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it
@@ -229,6 +234,7 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   const int per_block = kAdmmWarps * Cfg::NG, blocks = (io.B + per_block - 1) / per_block;
   io.iters_hint = c->prev_iters;
   io.qp_x = c->dbg_x; io.qp_y = c->dbg_y;
+  if (c->warm_on && !ID) { io.qp_x = c->ws_x; io.qp_y = c->ws_y; io.warm_x = c->ws_x; io.warm_y = c->ws_y; }
   if (c->roll_q && !io.roll_q) { io.roll_q = c->roll_q; io.roll_qd = c->roll_qd; io.sroll = c->sroll; io.roll_dt = c->roll_dt; io.fail_ticks = c->roll_fail; io.iters_total = c->roll_iters; }
   // one instantiation per QP shape (register cap 65536 / (128 * 3) = 168).  The dynamic shared-memory opt-in is a per-device
   // function attribute: set it for the context's device on every launch (cheap) so that contexts on several GPUs of one

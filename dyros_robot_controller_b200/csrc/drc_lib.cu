@@ -165,6 +165,19 @@ static int run_rollout(drc_ctx* c, int B, int T, double dt, double* q, double* q
   int *hist_next = c->roll_i, *offs_next = c->roll_i + kSchedBuckets, *ticket = c->roll_i + 2 * kSchedBuckets;
   if (fail_ticks) CU(cudaMemsetAsync(fail_ticks, 0, (size_t)B * sizeof(int), s));
   if (iters_total) CU(cudaMemsetAsync(iters_total, 0, (size_t)B * sizeof(int), s));
+  // warm start (extension, drc_params_t::rollout_warm_start): the solver launches read the previous tick's (x, y) of every robot and
+  // leave this tick's there; zeros = cold start, which is how tick 0 begins
+  constexpr int NX = NV * 3 + 2, NY = NV * 5 + 4;   // QpikCfg<NV>: NC (1 + KU) + NR, NC (1 + 2 KU) + 2 NR
+  struct WarmGuard { drc_ctx* c; ~WarmGuard() { c->warm_on = false; } } warm_guard{c};
+  if (c->prm.rollout_warm_start) {
+    if (!c->ws_x) {
+      CU(cudaMalloc((void**)&c->ws_x, (size_t)c->cap * NX * sizeof(double)));
+      CU(cudaMalloc((void**)&c->ws_y, (size_t)c->cap * NY * sizeof(double)));
+    }
+    CU(cudaMemsetAsync(c->ws_x, 0, (size_t)B * NX * sizeof(double), s));
+    CU(cudaMemsetAsync(c->ws_y, 0, (size_t)B * NY * sizeof(double), s));
+    c->warm_on = true;
+  }
   if (!c->prm.rollout_fused) {
     // pipeline variant: per tick [cubic profile kernel] + the multi-stream pipeline of the fused cycle (run_qp), whose solver launches
     // (priority, main, EPA-pending) integrate the state in place -- the slow robots' solves overlap the other robots' front stages
@@ -451,6 +464,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->epa_count) cudaFree(c->epa_count);
   if (c->prev_iters) cudaFree(c->prev_iters);
   if (c->roll) cudaFree(c->roll);
+  if (c->ws_x) cudaFree(c->ws_x);
+  if (c->ws_y) cudaFree(c->ws_y);
   if (c->roll_i) cudaFree(c->roll_i);
   if (c->order) cudaFree(c->order);
   if (c->sched_hist) cudaFree(c->sched_hist);
@@ -502,7 +517,7 @@ int drc_ctx_get_params(const drc_ctx_t* c, drc_params_t* p) {
   p->check_termination = s.check_termination; p->scaling = s.scaling; p->adaptive_rho = s.adaptive_rho;
   p->adaptive_rho_interval = s.adaptive_rho_interval; p->adaptive_rho_tolerance = s.adaptive_rho_tolerance;
   p->gjk_tol = s.gjk_tol; p->epa_tol = s.epa_tol; p->gjk_max_iter = s.gjk_max_iter; p->epa_max_iter = s.epa_max_iter;
-  p->pinv_threshold = s.pinv_threshold; p->schedule_hint = s.schedule_hint; p->rollout_fused = s.rollout_fused;
+  p->pinv_threshold = s.pinv_threshold; p->schedule_hint = s.schedule_hint; p->rollout_fused = s.rollout_fused; p->rollout_warm_start = s.rollout_warm_start;
   return DRC_OK;
 }
 int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
@@ -520,7 +535,7 @@ int drc_ctx_set_params(drc_ctx_t* c, const drc_params_t* p) {
   s.check_termination = p->check_termination; s.scaling = p->scaling; s.adaptive_rho = p->adaptive_rho;
   s.adaptive_rho_interval = p->adaptive_rho_interval; s.adaptive_rho_tolerance = p->adaptive_rho_tolerance;
   s.gjk_tol = p->gjk_tol; s.epa_tol = p->epa_tol; s.gjk_max_iter = p->gjk_max_iter; s.epa_max_iter = p->epa_max_iter;
-  s.pinv_threshold = p->pinv_threshold; s.schedule_hint = p->schedule_hint; s.rollout_fused = p->rollout_fused;
+  s.pinv_threshold = p->pinv_threshold; s.schedule_hint = p->schedule_hint; s.rollout_fused = p->rollout_fused; s.rollout_warm_start = p->rollout_warm_start;
   return DRC_OK;
 }
 int drc_ctx_max_batch(const drc_ctx_t* c) { return c ? c->cap : DRC_E_INVALID; }

@@ -199,8 +199,17 @@ DRC_HD double proj_sb(const LaneT& L, double v) { return (LaneT::kHasEq && L.sb_
 // the lanes; the caller unscales what it needs (x_c[j] = D x, singleton = Dd xd with D, Dd in the
 // group's cold data) and reads status / iters from the group's shared record.
 // ------------------------------------------------------------------------------------------------
+// Optional warm start (an extension: the reference creates a fresh solver every cycle and never warm starts, QP_base.h:146).
+// OSQP's osqp_warm_start semantics: x = D^-1 x0, z = A x, y = c E^-1 y0 in the scaled problem, then ordinary iterations.
+// x0 / y0 are a previous solve's primal / dual vectors in the structured order of SolveIO::qp_x / qp_y; all zeros is the cold start.
+struct WarmStart {
+  const double* x = nullptr;   // [robot][NC (1 + KU) + NR]
+  const double* y = nullptr;   // [robot][NC (1 + 2 KU) + 2 NR]
+  const int* ids = nullptr;    // optional: QP slot -> robot index of the two arrays
+};
+
 template <class Cfg, class W>
-DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOptions& o) {
+DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOptions& o, const WarmStart& warm = WarmStart()) {
   constexpr int NC = Cfg::NC, KU = Cfg::KU, ND = Cfg::ND, NR = Cfg::NR, GL = Cfg::GL, NG = Cfg::NG, NB = Cfg::NB;
   typedef Lane<Cfg> LaneT;
   typedef GroupShared<Cfg> GS;
@@ -520,18 +529,19 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
   // ---------------------------------------------------------------- hot loop phases (branch-free)
   // phase A: u = [sigma x - q + A_local'(rho z - y) ; t_r]
   // (OSQP's cold start sets z = y = 0 without projecting: on the first iteration Proj(v) is replaced by 0)
-  auto phase_a_impl = [&](LaneT& L, GS& S, const bool first) {
+  // (warm start: z of the first iteration is the given A x0, preloaded into pzc / pz / pzb, instead of a projection)
+  auto phase_a_impl = [&](LaneT& L, GS& S, const bool first, const bool warm_first = false) {
     if (L.done) return;
-    const double pzc = first ? 0.0 : clampd(L.vc, L.lc, L.uc);
+    const double pzc = warm_first ? L.pzc : (first ? 0.0 : clampd(L.vc, L.lc, L.uc));
     L.pzc = pzc;
     double u = L.sig * L.x - L.q + L.betac * (L.rhoc * (2.0 * pzc - L.vc));
 #pragma unroll
     for (int k = 0; k < NB; ++k) {
       BundleHot& b = L.b[k];
-      const double pz = first ? 0.0 : proj_row(L, b.v, b.l), pzb = first ? 0.0 : proj_sb(L, b.vb);
+      const double pz = warm_first ? b.pz : (first ? 0.0 : proj_row(L, b.v, b.l)), pzb = warm_first ? b.pzb : (first ? 0.0 : proj_sb(L, b.vb));
       // singleton bound row: 2 Proj(vb) - vb = |vb| on [0, inf), vb on a free row (exact)
       const double wr = L.rho_r * (2.0 * pz - b.v);
-      const double wb = L.rho_b * (first ? -b.vb : ((LaneT::kHasEq && L.sb_free) ? b.vb : fabs(b.vb)));
+      const double wb = L.rho_b * (warm_first ? (2.0 * pzb - b.vb) : (first ? -b.vb : ((LaneT::kHasEq && L.sb_free) ? b.vb : fabs(b.vb))));
       const double bd = sigma * b.xd - b.qd + b.e * wr + b.beta * wb;
       b.pz = pz; b.pzb = pzb; b.bd = bd;
       u += b.c * (wr - b.gam * bd);
@@ -540,6 +550,8 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
   };
   auto phase_a = [&](LaneT& L, GS& S) { phase_a_impl(L, S, false); };
   auto phase_a_first = [&](LaneT& L, GS& S) { phase_a_impl(L, S, true); };
+  auto phase_a_warm = [&](LaneT& L, GS& S) { phase_a_impl(L, S, false, true); };
+  const bool warm_on = warm.x != nullptr;
   // phase B: s = (U S^-1 U' u)_lane, then the x / v updates
   auto phase_b = [&](LaneT& L, GS& S) {
     if (L.done) return;
@@ -612,6 +624,56 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     }
   };
 
+  // ---------------------------------------------------------------- warm start (osqp_warm_start), optional
+  if (warm_on) {
+    factor();   // the rho vector of the first factorisation is needed to place y0 in the row states
+    constexpr int NX = NC * (1 + KU) + NR, NY = NC * (1 + 2 * KU) + 2 * NR;
+    // (W1) x = D^-1 x0; the scaled core part goes to shared memory for the dense rows
+    w.each([&](LaneT& L, GS& S) {
+      if (S.done) return;
+      const Cold& C = S.cold[L.gl];
+      const double* x0 = warm.x + (long long)(warm.ids ? warm.ids[S.robot] : S.robot) * NX;
+      if (L.is_core) {
+        const int j = L.gl;
+        L.x = x0[j] * C.Dinv;
+        S.xy[j] = L.x;
+#pragma unroll
+        for (int k = 0; k < KU; ++k) L.b[k].xd = C.has_sing[k] ? x0[NC * (1 + k) + j] * C.Ddinv[k] : 0.0;
+      } else {
+        L.b[0].xd = C.has_sing[0] ? x0[NC * (1 + KU) + (L.gl - NC)] * C.Ddinv[0] : 0.0;
+      }
+    });
+    // (W2) z = A x, y = c E^-1 y0, row states v = z + y / rho; z stays in pzc / pz / pzb for the first iteration
+    w.each([&](LaneT& L, GS& S) {
+      if (S.done) return;
+      const Cold& C = S.cold[L.gl];
+      const double* y0 = warm.y + (long long)(warm.ids ? warm.ids[S.robot] : S.robot) * NY;
+      auto place = [&](double z, double y_unscaled, double Einv, double rho, double& pz, double& v) {
+        pz = z;
+        v = rho > 0 ? z + (S.c * Einv * y_unscaled) / rho : z;
+      };
+      if (L.is_core) {
+        const int j = L.gl;
+        if (Cfg::BOUNDS) place(L.betac * L.x, y0[j], C.Ecbinv, L.rhoc, L.pzc, L.vc);
+#pragma unroll
+        for (int k = 0; k < KU; ++k) {
+          BundleHot& b = L.b[k];
+          if (!C.active[k]) continue;
+          place(b.c * L.x + b.e * b.xd, y0[NC * (1 + k) + j], C.Einv[k], L.rho_r, b.pz, b.v);
+          if (C.has_sb[k]) place(b.beta * b.xd, y0[NC * (1 + KU + k) + j], C.Ebinv[k], L.rho_b, b.pzb, b.vb);
+        }
+      } else {
+        const int r = L.gl - NC;
+        BundleHot& b = L.b[0];
+        double ax = b.e * b.xd;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) ax += S.A[r * NC + i] * S.xy[i];
+        place(ax, y0[NC * (1 + 2 * KU) + r], C.Einv[0], L.rho_r, b.pz, b.v);
+        if (C.has_sb[0]) place(b.beta * b.xd, y0[NC * (1 + 2 * KU) + NR + r], C.Ebinv[0], L.rho_b, b.pzb, b.vb);
+      }
+    });
+  }
+
   // ---------------------------------------------------------------- ADMM iterations (osqp_solve)
   int iter = 0;
   bool all_done = warp_done();
@@ -631,7 +693,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     nplain -= 1;
     for (int k = 0; k < nplain; ++k) {
       ++iter;
-      if (iter == 1) w.each(phase_a_first); else w.each(phase_a);
+      if (iter == 1) { if (warm_on) w.each(phase_a_warm); else w.each(phase_a_first); } else w.each(phase_a);
       w.each(phase_b);
     }
     to_check -= nplain; to_adapt -= nplain;
@@ -642,7 +704,7 @@ DRC_HD void admm_solve(W& w, const double* qp, const int* robots, const QpOption
     const bool can_adapt = to_adapt == 0;
     if (to_check == 0) to_check = chk;
     if (to_adapt == 0) to_adapt = adp;
-    if (iter == 1) w.each(phase_a_first); else w.each(phase_a);
+    if (iter == 1) { if (warm_on) w.each(phase_a_warm); else w.each(phase_a_first); } else w.each(phase_a);
     w.each(phase_b_keep);
 
     // ---------------- OSQP update_info + check_termination + adapt_rho

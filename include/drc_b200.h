@@ -55,6 +55,11 @@ typedef struct drc_params {
    * predicted-slow robots, integrate step fused into the solver launches); 1 = TWO launches per tick (k_tick_front: schedule
    * scatter + cubic profile + FK + narrow phase + EPA + QPIK record; k_admm: solve + integrate + next tick's schedule).  Same results. */
   int rollout_fused;
+  /* drc_batch_rollout_qpik: 1 = every tick's QP is warm started from the robot's previous tick (x0, y0 = its primal / dual
+   * solution, osqp_warm_start semantics; tick 0 and robots whose previous QP was infeasible start cold).  An EXTENSION for
+   * simulation rollouts: the reference builds a fresh solver per cycle and never warm starts (QP_base.h:133-177, warm_start is
+   * left at OSQP's cold path), so results with 1 are not the reference's iterates; 0 (default) = the reference's. */
+  int rollout_warm_start;
 } drc_params_t;
 
 const char* drc_last_error(void);

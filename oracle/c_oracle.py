@@ -211,6 +211,19 @@ class Oracle:
             r["y"] = qy
         return r
 
+    def cycle_warm(self, mode: int, q, qd, x_target, xdot_target, frame: int, warm_x, warm_y):
+        """Step cycle (mode 1 / 3) warm started from (warm_x, warm_y) = the previous tick's primal / dual solution (oracle order);
+        both arrays are updated in place with this tick's.  Zeros = cold start.  An extension (QP_base.h:146 never warm starts)."""
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        xt, xd = _c(x_target).reshape(B, 12), _c(xdot_target).reshape(B, 6)
+        out, st, it = np.zeros((B, n)), np.zeros(B, np.int32), np.zeros(B, np.int32)
+        nx, nc = self.qp_sizes(0 if mode <= 1 else 1)
+        assert warm_x.shape == (B, nx) and warm_y.shape == (B, nc) and warm_x.flags.c_contiguous and warm_y.flags.c_contiguous
+        lib().orc_cycle_warm(self.h, C.c_int(mode), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), C.c_int(frame), _d(out),
+                             _i(st), _i(it), C.c_int(nx), C.c_int(nc), _d(warm_x), _d(warm_y))
+        return dict(out=out, status=st, iters=it)
+
     def desired_task(self, mode: int, q, qd, x_target, xdot_target, frame: int):
         """desired task-space signal the Step controllers hand to the QP (robot_controller.cpp:292-300, 335-345):
         Kp e + Kv edot (modes 1, 3)."""

@@ -38,6 +38,10 @@ struct QpSettings {
 struct QpProblem {
   int n = 0, m = 0;
   Mat P, q, A, l, u;
+  // optional warm start (osqp_warm_start: x = D^-1 x0, z = A x, y = c E^-1 y0); null = OSQP's cold start, which is what the
+  // reference uses (QP_base.h:146).  Vectors in this problem's own variable / row order.
+  const double* x0 = nullptr;
+  const double* y0 = nullptr;
   void resize(int n_, int m_) {
     n = n_; m = m_;
     P.assign(n * n, 0.0); q.assign(n, 0.0); A.assign(m * n, 0.0);
@@ -160,6 +164,11 @@ inline void qp_solve(const QpProblem& pb, const QpSettings& st, QpResult& res, Q
   if (!qp_factor(w, n, m, st.sigma)) { res.status = QP_NON_CVX; return; }
   // ---------------- ADMM (osqp_solve), cold start
   w.x.assign(n, 0.0); w.z.assign(m, 0.0); w.y.assign(m, 0.0);
+  if (pb.x0 && pb.y0) {
+    for (int j = 0; j < n; ++j) w.x[j] = w.Dinv[j] * pb.x0[j];
+    a_mul(w, m, w.x.data(), w.z.data());
+    for (int i = 0; i < m; ++i) w.y[i] = w.c * w.Einv[i] * pb.y0[i];
+  }
   w.xp.assign(n, 0.0); w.zp.assign(m, 0.0); w.xt.assign(n, 0.0); w.zt.assign(m, 0.0);
   w.dx.assign(n, 0.0); w.dy.assign(m, 0.0); w.Ax.assign(m, 0.0); w.Px.assign(n, 0.0); w.Aty.assign(n, 0.0);
   w.tmpn.assign(n, 0.0); w.tmpm.assign(m, 0.0);

@@ -285,6 +285,37 @@ void orc_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* 
   }
 }
 
+// QPIKStep / QPIDStep cycle with a WARM START from (qp_x, qp_y) -- the previous tick's primal / dual solution of every robot, in the
+// oracle's own variable / row order -- which are then overwritten with this tick's (zeros after an infeasible / non-convex solve:
+// the next tick of that robot starts cold, and all zeros IS the cold start).  An extension, not a reference behaviour (QP_base.h:146).
+void orc_cycle_warm(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
+                    const double* xdot_target, int frame, double* out, int* status, int* iters, int nx, int ny, double* qp_x, double* qp_y) {
+  const Model& m = h->m;
+  const int n = m.nv;
+#pragma omp parallel num_threads(h->threads)
+  {
+    std::unique_ptr<Workspace> keep(new Workspace);
+#pragma omp for schedule(dynamic, 16)
+    for (int b = 0; b < B; ++b) {
+      Workspace& ws = *keep;
+      update_state(m, ws.s, q + b * n, qd + b * n);
+      double des[6];
+      desired_from_error(m, ws.s, frame, pose_from12(x_target + 12 * b), xdot_target + 6 * b, h->cp, true, des);
+      ws.pb.x0 = qp_x + size_t(b) * nx; ws.pb.y0 = qp_y + size_t(b) * ny;
+      int st;
+      if (mode <= 1) st = ctrl_qpik(m, ws, frame, des, h->cp, h->gp, h->qs, out + n * b);
+      else st = ctrl_qpid(m, ws, frame, des, h->cp, h->gp, h->qs, out + n * b, nullptr);
+      ws.pb.x0 = ws.pb.y0 = nullptr;
+      if (status) status[b] = st;
+      if (iters) iters[b] = ws.res.iters;
+      const bool keep_sol = st == QP_SOLVED || st == QP_MAX_ITER || st == QP_SOLVED_INACCURATE;
+      if ((int)ws.res.x.size() != nx || (int)ws.res.y.size() != ny) { if (status) status[b] = -1; continue; }
+      for (int i = 0; i < nx; ++i) qp_x[size_t(b) * nx + i] = keep_sol ? ws.res.x[i] : 0.0;
+      for (int i = 0; i < ny; ++i) qp_y[size_t(b) * ny + i] = keep_sol ? ws.res.y[i] : 0.0;
+    }
+  }
+}
+
 // desired task signal of the Step controllers: Kp e + Kv edot (QPIKStep / QPIDStep, robot_controller.cpp:292-300, 335-345)
 void orc_desired_task(OrcHandle* h, int mode, int B, const double* q, const double* qd, const double* x_target,
                       const double* xdot_target, int frame, double* des) {

@@ -131,6 +131,18 @@ class Emu:
             o["records"] = rec
         return o
 
+    def cycle_warm(self, mode, q, qd, x_target, xdot_target, frame, warm_x, warm_y):
+        """QPIKStep warm started from (warm_x, warm_y) (structured order, updated in place; zeros = cold start)"""
+        q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)
+        B, n = q.shape
+        xt, xd = _c(x_target).reshape(B, 12), _c(xdot_target).reshape(B, 6)
+        o = dict(out=np.zeros((B, n)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
+        assert warm_x.shape == (B, 3 * n + 2) and warm_y.shape == (B, 5 * n + 4)
+        rc = lib().emu_cycle_warm(self.h, C.c_int(mode), C.c_int(frame), C.c_int(B), _d(q), _d(qd), _d(xt), _d(xd), _d(o["out"]),
+                                  _i(o["status"]), _i(o["iters"]), _d(warm_x), _d(warm_y))
+        assert rc == 0
+        return o
+
     def cycle_xy(self, mode, q, qd, x_target, xdot_target, frame):
         """cycle() plus the dual vector: returns the same dictionary as engine.Context.qp_debug next to out / status / iters."""
         q, qd = _c(q).reshape(-1, self.nv), _c(qd).reshape(-1, self.nv)

@@ -207,7 +207,8 @@ int emu_min_distance(EmuHandle* h, int B, const double* q, const double* qd, dou
 }  // extern "C"
 template <int NV>
 static int emu_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
-              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records, double* qp_y) {
+              const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_records, double* qp_y,
+              bool warm = false) {
   const int n = h->hm.dev.nv;
   const DrcFrame fr = make_frame(h->hm, frame_id);
   Cache c(n, B);
@@ -236,6 +237,7 @@ static int emu_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const double
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.qp = rec.data(); sio.out = out; sio.sout = aos(n); sio.status = status; sio.iters = iters;
   sio.c_g = c.g.data(); sio.Bc = B; sio.qp_x = qp_x; sio.qp_y = qp_y;
+  if (warm) { sio.warm_x = qp_x; sio.warm_y = qp_y; }   // in place: read at the start of the solve, written by the emit stage
   if (ID) run_solve<QpidCfg<NV>, true>(h, sio, (1u << NV) - 1u);
   else run_solve<QpikCfg<NV>, false>(h, sio, (1u << NV) - 1u);
   return 0;
@@ -255,6 +257,12 @@ int emu_cycle_xy(EmuHandle* h, int mode, int frame_id, int B, const double* q, c
   if (h->hm.dev.nv == 7) return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, nullptr, qp_y);
   if (h->hm.dev.nv == 6) return emu_cycle_t<6>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, nullptr, qp_y);
   return -1;
+}
+// warm-started step cycle: (qp_x, qp_y) hold the previous tick's solution on entry (zeros = cold) and this tick's on return
+int emu_cycle_warm(EmuHandle* h, int mode, int frame_id, int B, const double* q, const double* qd, const double* x_target,
+                   const double* xdot_target, double* out, int* status, int* iters, double* qp_x, double* qp_y) {
+  if (!h->hm.chain || h->hm.dev.nv != 7) return -1;
+  return emu_cycle_t<7>(h, mode, frame_id, B, q, qd, x_target, xdot_target, out, status, iters, qp_x, nullptr, qp_y, true);
 }
 int emu_qp_stride(int mode) { return mode >= 2 ? QpidCfg<7>::STRIDE : QpikCfg<7>::STRIDE; }  // FR3 records
 

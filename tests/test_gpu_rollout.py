@@ -96,3 +96,33 @@ def test_rollout_rejects_bad_arguments(gpu_ctx, oracle):
         ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, 0, 1e-3)
     with pytest.raises(RuntimeError):
         ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, 3, 0.0)
+
+
+def test_warm_started_rollout_matches_the_oracle(gpu_ctx, oracle, variant):
+    """drc_params_t::rollout_warm_start (an extension; the reference never warm starts, QP_base.h:146): every tick's QP starts from the
+    robot's previous primal / dual solution (osqp_warm_start semantics) -- against the oracle's dense OSQP port run tick by tick with
+    the same warm start, each side fed with its own previous solution."""
+    model, ctx = gpu_ctx
+    B, T, dt = 192, 8, 1e-3
+    q, qd, q_t, xd_t = workload(oracle.model, B, 94)
+    f = oracle.frame_id(LINK)
+    x_t = oracle.update_state(q_t, qd, f)["pose"]
+    nx, ny = oracle.qp_sizes(0)
+    ox, oy = np.zeros((B, nx)), np.zeros((B, ny))
+    rq, rqd, its = q.copy(), qd.copy(), np.zeros(B, np.int32)
+    for _ in range(T):
+        r = oracle.cycle_warm(1, rq, rqd, x_t, xd_t, f, ox, oy)
+        rq = rq + dt * r["out"]; rqd = r["out"].copy(); its += r["iters"]
+    cold_q = oracle_rollout(oracle, q, qd, x_t, xd_t, T, dt)[0]
+    ctx.set_params(rollout_warm_start=1)
+    try:
+        g = ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, T, dt)
+    finally:
+        ctx.set_params(rollout_warm_start=0)
+    same = g["iters_total"] == its
+    assert same.mean() > 0.9, same.mean()
+    assert np.abs(g["q"] - rq)[same].max() < 1e-6 and np.abs(g["qdot"] - rqd)[same].max() < 1e-3
+    assert np.abs(g["q"] - cold_q).max() > 1e-9        # not the cold-started iterates
+    # the flag is off again: the next rollout is the reference's (cold) one
+    g0 = ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, T, dt)
+    assert np.abs(g0["q"] - cold_q)[g0["iters_total"] == oracle_rollout(oracle, q, qd, x_t, xd_t, T, dt)[3]].max() < 1e-6
