@@ -64,21 +64,45 @@ static __device__ __forceinline__ void collision_block(const DrcModelDev& m, con
     }
   }
   for (;;) {
-    const int bit = valid ? narrow_pick(st) : -1;
-    if (bit >= 0) {
-      const int slot = atomicAdd(&S.n_items, 1);
-      S.owner[slot] = (short)tid; S.bit[slot] = (unsigned char)bit; S.best_d[tid] = st.best.d;
+    // every robot posts its most promising candidate ...
+    const int bit0 = valid ? narrow_pick(st) : -1;
+    constexpr int kSpec = 2;   // speculative candidates per robot and round (3 measured: no further gain)
+    int slot0 = -1, bitx[kSpec], slotx[kSpec];
+#pragma unroll
+    for (int e = 0; e < kSpec; ++e) bitx[e] = -1;
+    if (bit0 >= 0) {
+      slot0 = atomicAdd(&S.n_items, 1);
+      S.owner[slot0] = (short)tid; S.bit[slot0] = (unsigned char)bit0; S.best_d[tid] = st.best.d;
     }
     __syncthreads();
-    const int n = S.n_items;
+    // ... and the lanes that are still free take further candidates, speculatively: an item that an earlier candidate's outcome
+    // would have culled cannot beat the running minimum (its distance is at least its bound), so the minimum over all pairs, its
+    // tie-break and the set of overlapping pairs that matter are unchanged -- only the number of rounds drops
+    if (bit0 >= 0) {
+#pragma unroll
+      for (int e = 0; e < kSpec; ++e) {
+        if (*(volatile int*)&S.n_items >= T) break;
+        const int bt = narrow_pick(st);
+        if (bt < 0) break;
+        const int sl = atomicAdd(&S.n_items, 1);
+        if (sl >= T) { st.cand |= 1ull << bt; break; }   // no lane left: back into the candidate set
+        S.owner[sl] = (short)tid; S.bit[sl] = (unsigned char)bt;
+        bitx[e] = bt; slotx[e] = sl;
+      }
+    }
+    __syncthreads();
+    const int n = S.n_items < T ? S.n_items : T;
     if (n == 0) break;
     if (tid < n) {
       const int ow = S.owner[tid];
-      narrow_gjk_item(m, G, prm, io, b0 + ow, S.bit[tid], S.best_d[ow], S.res[ow]);
+      narrow_gjk_item(m, G, prm, io, b0 + ow, S.bit[tid], S.best_d[ow], S.res[tid]);
     }
     __syncthreads();
     if (tid == 0) S.n_items = 0;
-    if (bit >= 0) narrow_apply(m, G, st, bit, S.res[tid]);
+    if (bit0 >= 0) narrow_apply(m, G, st, bit0, S.res[slot0]);
+#pragma unroll
+    for (int e = 0; e < kSpec; ++e)
+      if (bitx[e] >= 0) narrow_apply(m, G, st, bitx[e], S.res[slotx[e]]);
     __syncthreads();
   }
   if (valid) narrow_finish<NV, CHAIN>(m, prm, io, b0 + tid, st);

@@ -9,7 +9,7 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 > gpurun_out/${tag}_ncu_bench.log 2>&1
-for k in k_admm k_collision k_robot_job; do
+for k in k_admm k_collision_closed k_collision k_robot_job; do
   # MAIN-pipeline launch of the second control tick (the ADMM schedule then has the previous tick's iteration counts).
   # Launch order per tick: priority pipeline (FK store, collision, build, ADMM) then main pipeline (same kernels);
   # tools/prof_cycle.py adds two k_robot_job launches for its set-up.
