@@ -218,3 +218,16 @@ def test_qp_optimum_against_scipy_and_kkt(oracle):
     assert len(dist_x) >= 950 and len(slsqp_gap) >= 80
     # OSQP at eps 1e-3 is OSQP-accurate, not exact: bounded distance, mostly the same active set
     assert np.median(dist_x) < 5e-2 and agree.mean() > 0.97
+
+
+def test_explicit_inverse_of_the_schur_complement_is_accurate():
+    """the ADMM kernel inverts its NC x NC Schur complement explicitly (Gauss-Jordan, no pivoting) instead of
+    keeping a Cholesky factor.  On the stress set, for rho over OSQP's whole clip range, the equilibrated S has a condition number
+    below 20 and the inverse is accurate to rounding (tools/gj_accuracy.py; numbers in profiles/r02_gauss_jordan_accuracy.json)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "tools"))
+    from gj_accuracy import measure
+    r = measure(48)
+    assert r["max_condition_number"] < 20
+    assert r["max_abs_SSinv_minus_I"] < 1e-13 and r["max_rel_error_vs_cholesky_solve"] < 1e-13

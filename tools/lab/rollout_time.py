@@ -18,17 +18,21 @@ q, qd, q_t, xd = make_workload(model, B, 0)
 ctx.update_state(q_t, qd)
 x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
 dev = torch.device("cuda", 0)
-for rep in range(3):
-    tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xd))
-    torch.cuda.synchronize()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    r = ctx.rollout_qpik(tq, tqd, txt, txd, LINK, T, 1e-3)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(f"rollout B={B} T={T}: {ms:.2f} ms total, {ms / T:.3f} ms / tick, {B * T / ms / 1e3:.2f} M cycles/s, {(ctx.launch_count - l0) / T:.2f} launches / tick, "
-          f"failed ticks {int(r['fail_ticks'].sum())}, mean iterations / tick {float(r['iters_total'].double().mean()) / T:.1f}")
+for fused, warm in ((0, 0), (1, 0), (0, 1)):
+    ctx.set_params(rollout_fused=fused, rollout_warm_start=warm)
+    for rep in range(3):
+        tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xd))
+        torch.cuda.synchronize()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = ctx.rollout_qpik(tq, tqd, txt, txd, LINK, T, 1e-3)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"rollout [{'two launches per tick' if fused else 'pipeline per tick'}{', warm start' if warm else ''}] B={B} T={T}: {ms:.2f} ms total, "
+              f"{ms / T:.3f} ms / tick, {B * T / ms / 1e3:.2f} M cycles/s, {(ctx.launch_count - l0) / T:.2f} launches / tick, "
+              f"failed ticks {int(r['fail_ticks'].sum())}, mean iterations / tick {float(r['iters_total'].double().mean()) / T:.1f}")
+ctx.set_params(rollout_fused=0, rollout_warm_start=0)
 for rep in range(2):
     tq, tqd, txt, txd = (torch.from_numpy(a).to(dev) for a in (q, qd, x_t, xd))
     torch.cuda.synchronize()
