@@ -220,33 +220,43 @@ DRC_HD void closest_segment(SimplexVert* v, int& n, double* lam) {
   if (t >= den) { v[0] = v[1]; n = 1; lam[0] = 1; return; }
   lam[1] = t / den; lam[0] = 1 - lam[1];
 }
-DRC_HD void closest_triangle(SimplexVert* v, int& n, double* lam) {
-  const Vec3 a = v[0].w, b = v[1].w, c = v[2].w;
+// closest point to the origin on the triangle (a, b, c): which vertices support it (idx, in input order) and their weights
+DRC_HD int closest_triangle_w(Vec3 a, Vec3 b, Vec3 c, int* idx, double* lam) {
   const Vec3 ab = b - a, ac = c - a;
   const double d1 = -dot(ab, a), d2 = -dot(ac, a);
-  if (d1 <= 0 && d2 <= 0) { n = 1; lam[0] = 1; return; }
+  if (d1 <= 0 && d2 <= 0) { idx[0] = 0; lam[0] = 1; return 1; }
   const double d3 = -dot(ab, b), d4 = -dot(ac, b);
-  if (d3 >= 0 && d4 <= d3) { v[0] = v[1]; n = 1; lam[0] = 1; return; }
+  if (d3 >= 0 && d4 <= d3) { idx[0] = 1; lam[0] = 1; return 1; }
   const double vc = d1 * d4 - d3 * d2;
-  if (vc <= 0 && d1 >= 0 && d3 <= 0) { const double t = d1 / (d1 - d3); n = 2; lam[0] = 1 - t; lam[1] = t; return; }
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { const double t = d1 / (d1 - d3); idx[0] = 0; idx[1] = 1; lam[0] = 1 - t; lam[1] = t; return 2; }
   const double d5 = -dot(ab, c), d6 = -dot(ac, c);
-  if (d6 >= 0 && d5 <= d6) { v[0] = v[2]; n = 1; lam[0] = 1; return; }
+  if (d6 >= 0 && d5 <= d6) { idx[0] = 2; lam[0] = 1; return 1; }
   const double vb = d5 * d2 - d1 * d6;
-  if (vb <= 0 && d2 >= 0 && d6 <= 0) { const double t = d2 / (d2 - d6); v[1] = v[2]; n = 2; lam[0] = 1 - t; lam[1] = t; return; }
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { const double t = d2 / (d2 - d6); idx[0] = 0; idx[1] = 2; lam[0] = 1 - t; lam[1] = t; return 2; }
   const double va = d3 * d6 - d5 * d4;
   if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
     const double t = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-    v[0] = v[1]; v[1] = v[2]; n = 2; lam[0] = 1 - t; lam[1] = t; return;
+    idx[0] = 1; idx[1] = 2; lam[0] = 1 - t; lam[1] = t; return 2;
   }
   const double den = 1.0 / (va + vb + vc);
+  idx[0] = 0; idx[1] = 1; idx[2] = 2;
   lam[0] = va * den; lam[1] = vb * den; lam[2] = vc * den;
+  return 3;
 }
-// true when the origin lies inside the tetrahedron
+DRC_HD void closest_triangle(SimplexVert* v, int& n, double* lam) {
+  int idx[3];
+  n = closest_triangle_w(v[0].w, v[1].w, v[2].w, idx, lam);
+  // idx is increasing: compacting in place never reads an overwritten slot
+  for (int i = 0; i < n; ++i)
+    if (idx[i] != i) v[i] = v[idx[i]];
+}
+// true when the origin lies inside the tetrahedron.  The faces are examined on the Minkowski points only (three Vec3 each);
+// the simplex vertices move once, at the end (this routine used to copy three 9-double vertices per face into local memory).
 DRC_HD bool closest_tetra(SimplexVert* v, int& n, double* lam) {
   const int F[4][3] = {{0, 1, 2}, {0, 2, 3}, {0, 3, 1}, {1, 3, 2}};
   const int OPP[4] = {3, 1, 2, 0};
   double best = 1e300;
-  SimplexVert bv[3];
+  int bi[3] = {0, 0, 0};
   double bl[3] = {0, 0, 0};
   int bn = 0;
   bool outside = false;
@@ -257,22 +267,23 @@ DRC_HD bool closest_tetra(SimplexVert* v, int& n, double* lam) {
     // origin and the opposite vertex on different sides, or a (nearly) flat tetrahedron whose side test is noise
     if (so * sd < 0 || sd * sd <= 1e-20 * n2 * sqrt(n2)) {
       outside = true;
-      SimplexVert t[3] = {v[F[f][0]], v[F[f][1]], v[F[f][2]]};
+      int ti[3];
       double l[3] = {0, 0, 0};
-      int tn = 3;
-      closest_triangle(t, tn, l);
+      const int tn = closest_triangle_w(a, b, c, ti, l);
       Vec3 p = v3(0, 0, 0);
-      for (int i = 0; i < tn; ++i) p = p + l[i] * t[i].w;
+      for (int i = 0; i < tn; ++i) p = p + l[i] * v[F[f][ti[i]]].w;
       const double dd = dot(p, p);
       if (dd < best) {
         best = dd; bn = tn;
-        for (int i = 0; i < tn; ++i) { bv[i] = t[i]; bl[i] = l[i]; }
+        for (int i = 0; i < tn; ++i) { bi[i] = F[f][ti[i]]; bl[i] = l[i]; }
       }
     }
   }
   if (!outside) return true;
   n = bn;
-  for (int i = 0; i < n; ++i) { v[i] = bv[i]; lam[i] = bl[i]; }
+  SimplexVert keep[3];
+  for (int i = 0; i < n; ++i) keep[i] = v[bi[i]];
+  for (int i = 0; i < n; ++i) { v[i] = keep[i]; lam[i] = bl[i]; }
   return false;
 }
 
@@ -292,6 +303,10 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
   int n = 1;
   sv[0].a = support(A, d0); sv[0].b = support(B, -d0); sv[0].w = sv[0].a - sv[0].b;
   Vec3 v = sv[0].w;
+  // witness points of the current closest point, carried along with v: they are what a precision-loss restart and the
+  // numerical-floor exit need from the PREVIOUS simplex, so that simplex itself is never copied (the per-iteration backup of
+  // 4 x 9 doubles was most of the loop's local-memory traffic)
+  Vec3 pa = sv[0].a, pb = sv[0].b;
   bool inter = false;
   int it = 0;
   for (; it < max_iter; ++it) {
@@ -304,10 +319,6 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
     bool dup = false;
     for (int i = 0; i < n; ++i) dup = dup || (norm2(sv[i].w - nw.w) <= 1e-30);
     if (dup) break;
-    SimplexVert prev_sv[4];
-    double prev_lam[4];
-    const int prev_n = n;
-    for (int i = 0; i < n; ++i) { prev_sv[i] = sv[i]; prev_lam[i] = lam[i]; }
     sv[n++] = nw;
     bool inside = false;
     if (n == 2) closest_segment(sv, n, lam);
@@ -321,25 +332,27 @@ DRC_HD_NOINLINE void gjk_distance(const Prim& A, const Prim& B, double tol, int 
       // new vertex] -- a Frank-Wolfe step with exact line search, which improves whenever the gap is positive.
       // The closest point is a valid vertex: a convex combination of support points of A and of B.
       SimplexVert cp;
-      cp.w = v; cp.a = v3(0, 0, 0); cp.b = v3(0, 0, 0);
-      for (int i = 0; i < prev_n; ++i) { cp.a = cp.a + prev_lam[i] * prev_sv[i].a; cp.b = cp.b + prev_lam[i] * prev_sv[i].b; }
+      cp.w = v; cp.a = pa; cp.b = pb;
       sv[0] = cp; sv[1] = nw; n = 2;
       closest_segment(sv, n, lam);
       nv = v3(0, 0, 0);
       for (int i = 0; i < n; ++i) nv = nv + lam[i] * sv[i].w;
-      if (dot(nv, nv) >= vv) {  // numerical floor: keep the previous simplex
-        n = prev_n;
-        for (int i = 0; i < n; ++i) { sv[i] = prev_sv[i]; lam[i] = prev_lam[i]; }
+      if (dot(nv, nv) >= vv) {  // numerical floor: the previous closest point stands
+        sv[0] = cp; lam[0] = 1; n = 1;
         break;
       }
     }
     v = nv;
+    pa = v3(0, 0, 0); pb = v3(0, 0, 0);
+    for (int i = 0; i < n; ++i) { pa = pa + lam[i] * sv[i].a; pb = pb + lam[i] * sv[i].b; }
   }
   out.intersect = inter;
   out.n = n;
   out.iters = it + 1;
-  Vec3 pa = v3(0, 0, 0), pb = v3(0, 0, 0);
-  for (int i = 0; i < n; ++i) { pa = pa + lam[i] * sv[i].a; pb = pb + lam[i] * sv[i].b; }
+  if (inter) {  // the overlapping simplex (EPA's seed): witnesses from its weights
+    pa = v3(0, 0, 0); pb = v3(0, 0, 0);
+    for (int i = 0; i < n; ++i) { pa = pa + lam[i] * sv[i].a; pb = pb + lam[i] * sv[i].b; }
+  }
   out.pa = pa; out.pb = pb;
   out.dist = inter ? 0.0 : norm(v);
 }

@@ -53,7 +53,8 @@ struct drc_ctx {
   cudaStream_t stream;
   cudaStream_t side;      // EPA pass of the self-collision stage runs here, next to the state / QP-build kernel
   cudaEvent_t ev_col, ev_epa, ev_build;
-  cudaStream_t prio_side; cudaEvent_t ev_prio_fk, ev_prio_build;   // priority pipeline: QP build next to the narrow phase
+  cudaStream_t prio_side; cudaEvent_t ev_prio_fk, ev_prio_build;
+  cudaStream_t build_stream; cudaEvent_t ev_mbuild; bool par_build;   // main pipeline: QP build next to the narrow phase   // priority pipeline: QP build next to the narrow phase
   // state cache (SoA, stride cap)
   double *c_q, *c_qd, *c_oMi, *c_M, *c_Minv, *c_g, *c_nle;
   double *c_Mact, *c_Minvact, *c_gact, *c_nleact;  // mobile manipulator only (actuated-space dynamics)
