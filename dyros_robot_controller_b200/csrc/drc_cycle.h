@@ -56,6 +56,11 @@ struct JobIO {
   // priority sub-batch (robots predicted to need many ADMM iterations, see run_qp): slot b of the cache / QP scratch
   // holds robot ids[b] of the INPUT arrays; *count slots are in use (null = identity / io.B)
   const int* ids; const int* count;
+  // two-route manipulability (device, main pipeline of the fused QPIK cycle): robots whose J J^T fails the conditioning
+  // certificate of the Cholesky route are appended here and redone by the exact (rank-revealing) route in a small follow-up
+  // launch of the same job over this list (`redo`: the launch IS that follow-up; slot index = list entry).  null = exact route.
+  int* manip_list; int* manip_count;
+  bool redo;
 };
 
 template <int NV>
@@ -278,7 +283,23 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   double mani = 0, mgrad[NV], mgraddot[NV];
   if (FLAGS & (F_MANIP_OUT | F_QPIK | F_QPID)) {
     constexpr bool gd = (FLAGS & (F_QPID | F_GRADDOT)) != 0;
-    manipulability<NV, MANI, CHAIN>(m, k, frame.parent, pf, J, Jd, MOMA ? m.mani_start : 0, gd, prm.pinv_threshold, mani, mgrad, mgraddot);
+    // Two routes, chosen by the robot's own data only (so a robot's result does not depend on the launch it sits in): Cholesky when
+    // the conditioning certificate holds (drc_kin.h), else the rank-revealing QR.  Where the caller provides a list (main pipeline of
+    // the fused QPIK cycle) the uncertified robots are left to a follow-up launch over that list instead of stalling their warps here.
+    int route = 2;
+#ifdef DRC_FORCE_EXACT_MANIP   // test infrastructure: the rank-revealing route for every robot
+    route = 0;
+#endif
+#if defined(__CUDA_ARCH__)
+    if (io.redo) route = 0;                 // the follow-up launch: these robots failed the certificate already
+    else if (io.manip_list) route = 1;
+#endif
+    if (!manipulability<NV, MANI, CHAIN>(m, k, frame.parent, pf, J, Jd, MOMA ? m.mani_start : 0, gd, prm.pinv_threshold, mani, mgrad, mgraddot, route)) {
+#if defined(__CUDA_ARCH__)
+      io.manip_list[atomicAdd(io.manip_count, 1)] = b;
+#endif
+      return;
+    }
     if ((FLAGS & F_MANIP_OUT) && io.mani) {
       io.mani[b] = mani;
 #pragma unroll

@@ -64,6 +64,7 @@ struct drc_ctx {
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
   int* nar_k; float* nar_lb;
+  int *manip_list, *manip_count;         // two-route manipulability of the main QPIK build: robots left to the exact route
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
   double* roll; int* roll_i;             // rollout scratch (cubic profile; next tick's schedule histogram / offsets / ticket), allocated on first use
   int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
@@ -143,7 +144,7 @@ static void bind_cache(const drc_ctx* c, JobIO& io) {
 template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStream_t s) {
   constexpr int threads = 64;
-  const int blocks = (io.B + threads - 1) / threads;
+  const int blocks = io.redo ? 2 * c->sm_count : (io.B + threads - 1) / threads;   // redo: grid-stride over JobIO::manip_list
   k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->mdev, c->prm, fr, io);
   c->launches++;
   CU(cudaGetLastError());
@@ -169,7 +170,7 @@ static int launch_collision(drc_ctx* c, CollisionIO io, cudaStream_t s, bool epa
   io.nar_k = sc.nar_k; io.nar_lb = sc.nar_lb;
   k_collision_closed<NV, CHAIN><<<blocks, threads, 0, s>>>(c->mdev, io);
   CU(cudaGetLastError());
-  k_collision<NV, CHAIN, true, DRC_GJK_MINB><<<blocks, threads, 0, s>>>(c->mdev, c->prm, io);
+  k_collision<NV, CHAIN, true, DRC_GJK_MINB><<<(io.B + kGjkThreads - 1) / kGjkThreads, kGjkThreads, 0, s>>>(c->mdev, c->prm, io);
   CU(cudaGetLastError());
   c->launches++;
   // the EPA pass touches ~0.1 % of the robots with one warp each: a long, nearly empty kernel.  The QP entry points run it

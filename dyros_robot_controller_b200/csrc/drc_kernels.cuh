@@ -21,6 +21,11 @@ template <int NV, bool CHAIN, unsigned FLAGS, int W = 0>
 __global__ void __launch_bounds__(128) k_robot_job(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ DrcFrame frame, const __grid_constant__ JobIO io) {
 #ifndef DRC_SYNTAX_CHECK   // -DDRC_SYNTAX_CHECK: empty kernel bodies, for a host-code syntax pass in seconds (build.py --check)
+  if (io.redo) {   // follow-up launch over the robots the Cholesky route of the manipulability could not certify (JobIO::manip_list)
+    const int n = *io.manip_count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, io.manip_list[i]);
+    return;
+  }
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < io.B && (!io.count || b < *io.count)) robot_job<NV, CHAIN, FLAGS, W>(m, prm, frame, io, b);
 #endif
@@ -126,13 +131,17 @@ __global__ void __launch_bounds__(kColThreads, 4) k_collision_closed(const __gri
   for (int i = 0; i < m.ngjk; ++i) io.nar_lb[(long long)i * io.Bc + b] = st.lbs[i];
 #endif
 }
+#ifndef DRC_GJK_THREADS
+#define DRC_GJK_THREADS 128
+#endif
+constexpr int kGjkThreads = DRC_GJK_THREADS;
 template <int NV, bool CHAIN, bool LOAD, int MINB = 2>
-__global__ void __launch_bounds__(kColThreads, MINB) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
+__global__ void __launch_bounds__(kGjkThreads, MINB * (128 / kGjkThreads)) k_collision(const __grid_constant__ DrcModelDev m, const __grid_constant__ DrcParams prm,
                                                     const __grid_constant__ CollisionIO io) {
 #ifndef DRC_SYNTAX_CHECK
   // stage the geometry table in shared memory: the GJK pass indexes it with per-thread pair ids
   __shared__ GeomTable G;
-  __shared__ NarrowBlockSmem<kColThreads> S;
+  __shared__ NarrowBlockSmem<kGjkThreads> S;
   {
     const int* src = reinterpret_cast<const int*>(&m.geom);
     int* dst = reinterpret_cast<int*>(&G);
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(kColThreads, MINB) k_collision(const __grid_co
   }
   __syncthreads();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  collision_block<NV, CHAIN, kColThreads, LOAD>(m, G, prm, io, blockIdx.x * blockDim.x, b < io.B && (!io.count || b < *io.count), S);
+  collision_block<NV, CHAIN, kGjkThreads, LOAD>(m, G, prm, io, blockIdx.x * blockDim.x, b < io.B && (!io.count || b < *io.count), S);
 #endif
 }
 // ---- EPA, one WARP per flagged robot (~0.1 % of a random batch).  Same algorithm and rules as the scalar

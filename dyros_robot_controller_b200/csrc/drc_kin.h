@@ -246,6 +246,34 @@ DRC_HD void spd_pinv(const double* A, double* Ainv, double threshold) {
   else pinv_cpqr<N, N>(A, Ainv, threshold);
 }
 
+// Cholesky route of the manipulability for a well-conditioned 6 x 6 SPD matrix: inverse, product of the factor's diagonal, and the
+// certificate kappa <= min(tr A, |A|_inf) * min(tr A^-1, |A^-1|_inf) < 1.25e4 (see `manipulability`).  NOT inlined: one copy of this
+// arithmetic per translation unit, so every kernel that evaluates a robot gets the same bits (as with pinv_cpqr).
+DRC_HD_NOINLINE bool chol6_certified(const double* A, double* Ainv, double* prod_diag) {
+  double L[36];
+  double trA = 0, infA = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double rs = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { L[r * 6 + c] = A[r * 6 + c]; rs += fabs(A[r * 6 + c]); }
+    trA += A[r * 6 + r]; infA = dmax(infA, rs);
+  }
+  if (!(chol_inplace<6>(L) > 0)) return false;
+  chol_inverse<6>(L, Ainv);
+  double trI = 0, infI = 0, det = 1.0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double rs = 0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) rs += fabs(Ainv[r * 6 + c]);
+    trI += Ainv[r * 6 + r]; infI = dmax(infI, rs);
+    det *= L[r * 6 + r];
+  }
+  *prod_diag = det;
+  return dmin(trA, infA) * dmin(trI, infI) < 1.25e4;
+}
+
 // Manipulability m = sqrt(det(J J^T)), gradient and the reference's "gradient time variation"
 // (robot_data.cpp:519-573).  J, Jd are 6 x NC blocks (columns col0..col0+NC-1 of the frame Jacobian).
 // dJ/dq_i is the closed-form kinematic Hessian (replaces the reference's NC extra J-dot passes):
@@ -253,9 +281,15 @@ DRC_HD void spd_pinv(const double* A, double* Ainv, double threshold) {
 //   otherwise (i in the support):  d(col j) = [ a_j x (a_i x d_i) ; 0 ]
 // (revolute joints; prismatic joints contribute a_i x a_j = 0 and d p = a_i).
 template <int NV, int NC, bool CHAIN>
-DRC_HD void manipulability(const DrcModelDev& m, const KinState<NV>& k, int pj, Vec3 pf, const double* J /*6xNV*/,
+// `route`: 0 = rank-revealing QR only; 1 = Cholesky route or give up (returns false); 2 = Cholesky route, else the QR.
+// Cholesky route -- for a well-conditioned J J^T the rank-revealing QR keeps every column, so its
+// pseudo-inverse IS the inverse and |det| = prod of the Cholesky pivots.  The route is taken only under a certificate that the QR
+// would not truncate: with kappa <= min(tr A, |A|_inf) * min(tr A^-1, |A^-1|_inf) < 1.25e4 the column-pivoted R satisfies
+// min|R_kk| / max|R_kk| >= 1 / (sqrt(6) 2^5 kappa) > 1e-6 = the rank threshold.  Returns false (nothing computed) when the certificate
+// fails: the caller hands that robot to the exact route (k_robot_job's fix-up launch).
+DRC_HD bool manipulability(const DrcModelDev& m, const KinState<NV>& k, int pj, Vec3 pf, const double* J /*6xNV*/,
                            const double* Jd /*6xNV or null*/, int col0, bool with_graddot, double threshold,
-                           double& mani, double* grad, double* grad_dot) {
+                           double& mani, double* grad, double* grad_dot, int route = 0) {
   double A[36], Ainv[36];
 #pragma unroll
   for (int r = 0; r < 6; ++r)
@@ -266,7 +300,12 @@ DRC_HD void manipulability(const DrcModelDev& m, const KinState<NV>& k, int pj, 
       for (int j = 0; j < NC; ++j) s += J[r * NV + col0 + j] * J[c * NV + col0 + j];
       A[r * 6 + c] = s;
     }
-  {
+  bool certified = false;
+  if (route != 0) {
+    certified = threshold <= 1e-6 && chol6_certified(A, Ainv, &mani);   // mani = sqrt(det(J J^T)) = prod L_kk
+    if (!certified && route == 1) return false;
+  }
+  if (!certified) {
     // the reference takes sqrt(det(JJ^T)) and PinvCOD(JJ^T) (robot_data.cpp:526,539): one rank-revealing
     // QR gives both (|det| = prod |R_kk|), including the rank truncation near singular postures
     double ad;
@@ -366,6 +405,7 @@ DRC_HD void manipulability(const DrcModelDev& m, const KinState<NV>& k, int pj, 
     grad[ii] = mani * trG;
     if (with_graddot) grad_dot[ii] = mani_dot * trG + mani * trH;
   }
+  return true;
 }
 
 // DyrosMath::getPhi(target, current) orientation error (math_type_define.h:283-298, call at :642)

