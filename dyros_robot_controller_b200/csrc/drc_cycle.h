@@ -286,7 +286,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     // Two routes, chosen by the robot's own data only (so a robot's result does not depend on the launch it sits in): Cholesky when
     // the conditioning certificate holds (drc_kin.h), else the rank-revealing QR.  Where the caller provides a list (main pipeline of
     // the fused QPIK cycle) the uncertified robots are left to a follow-up launch over that list instead of stalling their warps here.
-    int route = 2;
+    int route = MOMA ? 0 : 2;   // whole-body kernels have no follow-up list: the inline fallback would buy nothing there
 #ifdef DRC_FORCE_EXACT_MANIP   // test infrastructure: the rank-revealing route for every robot
     route = 0;
 #endif

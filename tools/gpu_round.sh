@@ -14,7 +14,7 @@ for k in k_admm k_collision_closed k_collision k_robot_job; do
   # MAIN-pipeline launch of the second control tick (the ADMM schedule then has the previous tick's iteration counts).
   # Launch order per tick: priority pipeline (FK store, collision, build, ADMM) then main pipeline (same kernels);
   # tools/prof_cycle.py adds two k_robot_job launches for its set-up.
-  skip=3; [ "$k" = "k_robot_job" ] && skip=10   # per tick: prio FK, prio build, main FK, main build, dynamics-only
+  skip=3; [ "$k" = "k_robot_job" ] && skip=11   # per tick: main FK, prio FK, prio build, main build, its follow-up, dynamics-only (+2 set-up launches)
   [ "$k" = "k_admm" ] && skip=5                    # per tick: priority launch, EPA-pending robots, main launch
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^${k}\$" --launch-skip $skip -c 1 -f -o gpurun_out/${tag}_${k} \
     python tools/prof_cycle.py 65536 2 > gpurun_out/${tag}_ncu_${k}.log 2>&1
