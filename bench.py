@@ -322,7 +322,9 @@ def run_ours(args):
         x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
         nout = model.actuated_dof
     else:
-        q, qd, q_t, xdot_t = make_workload(model, B, seed=1000 * rank)
+        # DRC_BENCH_SAME_SEED: experiment knob for the scaling analysis (every rank gets rank 0's batch: what is left of the per-rank
+        # spread is the machine, not the data); never set for a reported number
+        q, qd, q_t, xdot_t = make_workload(model, B, seed=0 if os.environ.get("DRC_BENCH_SAME_SEED") else 1000 * rank)
         ctx.update_state(q_t, qd)
         x_t = ctx.get_frame(link, want=("pose",))["pose"]
         nout = model.dof
