@@ -29,6 +29,8 @@ enum JobFlags : unsigned {
   F_TORQUE = 1u << 10,    // moveJointTorqueStep(q_target, qdot_target)
   F_GRADDOT = 1u << 11,   // manipulability gradient time variation
   F_MOMA = 1u << 12,      // mobile manipulator: actuated quantities through the selection matrix S, whole-body QPs
+  F_DYN_LIGHT = 1u << 13, // with F_DYN: only what a QPID record reads (M, g; whole-body: M~, g~) and nothing but g~ stored -- a
+                          // dynamics-only launch (F_DYN | F_FROM_CACHE) behind the solver completes the cache (inverses, nle)
 };
 
 struct JobIO {
@@ -96,7 +98,8 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   constexpr bool MOMA = (FLAGS & F_MOMA) != 0;
   constexpr int ACT = MOMA ? NV - 3 : NV;        // actuated dof = wheels + manipulator joints
   constexpr int MANI = MOMA ? NV - 3 - W : NV;   // manipulator dof (mobile_manipulator/robot_data.cpp:19)
-  static_assert(!MOMA || (FLAGS & F_DYN), "mobile-manipulator jobs always recompute the dynamics");
+  static_assert(!(FLAGS & F_QPID) || !MOMA || (FLAGS & F_DYN), "whole-body QPID records read the actuated dynamics");
+  constexpr bool LIGHT = (FLAGS & F_DYN_LIGHT) != 0;
   // mobile-manipulator jobs pick the state source and the task signal at run time (fewer heavy instantiations)
   const bool from_cache = (FLAGS & F_FROM_CACHE) || (MOMA && io.q == nullptr);
   const bool step = (FLAGS & F_STEP) || (MOMA && io.x_target != nullptr);
@@ -132,20 +135,22 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   double M[NV * NV], g[NV], Minv[NV * NV];
   constexpr bool need_dyn_vals = (FLAGS & (F_QPID | F_OSF | F_TORQUE)) != 0;
   if (FLAGS & F_DYN) {
-    double nle[NV];
     mass_matrix<NV, CHAIN>(m, k, M);
     rnea_bias<NV, CHAIN>(m, k, v, false, qd, g);
-    rnea_bias<NV, CHAIN>(m, k, v, true, qd, nle);
+    if (!LIGHT) {
+      double nle[NV];
+      rnea_bias<NV, CHAIN>(m, k, v, true, qd, nle);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      io.c_g[i * io.Bc + b] = g[i];
-      io.c_nle[i * io.Bc + b] = nle[i];
+      for (int i = 0; i < NV; ++i) {
+        io.c_g[i * io.Bc + b] = g[i];
+        io.c_nle[i * io.Bc + b] = nle[i];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) io.c_M[(i * NV + j) * io.Bc + b] = M[i * NV + j];
+        for (int j = 0; j < NV; ++j) io.c_M[(i * NV + j) * io.Bc + b] = M[i * NV + j];
+      }
+      spd_pinv<NV>(M, Minv, prm.pinv_threshold);
+#pragma unroll
+      for (int i = 0; i < NV * NV; ++i) io.c_Minv[i * io.Bc + b] = Minv[i];
     }
-    spd_pinv<NV>(M, Minv, prm.pinv_threshold);
-#pragma unroll
-    for (int i = 0; i < NV * NV; ++i) io.c_Minv[i * io.Bc + b] = Minv[i];
   } else if (need_dyn_vals) {
     if (FLAGS & F_OSF) {
 #pragma unroll
@@ -182,25 +187,34 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
       Sm[1 * W + k] = sy * Jm[0 * W + k] + cy * Jm[1 * W + k];
       Sm[2 * W + k] = Jm[2 * W + k];
     }
-    double T[NV * ACT], nleact[ACT], nle_full[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { row_times_S<NV, W>(m, Sm, M + i * NV, 1, T + i * ACT, 1); nle_full[i] = io.c_nle[i * io.Bc + b]; }
-#pragma unroll
-    for (int a = 0; a < ACT; ++a) row_times_S<NV, W>(m, Sm, T + a, ACT, Mact + a, ACT);
-    row_times_S<NV, W>(m, Sm, g, 1, gact, 1);
-    row_times_S<NV, W>(m, Sm, nle_full, 1, nleact, 1);
 #pragma unroll
     for (int i = 0; i < MANI; ++i) qd_act[m.act_mani_start + i] = qd[m.mani_start + i];
 #pragma unroll
     for (int k = 0; k < W; ++k) qd_act[m.act_mobi_start + k] = qd[m.mobi_start + k];
-    if (io.c_Mact) {
-      double Mi[ACT * ACT];
-      spd_pinv<ACT>(Mact, Mi, prm.pinv_threshold);
+    if (FLAGS & F_DYN) {
+      double T[NV * ACT];
 #pragma unroll
-      for (int i = 0; i < ACT * ACT; ++i) { io.c_Mact[i * io.Bc + b] = Mact[i]; io.c_Minvact[i * io.Bc + b] = Mi[i]; }
+      for (int i = 0; i < NV; ++i) row_times_S<NV, W>(m, Sm, M + i * NV, 1, T + i * ACT, 1);
+#pragma unroll
+      for (int a = 0; a < ACT; ++a) row_times_S<NV, W>(m, Sm, T + a, ACT, Mact + a, ACT);
+      row_times_S<NV, W>(m, Sm, g, 1, gact, 1);
+#pragma unroll
+      for (int i = 0; i < ACT; ++i) io.c_gact[i * io.Bc + b] = gact[i];   // the QPID fallback of the solver launch reads it
+      if (!LIGHT) {
+        double nleact[ACT], nle_full[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) nle_full[i] = io.c_nle[i * io.Bc + b];
+        row_times_S<NV, W>(m, Sm, nle_full, 1, nleact, 1);
+        if (io.c_Mact) {
+          double Mi[ACT * ACT];
+          spd_pinv<ACT>(Mact, Mi, prm.pinv_threshold);
+#pragma unroll
+          for (int i = 0; i < ACT * ACT; ++i) { io.c_Mact[i * io.Bc + b] = Mact[i]; io.c_Minvact[i * io.Bc + b] = Mi[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < ACT; ++i) io.c_nleact[i * io.Bc + b] = nleact[i];
+      }
     }
-#pragma unroll
-    for (int i = 0; i < ACT; ++i) { io.c_gact[i * io.Bc + b] = gact[i]; io.c_nleact[i * io.Bc + b] = nleact[i]; }
   }
 
   DRC_PHASE(PH_BUILD);
@@ -286,7 +300,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     // Two routes, chosen by the robot's own data only (so a robot's result does not depend on the launch it sits in): Cholesky when
     // the conditioning certificate holds (drc_kin.h), else the rank-revealing QR.  Where the caller provides a list (main pipeline of
     // the fused QPIK cycle) the uncertified robots are left to a follow-up launch over that list instead of stalling their warps here.
-    int route = MOMA ? 0 : 2;   // whole-body kernels have no follow-up list: the inline fallback would buy nothing there
+    int route = MOMA ? 0 : 2;   // whole-body kernels: the inline fallback would buy nothing (some lane of every warp takes it)
 #ifdef DRC_FORCE_EXACT_MANIP   // test infrastructure: the rank-revealing route for every robot
     route = 0;
 #endif

@@ -40,9 +40,15 @@ struct Scratch {
   int* epa_list; int* epa_count;
   int* nar_k; float* nar_lb;   // split narrow phase: hand-over from the closed-form kernel to the GJK kernel
 };
-constexpr int kPrioSlots = 2048;        // capacity of the priority sub-batch
-constexpr int kPrioMinBatch = 8192;     // batches below this run as one pipeline
-constexpr int kPrioIters = 300;         // previous-tick iteration count from which a robot is "slow"
+#ifndef DRC_PRIO_SLOTS   // lab builds (python -m dyros_robot_controller_b200.build --dev -DDRC_PRIO_SLOTS=...) measure other settings
+#define DRC_PRIO_SLOTS 2048
+#endif
+#ifndef DRC_PRIO_ITERS
+#define DRC_PRIO_ITERS 300
+#endif
+constexpr int kPrioSlots = DRC_PRIO_SLOTS;   // capacity of the priority sub-batch
+constexpr int kPrioMinBatch = 8192;          // batches below this run as one pipeline
+constexpr int kPrioIters = DRC_PRIO_ITERS;   // previous-tick iteration count from which a robot is "slow"
 
 struct drc_ctx {
   const drc_model* model;
@@ -70,10 +76,10 @@ struct drc_ctx {
   int* slow_count;                       // device: number of leading entries of `order` that run in the priority pipeline
   Scratch prio;                          // compact scratch of the priority pipeline (kPrioSlots robots)
   cudaStream_t prio_stream;              // high-priority stream of the priority pipeline
-  cudaEvent_t ev_sched, ev_prio;
+  cudaEvent_t ev_sched, ev_prio, ev_order;   // ev_order: the ADMM schedule (built on the priority stream) is ready
   cudaStream_t last_stream; bool last_stream_set; cudaEvent_t ev_last;  // cross-stream ordering of consecutive calls (pick)
   cudaEvent_t ev_in, ev_out;   // joins of a caller stream with the context's prioritised streams (fused QPIK cycles)
-  cudaStream_t dyn_stream; cudaEvent_t ev_store, ev_dyn;  // fused QPIK cycles: dynamics-only kernel behind the ADMM launch
+  cudaStream_t dyn_stream; cudaEvent_t ev_store, ev_dyn, ev_solve;  // fused QPIK cycles: dynamics-only kernel behind the ADMM launch
   cudaStream_t copy;                     // host entry points: inputs that only stage 2 reads are uploaded here, behind stage 1
   cudaEvent_t ev_late, ev_early; bool late_pending;
   int sm_count;

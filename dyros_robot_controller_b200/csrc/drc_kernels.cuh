@@ -337,8 +337,11 @@ static __device__ __forceinline__ int sched_bucket_of(int iters) {
 #define DRC_ADMM_WARPS 1
 #endif
 constexpr int kAdmmWarps = DRC_ADMM_WARPS;  // one warp per block: a finished warp frees its slot without waiting for block-mates
+#ifndef DRC_ADMM_MINBLOCKS   // lab builds measure other register budgets (blocks per SM; 12 = 168 registers)
+#define DRC_ADMM_MINBLOCKS ((4 * MINB) / kAdmmWarps)
+#endif
 template <class Cfg, bool ID, int MINB>
-__global__ void __launch_bounds__(kAdmmWarps * 32, (4 * MINB) / kAdmmWarps) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
+__global__ void __launch_bounds__(kAdmmWarps * 32, DRC_ADMM_MINBLOCKS) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
 #ifndef DRC_SYNTAX_CHECK
   extern __shared__ __align__(16) unsigned char admm_smem[];  // dynamic: the QPID record exceeds the 48 KB static limit
   GroupShared<Cfg>* sh = reinterpret_cast<GroupShared<Cfg>*>(admm_smem);

@@ -243,7 +243,9 @@ DRC_HD void spd_pinv(const double* A, double* Ainv, double threshold) {
   for (int i = 0; i < N; ++i) maxd = dmax(maxd, A[i * N + i]);
   const double minpiv = chol_inplace<N>(L);
   if (minpiv > 1e-5 * maxd) chol_inverse<N>(L, Ainv);
-  else pinv_cpqr<N, N>(A, Ainv, threshold);
+  // below the guard the rank-revealing factorisation decides, as in the reference: it either truncates (its pseudo-inverse is the
+  // result) or keeps every pivot -- then PinvCOD(A) = A^-1 and the Cholesky factor at hand gives it without forming Q
+  else if (pinv_cpqr<N, N>(A, Ainv, threshold, nullptr, minpiv > 0)) chol_inverse<N>(L, Ainv);
 }
 
 // Cholesky route of the manipulability for a well-conditioned 6 x 6 SPD matrix: inverse, product of the factor's diagonal, and the

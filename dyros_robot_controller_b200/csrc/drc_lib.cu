@@ -45,7 +45,9 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   const int qp_row_off = (id ? QpidCfg<NV>::OFF_ROW : QpikCfg<NV>::OFF_ROW) + (NV + 1);
   const bool sched = c->prm.schedule_hint != 0 && B >= 64;
   const bool prio = sched && fused && B >= kPrioMinBatch;
-  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; mark(c, "schedule", s); }
+  // The schedule is needed by the priority pipeline (its robot list) and by the ADMM launches, not by the main pipeline's front
+  // stages: with a priority pipeline it is built on the priority stream, off the main pipeline's critical path.
+  if (sched && !prio) { rc = launch_schedule(c, B, s); if (rc) return rc; mark(c, "schedule", s); }
 
 #define J(FL, IO, ST) launch_job<NV, CHAIN, FL>(c, fr, IO, ST)
   // QPIK does not read the dynamics (M, M^-1, g, nle of updateState): in fused calls they leave the critical path -- the QP
@@ -67,6 +69,9 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     // ---- priority pipeline: slots [0, *slow_count) of the compact scratch hold robots order[slot]
     CU(cudaStreamWaitEvent(c->prio_stream, c->ev_sched, 0));
     cudaStream_t ps = c->prio_stream;
+    rc = launch_schedule(c, B, ps); if (rc) return rc;
+    mark(c, "schedule", ps);
+    CU(cudaEventRecord(c->ev_order, ps));
     JobIO pio = io;
     pio.B = kPrioSlots; pio.ids = c->order; pio.count = c->slow_count;
     bind_scratch(c->prio, pio);
@@ -144,12 +149,17 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (rc) return rc;
   sio.skip = c->epa_flag;
   if (sched) sio.order = c->order;
-  if (prio) sio.order_off = c->slow_count;   // those robots are solved by the priority pipeline
+  if (prio) { sio.order_off = c->slow_count; CU(cudaStreamWaitEvent(s, c->ev_order, 0)); }   // those robots are solved by the priority pipeline
+  if (split_dyn) CU(cudaEventRecord(c->ev_solve, s));
   rc = id ? launch_admm<QpidCfg<NV>, true>(c, sio, s) : launch_admm<QpikCfg<NV>, false>(c, sio, s);
   if (rc) return rc;
   mark(c, "admm", s);
-  if (split_dyn) {  // enqueued behind the ADMM launch: its blocks are dispatched as the solver's grid drains
-    CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_store, 0));
+  if (split_dyn) {
+    // On the low-priority stream, eligible TOGETHER WITH the main solver launch (ev_solve), not with the front stages: the host
+    // enqueues everything long before the GPU gets there, so a job that only waited for the cached placements would start next to
+    // the narrow phase and take SM room from the critical path (same-box A/B, profiles/: 2.264 -> 2.300e7 cycles/s); behind the
+    // solver's dispatch its blocks fill what the convergence tail leaves idle.
+    CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_solve, 0));
     rc = launch_job<NV, CHAIN, F_DYN | F_FROM_CACHE>(c, fr, io, c->dyn_stream); if (rc) return rc;
     mark(c, "dynamics", c->dyn_stream);
     CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
@@ -431,11 +441,13 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
     CU(cudaEventCreateWithFlags(&c->ev_prio_fk, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio_build, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_sched, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_prio, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithPriority(&c->dyn_stream, cudaStreamNonBlocking, prio_lo));
     CU(cudaEventCreateWithFlags(&c->ev_store, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_dyn, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_solve, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_late, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_early, cudaEventDisableTiming));
   }
@@ -514,6 +526,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->ev_prio_build) cudaEventDestroy(c->ev_prio_build);
     if (c->ev_build) cudaEventDestroy(c->ev_build);
     if (c->ev_sched) cudaEventDestroy(c->ev_sched);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     if (c->ev_prio) cudaEventDestroy(c->ev_prio);
     if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
     if (c->dyn_stream) { cudaStreamSynchronize(c->dyn_stream); cudaStreamDestroy(c->dyn_stream); }
@@ -522,6 +535,7 @@ void drc_ctx_destroy(drc_ctx_t* c) {
     if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->ev_dyn) cudaEventDestroy(c->ev_dyn);
+    if (c->ev_solve) cudaEventDestroy(c->ev_solve);
     if (c->ev_late) cudaEventDestroy(c->ev_late);
     if (c->ev_early) cudaEventDestroy(c->ev_early);
   }

@@ -136,16 +136,21 @@ DRC_HD void chol_inverse(const double* L, double* Ainv) {
 // (|R_ii| > threshold * max|R_ii|) and minimum-norm completion -- what
 // CompleteOrthogonalDecomposition::pseudoInverse() returns (reference math_type_define.h:563-570).
 // Runtime-indexed (local memory); only taken on the rare ill-conditioned path.
+// Two phases: (1) the pivoted factorisation of R with the reflectors kept aside, which fixes the rank; (2) Q from the reflectors (the
+// same updates in the same order as accumulating it on the fly) and the pseudo-inverse.  `stop_if_full_rank`: return true after
+// phase 1 without touching `out` when no pivot is truncated -- the caller then knows that PinvCOD(A) is the plain inverse and takes
+// it by a cheaper route (spd_pinv: whole-body mass matrices sit a factor 1.5 above the rank threshold, every robot came here).
 template <int M, int N>
-DRC_HD_NOINLINE void pinv_cpqr(const double* Ain, double* out /* N x M */, double threshold, double* abs_det = nullptr) {
+DRC_HD_NOINLINE bool pinv_cpqr(const double* Ain, double* out /* N x M */, double threshold, double* abs_det = nullptr,
+                               bool stop_if_full_rank = false) {
   double R[M * N], Q[M * M], v[M];
+  constexpr int K = M < N ? M : N;
+  double V[K * M], vn2s[K];   // reflector k: V[k][k..M), its squared norm (0 = none)
   int perm[N];
   for (int i = 0; i < M * N; ++i) R[i] = Ain[i];
-  for (int i = 0; i < M * M; ++i) Q[i] = 0.0;
-  for (int i = 0; i < M; ++i) Q[i * M + i] = 1.0;
   for (int j = 0; j < N; ++j) perm[j] = j;
-  constexpr int K = M < N ? M : N;
   for (int k = 0; k < K; ++k) {
+    vn2s[k] = 0.0;
     int piv = k;
     double best = -1.0;
     for (int j = k; j < N; ++j) {
@@ -171,12 +176,8 @@ DRC_HD_NOINLINE void pinv_cpqr(const double* Ain, double* out /* N x M */, doubl
       s = 2 * s / vn2;
       for (int i = k; i < M; ++i) R[i * N + j] -= s * v[i];
     }
-    for (int j = 0; j < M; ++j) {
-      double s = 0;
-      for (int i = k; i < M; ++i) s += Q[j * M + i] * v[i];
-      s = 2 * s / vn2;
-      for (int i = k; i < M; ++i) Q[j * M + i] -= s * v[i];
-    }
+    for (int i = k; i < M; ++i) V[k * M + i] = v[i];
+    vn2s[k] = vn2;
   }
   double maxpiv = 0;
   for (int k = 0; k < K; ++k) maxpiv = dmax(maxpiv, fabs(R[k * N + k]));
@@ -187,8 +188,22 @@ DRC_HD_NOINLINE void pinv_cpqr(const double* Ain, double* out /* N x M */, doubl
   }
   int r = 0;
   for (int k = 0; k < K; ++k) if (fabs(R[k * N + k]) > threshold * maxpiv) ++r;
+  if (stop_if_full_rank && r == K) return true;
   for (int i = 0; i < N * M; ++i) out[i] = 0.0;
-  if (r == 0) return;
+  if (r == 0) return false;
+  // phase 2: Q = H_0 H_1 ... applied to the identity
+  for (int i = 0; i < M * M; ++i) Q[i] = 0.0;
+  for (int i = 0; i < M; ++i) Q[i * M + i] = 1.0;
+  for (int k = 0; k < K; ++k) {
+    const double vn2 = vn2s[k];
+    if (vn2 == 0) continue;
+    for (int j = 0; j < M; ++j) {
+      double s = 0;
+      for (int i = k; i < M; ++i) s += Q[j * M + i] * V[k * M + i];
+      s = 2 * s / vn2;
+      for (int i = k; i < M; ++i) Q[j * M + i] -= s * V[k * M + i];
+    }
+  }
   double G[K * K], e[K], Wp[N * K];
   for (int i = 0; i < r; ++i)
     for (int j = 0; j < r; ++j) {
@@ -232,6 +247,7 @@ DRC_HD_NOINLINE void pinv_cpqr(const double* Ain, double* out /* N x M */, doubl
       for (int c = 0; c < r; ++c) s += Wp[l * K + c] * Q[j * M + c];
       out[perm[l] * M + j] = s;
     }
+  return false;
 }
 
 }  // namespace drc

@@ -19,8 +19,13 @@ static int check_moma(const drc_ctx* c, int B) {
 }
 
 constexpr unsigned K_STATE = F_DYN | F_STORE | F_FRAME_OUT | F_MANIP_OUT | F_GRADDOT | F_MOMA;
-constexpr unsigned K_IK = F_DYN | F_STORE | F_QPIK | F_MOMA;
-constexpr unsigned K_ID = F_DYN | F_STORE | F_QPID | F_MOMA;
+// QP-build jobs read the state the F_STORE job (or an earlier updateState) cached.  The whole-body QPIK record is kinematic; the QPID
+// record reads M~ and g~ only.  Everything else updateState owes the cache (nle, the inverses -- the full-model M^-1 goes through the
+// rank-revealing route for these models: 77 % of the old single kernel, ncu round 2) is left to the dynamics-only job K_DYN, which
+// fused calls enqueue behind the solver launch on the low-priority stream.
+constexpr unsigned K_IK = F_FROM_CACHE | F_QPIK | F_MOMA;
+constexpr unsigned K_ID = F_DYN | F_DYN_LIGHT | F_FROM_CACHE | F_QPID | F_MOMA;
+constexpr unsigned K_DYN = F_DYN | F_FROM_CACHE | F_MOMA;
 
 // state update (+ optional getter outputs); q == null: from the cached state
 template <int NV, int W>
@@ -57,6 +62,27 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; }
   // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; EPA pass on the side stream
   if (q) { rc = launch_job<NV, false, F_STORE>(c, fr, io, s); if (rc) return rc; }
+  CU(cudaEventRecord(c->ev_store, s));
+  // stage 2 NEXT TO the narrow phase on its own stream (both only read the cached state): whole-body kinematics, manipulability and
+  // the QP record except the self-collision row.  QPIK: manipulability in two routes as in the manipulator pipeline (Cholesky under
+  // the conditioning certificate, the uncertified robots redone by the rank-revealing route in a follow-up launch over their list).
+  // QPID keeps the rank-revealing route for every robot: its hard-constrained QP (KKT condition ~1e8) turns the last-digit
+  // difference of the two routes into another ADMM path on single robots, and parity with the reference's path comes first.
+  {
+    cudaStream_t bs = c->build_stream;
+    CU(cudaStreamWaitEvent(bs, c->ev_store, 0));
+    JobIO bio = io;
+    if (id) {
+      rc = launch_job<NV, false, K_ID, W>(c, fr, bio, bs); if (rc) return rc;
+    } else {
+      bio.manip_list = c->manip_list; bio.manip_count = c->manip_count;
+      CU(cudaMemsetAsync(c->manip_count, 0, sizeof(int), bs));
+      rc = launch_job<NV, false, K_IK, W>(c, fr, bio, bs); if (rc) return rc;
+      bio.redo = true;
+      rc = launch_job<NV, false, K_IK, W>(c, fr, bio, bs); if (rc) return rc;
+    }
+    CU(cudaEventRecord(c->ev_mbuild, bs));
+  }
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);
   cio.B = B; cio.mode = id ? 2 : 1; cio.qp = c->qp;
@@ -66,10 +92,9 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   rc = launch_collision<NV, false>(c, cio, s, true);
   if (rc) return rc;
   if (c->timing) cudaEventRecord(c->ev[1], s);
-  // stage 2 (next to the EPA pass): whole-body state update and QP record except the self-collision row
-  rc = id ? launch_job<NV, false, K_ID, W>(c, fr, io, s) : launch_job<NV, false, K_IK, W>(c, fr, io, s);
-  if (rc) return rc;
+  CU(cudaStreamWaitEvent(s, c->ev_mbuild, 0));
   if (c->timing) cudaEventRecord(c->ev[2], s);
+  if (q) CU(cudaEventRecord(c->ev_solve, s));   // "the solver launch may start": the dynamics-only job becomes eligible with it
   SolveIO sio;
   std::memset(&sio, 0, sizeof sio);
   sio.B = B; sio.out = out; sio.sout = lay(layout, ACT, B); sio.out2 = out2; sio.sout2 = sio.sout; sio.status = status; sio.iters = iters;
@@ -81,6 +106,14 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   if (sched) sio.order = c->order;
   rc = id ? launch_admm<MomaIdCfg<ACT>, true>(c, sio, s, mani_mask, c->c_gact) : launch_admm<MomaIkCfg<ACT>, false>(c, sio, s, mani_mask, c->c_gact);
   if (rc) return rc;
+  if (q) {  // updateState's dynamics -> cache, behind the solver launch: its blocks fill the SMs the convergence tail leaves idle
+    // (eligible together with the solver launch, not earlier: its long-lived 255-register blocks would otherwise sit on the SMs
+    // while the narrow phase and the QP build -- the critical path -- wait for room)
+    CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_solve, 0));
+    rc = launch_job<NV, false, K_DYN, W>(c, fr, io, c->dyn_stream); if (rc) return rc;
+    CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
+    CU(cudaStreamWaitEvent(s, c->ev_dyn, 0));
+  }
   rc = join_epa(c, s);
   if (c->timing) cudaEventRecord(c->ev[3], s);
   return rc;

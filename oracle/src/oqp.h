@@ -52,6 +52,9 @@ struct QpProblem {
 struct QpResult {
   int status = 0, iters = 0, rho_updates = 0;
   double pri_res = 0, dua_res = 0, rho = 0;
+  // diagnostics of the adaptive-rho decisions (schedule studies): smallest | log(rho_new / rho) | - log(tolerance) | over the
+  // adaptation points (how close a decision was to flipping), and log(rho_new / rho) at the first one
+  double rho_margin = 1e9, rho_first = 0;
   Mat x, y, z;
 };
 
@@ -160,7 +163,7 @@ inline void qp_solve(const QpProblem& pb, const QpSettings& st, QpResult& res, Q
   };
   set_rho();
   res.x.assign(n, 0.0); res.y.assign(m, 0.0); res.z.assign(m, 0.0);
-  res.status = 0; res.iters = 0; res.rho_updates = 0;
+  res.status = 0; res.iters = 0; res.rho_updates = 0; res.rho_margin = 1e9; res.rho_first = 0;
   if (!qp_factor(w, n, m, st.sigma)) { res.status = QP_NON_CVX; return; }
   // ---------------- ADMM (osqp_solve), cold start
   w.x.assign(n, 0.0); w.z.assign(m, 0.0); w.y.assign(m, 0.0);
@@ -300,6 +303,11 @@ inline void qp_solve(const QpProblem& pb, const QpSettings& st, QpResult& res, Q
       double dr = dua_res_s / (dn + 1e-10);
       double rho_new = rho * std::sqrt(pr / (dr + 1e-10));
       rho_new = std::min(std::max(rho_new, OSQP_RHO_MIN), OSQP_RHO_MAX);
+      {
+        const double lr = std::log(rho_new / rho);
+        if (res.rho_margin > 1e8) res.rho_first = lr;
+        res.rho_margin = std::min(res.rho_margin, std::fabs(std::fabs(lr) - std::log(st.adaptive_rho_tolerance)));
+      }
       if (rho_new > rho * st.adaptive_rho_tolerance || rho_new < rho / st.adaptive_rho_tolerance) {
         rho = rho_new;
         for (int i = 0; i < m; ++i) {

@@ -22,6 +22,8 @@ struct OrcHandle {
   // the reference does (new OsqpEigen::Solver per solveQP, QP_base.h:143-177; new pinocchio::Data per getManipulability,
   // robot_data.cpp:542); 0 = one preallocated workspace per thread (optimistic)
   int fresh_workspace = 0;
+  // optional per-robot solver diagnostics of orc_cycle*: [rho_margin, rho_first, rho_updates, final rho] (schedule studies)
+  double* diag = nullptr;
 };
 
 static SE3 pose_from12(const double* a) {
@@ -94,6 +96,7 @@ void orc_model_set_hulls(OrcHandle* h, int nvert_total, const double* verts, con
 void orc_model_destroy(OrcHandle* h) { delete h; }
 void orc_set_threads(OrcHandle* h, int t) { h->threads = t > 0 ? t : 1; }
 void orc_set_fresh_workspace(OrcHandle* h, int on) { h->fresh_workspace = on != 0; }
+void orc_set_diag(OrcHandle* h, double* buf) { h->diag = buf; }
 void orc_set_task_gains(OrcHandle* h, const double* kp, const double* kv) {
   for (int i = 0; i < 6; ++i) { h->cp.Kp_task[i] = kp[i]; h->cp.Kv_task[i] = kv[i]; }
 }
@@ -279,6 +282,7 @@ void orc_cycle_xy(OrcHandle* h, int mode, int B, const double* q, const double* 
       else st = ctrl_qpid(m, ws, frame, des, h->cp, h->gp, h->qs, out + n * b, nullptr);
       if (status) status[b] = st;
       if (iters) iters[b] = ws.res.iters;
+      if (h->diag) { double* d = h->diag + 4 * size_t(b); d[0] = ws.res.rho_margin; d[1] = ws.res.rho_first; d[2] = ws.res.rho_updates; d[3] = ws.res.rho; }
       if (qp_x) std::copy(ws.res.x.begin(), ws.res.x.end(), qp_x + size_t(b) * ws.res.x.size());
       if (qp_y) std::copy(ws.res.y.begin(), ws.res.y.end(), qp_y + size_t(b) * ws.res.y.size());
     }

@@ -417,9 +417,13 @@ static int moma_cycle_t(EmuHandle* h, int mode, int frame_id, int B, const doubl
   const int stride = ID ? MomaIdCfg<ACT>::STRIDE : MomaIkCfg<ACT>::STRIDE;
   std::vector<double> rec((size_t)stride * B, 0.0);
   io.qp = rec.data();
+  // the product's launch sequence (csrc/drc_moma.cu moma_qp): joint placements -> cache; QP record from the cached state (QPIK:
+  // kinematics only, QPID: M~ and g~ only); the dynamics-only job completes the cache
   for (int b = 0; b < B; ++b) {
-    if (!ID) robot_job<NV, false, F_DYN | F_STORE | F_QPIK | F_MOMA, W>(d, h->prm, fr, io, b);
-    else robot_job<NV, false, F_DYN | F_STORE | F_QPID | F_MOMA, W>(d, h->prm, fr, io, b);
+    robot_job<NV, false, F_STORE>(d, h->prm, fr, io, b);
+    if (!ID) robot_job<NV, false, F_FROM_CACHE | F_QPIK | F_MOMA, W>(d, h->prm, fr, io, b);
+    else robot_job<NV, false, F_DYN | F_DYN_LIGHT | F_FROM_CACHE | F_QPID | F_MOMA, W>(d, h->prm, fr, io, b);
+    robot_job<NV, false, F_DYN | F_FROM_CACHE | F_MOMA, W>(d, h->prm, fr, io, b);
   }
   CollisionIO cio;
   std::memset(&cio, 0, sizeof cio);

@@ -52,6 +52,31 @@ def test_moma_model_and_state(rig):
     assert np.abs(r["mani_graddot"] - ref["mani_graddot"]).max() < 1e-8 * max(1.0, np.abs(ref["mani_graddot"]).max())
 
 
+@pytest.mark.parametrize("kind", ["ik", "id"])
+def test_moma_cycle_leaves_the_full_state_cache(rig, kind):
+    """updateState's part of a fused cycle (mobile_manipulator/robot_data.cpp:83-144): the QP-build jobs compute only what their record
+    reads and a dynamics-only job behind the solver launch completes the cache -- every getter must see the NEW state afterwards."""
+    name, d, o, model, ctx = rig
+    f = o.frame_id(LINK)
+    q0, qd0, _, _ = moma_workload(o.model, o.w, 1500, 61)
+    q, qd, q_t, xd = moma_workload(o.model, o.w, 1500, 62)
+    qd = consistent(o, q, qd)
+    x_t = o.update_state(q_t, qd, f)["pose"]
+    ctx.moma_update_state(q0, qd0)                      # an OLD state in the cache
+    ctx.moma_cycle(kind, q, qd, x_t, xd, LINK)
+    ref, full = o.moma_update_state(q, qd, f), o.update_state(q, qd, f)
+    # the cache as the cycle left it (these getters only copy; moma_get_state below re-evaluates the state from the cached q)
+    dyn = ctx.get_dynamics(want=("M", "Minv", "g", "nle"))   # full-model quantities (Manipulator::RobotData getters)
+    assert rel(dyn["M"], full["M"]) < 1e-9 and rel(dyn["g"], full["g"]) < 1e-9 and rel(dyn["nle"], full["nle"]) < 1e-9
+    # PinvCOD with the reference's 1e-6 rank threshold: either the inverse (Husky-FR3, every pivot kept) or the truncated
+    # pseudo-inverse (XLS-FR3); the oracle applies the same rule
+    assert rel(dyn["Minv"], full["Minv"]) < 1e-6
+    r = ctx.moma_get_state(LINK)
+    assert rel(r["pose"], full["pose"]) < 1e-12 and rel(r["J"], ref["J"]) < 1e-12
+    assert rel(r["M"], ref["M"]) < 1e-9 and rel(r["g"], ref["g"]) < 1e-9 and rel(r["nle"], ref["nle"]) < 1e-9
+    assert rel(r["Minv"], ref["Minv"]) < 1e-7
+
+
 @pytest.mark.parametrize("mode,B", [(1, 2000), (3, 1000), (0, 500), (2, 500)])
 def test_moma_control_cycle_matches_oracle(rig, mode, B):
     name, d, o, model, ctx = rig
