@@ -63,6 +63,9 @@ struct JobIO {
   // launch of the same job over this list (`redo`: the launch IS that follow-up; slot index = list entry).  null = exact route.
   int* manip_list; int* manip_count;
   bool redo;
+  // PinvCOD(M) of the full model (robot_data.cpp:118): robots whose mass matrix fails the Cholesky guard of spd_pinv (whole-body
+  // models: every robot) are appended here and k_pinv_list takes their rank-revealing route with 16 lanes per robot.  null = inline.
+  int* pinv_list; int* pinv_count;
 };
 
 template <int NV>
@@ -147,9 +150,18 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
 #pragma unroll
         for (int j = 0; j < NV; ++j) io.c_M[(i * NV + j) * io.Bc + b] = M[i * NV + j];
       }
-      spd_pinv<NV>(M, Minv, prm.pinv_threshold);
+      bool have_inv = true;
+#if defined(__CUDA_ARCH__)
+      if (io.pinv_list) {
+        have_inv = spd_pinv<NV>(M, Minv, prm.pinv_threshold, true);
+        if (!have_inv) io.pinv_list[atomicAdd(io.pinv_count, 1)] = b;
+      } else
+#endif
+        spd_pinv<NV>(M, Minv, prm.pinv_threshold);
+      if (have_inv) {
 #pragma unroll
-      for (int i = 0; i < NV * NV; ++i) io.c_Minv[i * io.Bc + b] = Minv[i];
+        for (int i = 0; i < NV * NV; ++i) io.c_Minv[i * io.Bc + b] = Minv[i];
+      }
     }
   } else if (need_dyn_vals) {
     if (FLAGS & F_OSF) {

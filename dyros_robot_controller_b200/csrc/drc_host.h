@@ -70,6 +70,7 @@ struct drc_ctx {
   int* epa_flag; unsigned long long* cand_mask; double* col_dist; int* col_pair; double* col_wit;
   int* epa_list; int* epa_count;
   int* nar_k; float* nar_lb;
+  int *pinv_list, *pinv_count;           // whole-body models: robots whose full-model PinvCOD(M) goes to k_pinv_list
   int *manip_list, *manip_count;         // two-route manipulability of the main QPIK build: robots left to the exact route
   int *prev_iters, *order, *sched_hist;  // ADMM schedule: previous tick's iteration counts -> robot order (k_sched_*)
   double* roll; int* roll_i;             // rollout scratch (cubic profile; next tick's schedule histogram / offsets / ticket), allocated on first use
@@ -152,6 +153,21 @@ static int launch_job(drc_ctx* c, const DrcFrame& fr, const JobIO& io, cudaStrea
   constexpr int threads = 64;
   const int blocks = io.redo ? 2 * c->sm_count : (io.B + threads - 1) / threads;   // redo: grid-stride over JobIO::manip_list
   k_robot_job<NV, CHAIN, FLAGS, W><<<blocks, threads, 0, s>>>(c->mdev, c->prm, fr, io);
+  c->launches++;
+  CU(cudaGetLastError());
+  return DRC_OK;
+}
+
+// A job that refreshes the full-model dynamics of a whole-body model: the robots whose mass matrix fails the Cholesky guard (all of
+// them for these models) are collected in a list and k_pinv_list takes PinvCOD(M) with 16 lanes per robot, behind the job.
+template <int NV, unsigned FLAGS, int W>
+static int launch_dyn_job(drc_ctx* c, const DrcFrame& fr, JobIO io, cudaStream_t s) {
+  static_assert((FLAGS & F_DYN) && !(FLAGS & F_DYN_LIGHT), "a job that computes M^-1");
+  io.pinv_list = c->pinv_list; io.pinv_count = c->pinv_count;
+  CU(cudaMemsetAsync(c->pinv_count, 0, sizeof(int), s));
+  int rc = launch_job<NV, false, FLAGS, W>(c, fr, io, s);
+  if (rc) return rc;
+  k_pinv_list<NV><<<4 * c->sm_count, 128, 0, s>>>(c->c_M, c->c_Minv, c->cap, c->pinv_list, c->pinv_count, c->prm.pinv_threshold);
   c->launches++;
   CU(cudaGetLastError());
   return DRC_OK;

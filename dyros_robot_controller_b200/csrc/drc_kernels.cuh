@@ -557,6 +557,225 @@ __global__ void __launch_bounds__(kTickThreads) k_tick_front(const __grid_consta
 #endif
 }
 
+// ---- PinvCOD of full-model mass matrices that fail the Cholesky guard of spd_pinv (robot_data.cpp:118; whole-body models: every
+// robot -- the arm's last joint has 1e-6 of the base's inertia, right at the reference's rank threshold), SIXTEEN LANES PER ROBOT.
+// The thread-serial pinv_cpqr keeps R, Q and its work arrays in local memory (runtime pivots): 92 k instructions per robot at an IPC
+// of 0.04, 77 % of the whole-body state kernel (ncu, round 2).  Here lane j of a group owns column j of R during the pivoted
+// factorisation and row j of Q afterwards, in registers (the pivot loop is unrolled, a column's POSITION is a register); the
+// pivot column, the reflectors and the final R travel through shared memory as broadcasts.  Same algorithm and rank rule as
+// pinv_cpqr: A P = Q R, r = #{|R_kk| > threshold max|R_kk|}, pinv(A) = P pinv(R_1) Q_1' with R_1 = R_11 [I X] the first r rows:
+//   pinv(R_1) = [I; X'] (I + X X')^-1 R_11^-1,  (I + X X')^-1 = I - X (I + X'X)^-1 X'   (X is r x (N - r): N - r is 0 or 1 here),
+// i.e. two triangular solves per lane instead of the Gram matrix, its Cholesky factor and r solves of the serial routine.
+constexpr int kPinvMaxDrop = 4;   // columns dropped by the rank rule that the lane-parallel path handles (more: serial routine)
+template <int N>
+struct PinvGroupSmem {
+  double piv[16];
+  double V[N][N];
+  double vn2[N];
+  double R[N][N];                 // final R, columns by POSITION
+  double X[N][kPinvMaxDrop];
+  int perm[16];                   // position -> original column
+};
+template <int N>
+__global__ void __launch_bounds__(128) k_pinv_list(const double* c_M, double* c_Minv, long long Bc, const int* list, const int* count,
+                                                    double threshold) {
+#ifndef DRC_SYNTAX_CHECK
+  static_assert(N <= 16, "one lane per column");
+  __shared__ PinvGroupSmem<N> sm[8];
+  const int lane = threadIdx.x & 31, g = lane & 15, grp = threadIdx.x >> 4;
+  PinvGroupSmem<N>& S = sm[grp];
+  const unsigned gmask = 0xffffu << (lane & 16);
+  const bool act = g < N;
+  const int n = *count, ngroups = gridDim.x * 8;
+  for (int it = blockIdx.x * 8 + grp; it < n; it += ngroups) {
+    const int b = list[it];
+    double col[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i] = act ? c_M[(long long)(i * N + g) * Bc + b] : 0.0;   // column g (M is symmetric)
+    int pos = g;
+    // ---- phase 1: Householder factorisation with column pivoting
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double bn = -1.0;
+      if (act && pos >= k) {
+        bn = 0.0;
+#pragma unroll
+        for (int i = k; i < N; ++i) bn += col[i] * col[i];
+      }
+      int bp = pos;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) {   // largest remaining column norm, ties to the smaller position (pinv_cpqr's scan order)
+        const double on = __shfl_xor_sync(gmask, bn, off, 16);
+        const int op = __shfl_xor_sync(gmask, bp, off, 16);
+        if (on > bn || (on == bn && op < bp)) { bn = on; bp = op; }
+      }
+      if (act) { if (pos == bp) pos = k; else if (pos == k) pos = bp; }
+      const double nrm = sqrt(bn);
+      double vn2 = 0.0;
+      if (nrm != 0.0) {
+        if (act && pos == k) {
+#pragma unroll
+          for (int i = k; i < N; ++i) S.piv[i] = col[i];
+        }
+        __syncwarp(gmask);
+        double v[N];
+#pragma unroll
+        for (int i = k; i < N; ++i) v[i] = S.piv[i];
+        const double alpha = v[k] > 0 ? -nrm : nrm;
+        v[k] -= alpha;
+#pragma unroll
+        for (int i = k; i < N; ++i) vn2 += v[i] * v[i];
+        if (vn2 != 0.0) {
+          if (act && pos >= k) {
+            double sc = 0.0;
+#pragma unroll
+            for (int i = k; i < N; ++i) sc += v[i] * col[i];
+            sc = 2 * sc / vn2;
+#pragma unroll
+            for (int i = k; i < N; ++i) col[i] -= sc * v[i];
+          }
+          if (g == 0) {
+#pragma unroll
+            for (int i = k; i < N; ++i) S.V[k][i] = v[i];
+          }
+        }
+        __syncwarp(gmask);
+      }
+      if (g == 0) S.vn2[k] = vn2;
+    }
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) S.R[i][pos] = col[i];
+      S.perm[pos] = g;
+    }
+    __syncwarp(gmask);
+    double maxpiv = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) maxpiv = dmax(maxpiv, fabs(S.R[k][k]));
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) if (fabs(S.R[k][k]) > threshold * maxpiv) ++r;
+    const int d = N - r;
+    if (r == 0 || d > kPinvMaxDrop) {
+      if (g == 0) {   // outside the lane-parallel path: the serial routine (never seen for a mass matrix)
+        double A[N * N], P[N * N];
+        for (int i = 0; i < N * N; ++i) A[i] = c_M[(long long)i * Bc + b];
+        pinv_cpqr<N, N>(A, P, threshold);
+        for (int i = 0; i < N * N; ++i) c_Minv[(long long)i * Bc + b] = P[i];
+      }
+      __syncwarp(gmask);
+      continue;
+    }
+    // ---- phase 2: row g of Q = e_g' H_0 H_1 ...
+    double y[N];
+    {
+      double qrow[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) qrow[i] = (i == g) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const double vn2 = S.vn2[k];
+        if (vn2 != 0.0) {
+          double sc = 0.0;
+#pragma unroll
+          for (int i = k; i < N; ++i) sc += qrow[i] * S.V[k][i];
+          sc = 2 * sc / vn2;
+#pragma unroll
+          for (int i = k; i < N; ++i) qrow[i] -= sc * S.V[k][i];
+        }
+      }
+      // y = R_11^-1 (Q_1' e_g)
+#pragma unroll
+      for (int i = N - 1; i >= 0; --i) {
+        y[i] = 0.0;
+        if (i < r) {
+          double sc = qrow[i];
+#pragma unroll
+          for (int l = i + 1; l < N; ++l) if (l < r) sc -= S.R[i][l] * y[l];
+          y[i] = sc / S.R[i][i];
+        }
+      }
+    }
+    if (d > 0) {
+      if (g < d) {   // X = R_11^-1 R_12, one dropped column per lane
+        double x[N];
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+          x[i] = 0.0;
+          if (i < r) {
+            double sc = S.R[i][r + g];
+#pragma unroll
+            for (int l = i + 1; l < N; ++l) if (l < r) sc -= S.R[i][l] * x[l];
+            x[i] = sc / S.R[i][i];
+          }
+          S.X[i][g] = x[i];
+        }
+      }
+      __syncwarp(gmask);
+      // u = (I + X'X)^-1 X'y  (d x d, every lane on its own copy), then z = y - X u
+      double w[kPinvMaxDrop], G[kPinvMaxDrop][kPinvMaxDrop];
+#pragma unroll
+      for (int c = 0; c < kPinvMaxDrop; ++c) {
+        w[c] = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < kPinvMaxDrop; ++c2) G[c][c2] = (c == c2) ? 1.0 : 0.0;
+        if (c < d) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) w[c] += S.X[i][c] * y[i];   // rows >= r of X and y are zero
+#pragma unroll
+          for (int c2 = 0; c2 < kPinvMaxDrop; ++c2) {
+            if (c2 < d) {
+              double sc = 0.0;
+#pragma unroll
+              for (int i = 0; i < N; ++i) sc += S.X[i][c] * S.X[i][c2];
+              G[c][c2] += sc;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < kPinvMaxDrop; ++p) {   // SPD: elimination without pivoting (rows / columns >= d are the identity)
+#pragma unroll
+        for (int q2 = p + 1; q2 < kPinvMaxDrop; ++q2) {
+          const double f = G[q2][p] / G[p][p];
+#pragma unroll
+          for (int t = p; t < kPinvMaxDrop; ++t) G[q2][t] -= f * G[p][t];
+          w[q2] -= f * w[p];
+        }
+      }
+#pragma unroll
+      for (int p = kPinvMaxDrop - 1; p >= 0; --p) {
+        double sc = w[p];
+#pragma unroll
+        for (int t = p + 1; t < kPinvMaxDrop; ++t) sc -= G[p][t] * w[t];
+        w[p] = sc / G[p][p];
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        if (i < r) {
+#pragma unroll
+          for (int c = 0; c < kPinvMaxDrop; ++c) if (c < d) y[i] -= S.X[i][c] * w[c];
+        }
+      }
+    }
+    // column g of the pseudo-inverse: positions < r take z, the dropped ones X'z; rows back in the original order
+    if (act) {
+#pragma unroll
+      for (int p = 0; p < N; ++p) {
+        double val = y[p];
+        if (p >= r) {
+          val = 0.0;
+#pragma unroll
+          for (int i = 0; i < N; ++i) val += S.X[i][p - r] * y[i];
+        }
+        c_Minv[(long long)(S.perm[p] * N + g) * Bc + b] = val;
+      }
+    }
+    __syncwarp(gmask);
+  }
+#endif
+}
+
 // cache (SoA [K][Bc]) -> user array; `sub` != null writes src - sub (coriolis = nle - g)
 static __global__ void k_copy_cache(const double* src, const double* sub, long long Bc, int K, int B, double* dst, Strided s) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -233,8 +233,10 @@ DRC_HD void rnea_bias(const DrcModelDev& m, const KinState<NV>& k, const Spatial
 // Inverse of the SPD mass matrix.  The reference uses PinvCOD(M) (robot_data.cpp:118); for a
 // positive-definite M that is the inverse, taken here by Cholesky, with the rank-revealing route
 // as the guard for (near-)singular input.
+// `defer`: when the guard fails, return false with Ainv untouched -- the caller hands the robot to the group-cooperative
+// rank-revealing kernel (k_pinv_list) instead of running the thread-serial routine here.
 template <int N>
-DRC_HD void spd_pinv(const double* A, double* Ainv, double threshold) {
+DRC_HD bool spd_pinv(const double* A, double* Ainv, double threshold, bool defer = false) {
   double L[N * N];
   double maxd = 0;
 #pragma unroll
@@ -242,10 +244,12 @@ DRC_HD void spd_pinv(const double* A, double* Ainv, double threshold) {
 #pragma unroll
   for (int i = 0; i < N; ++i) maxd = dmax(maxd, A[i * N + i]);
   const double minpiv = chol_inplace<N>(L);
-  if (minpiv > 1e-5 * maxd) chol_inverse<N>(L, Ainv);
+  if (minpiv > 1e-5 * maxd) { chol_inverse<N>(L, Ainv); return true; }
+  if (defer) return false;
   // below the guard the rank-revealing factorisation decides, as in the reference: it either truncates (its pseudo-inverse is the
   // result) or keeps every pivot -- then PinvCOD(A) = A^-1 and the Cholesky factor at hand gives it without forming Q
-  else if (pinv_cpqr<N, N>(A, Ainv, threshold, nullptr, minpiv > 0)) chol_inverse<N>(L, Ainv);
+  if (pinv_cpqr<N, N>(A, Ainv, threshold, nullptr, minpiv > 0)) chol_inverse<N>(L, Ainv);
+  return true;
 }
 
 // Cholesky route of the manipulability for a well-conditioned 6 x 6 SPD matrix: inverse, product of the factor's diagonal, and the

@@ -401,6 +401,8 @@ static int ctx_create_impl(drc_ctx* c, const drc_model_t* m, int device, int max
   CU(dalloc(&c->col_dist, B));
   CU(cudaMalloc((void**)&c->col_pair, B * sizeof(int)));
   CU(dalloc(&c->col_wit, 6 * B));
+  CU(cudaMalloc((void**)&c->pinv_list, B * sizeof(int)));
+  CU(cudaMalloc((void**)&c->pinv_count, sizeof(int)));
   CU(cudaMalloc((void**)&c->manip_list, B * sizeof(int)));
   CU(cudaMalloc((void**)&c->manip_count, sizeof(int)));
   CU(cudaMalloc((void**)&c->nar_k, B * sizeof(int)));
@@ -497,6 +499,8 @@ void drc_ctx_destroy(drc_ctx_t* c) {
   if (c->epa_flag) cudaFree(c->epa_flag);
   if (c->cand_mask) cudaFree(c->cand_mask);
   if (c->col_pair) cudaFree(c->col_pair);
+  if (c->pinv_list) cudaFree(c->pinv_list);
+  if (c->pinv_count) cudaFree(c->pinv_count);
   if (c->manip_list) cudaFree(c->manip_list);
   if (c->manip_count) cudaFree(c->manip_count);
   if (c->nar_k) cudaFree(c->nar_k);

@@ -41,7 +41,7 @@ static int moma_state(drc_ctx* c, int B, const double* q, const double* qd, int 
   io.mani = mani; io.mani_grad = mgrad; io.smg = lay(layout, MANI, B); io.mani_graddot = mgraddot; io.smgd = io.smg;
   DrcFrame fr; std::memset(&fr, 0, sizeof fr); fr.parent = -1;
   if (frame >= 0) fr = frame_of(c->model, frame);
-  return launch_job<NV, false, K_STATE, W>(c, fr, io, s);
+  return launch_dyn_job<NV, K_STATE, W>(c, fr, io, s);
 }
 
 template <int NV, int W>
@@ -110,7 +110,7 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
     // (eligible together with the solver launch, not earlier: its long-lived 255-register blocks would otherwise sit on the SMs
     // while the narrow phase and the QP build -- the critical path -- wait for room)
     CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_solve, 0));
-    rc = launch_job<NV, false, K_DYN, W>(c, fr, io, c->dyn_stream); if (rc) return rc;
+    rc = launch_dyn_job<NV, K_DYN, W>(c, fr, io, c->dyn_stream); if (rc) return rc;
     CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
     CU(cudaStreamWaitEvent(s, c->ev_dyn, 0));
   }

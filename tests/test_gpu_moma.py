@@ -52,6 +52,30 @@ def test_moma_model_and_state(rig):
     assert np.abs(r["mani_graddot"] - ref["mani_graddot"]).max() < 1e-8 * max(1.0, np.abs(ref["mani_graddot"]).max())
 
 
+def test_full_model_pinv_cod_against_lapack(rig):
+    """PinvCOD(M) of the full model (robot_data.cpp:118, COD threshold 1e-6) as k_pinv_list computes it with 16 lanes per robot,
+    against an independent statement: LAPACK's column-pivoted QR (scipy), the rank rule |R_kk| > 1e-6 max|R_kk|, numpy's pinv of the
+    kept rows.  Husky-FR3 keeps every pivot (the result is the inverse), XLS-FR3 drops one (a rank-13 pseudo-inverse)."""
+    import scipy.linalg as sl
+    name, d, o, model, ctx = rig
+    q, qd, _, _ = moma_workload(o.model, o.w, 300, 77)
+    ctx.moma_update_state(q, qd)
+    dyn = ctx.get_dynamics(want=("M", "Minv"))
+    ranks = []
+    for M, Mi in zip(dyn["M"], dyn["Minv"]):
+        Q, R, P = sl.qr(M, pivoting=True)
+        dg = np.abs(np.diag(R))
+        r = int((dg > 1e-6 * dg.max()).sum())
+        ranks.append(r)
+        ref = np.zeros_like(M)
+        ref[P, :] = np.linalg.pinv(R[:r, :]) @ Q[:, :r].T
+        assert np.abs(Mi - ref).max() < 1e-7 * np.abs(ref).max()
+        if r == M.shape[0]:   # (the truncated COD pseudo-inverse is not symmetric: dropping R_22 perturbs M unsymmetrically)
+            assert np.abs(Mi - Mi.T).max() < 1e-7 * np.abs(ref).max()
+    n = dyn["M"].shape[1]
+    assert set(ranks) == ({n} if name == "husky_fr3" else {n - 1})
+
+
 @pytest.mark.parametrize("kind", ["ik", "id"])
 def test_moma_cycle_leaves_the_full_state_cache(rig, kind):
     """updateState's part of a fused cycle (mobile_manipulator/robot_data.cpp:83-144): the QP-build jobs compute only what their record
