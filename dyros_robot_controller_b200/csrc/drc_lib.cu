@@ -56,7 +56,8 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   const bool split_dyn = fused && !id;
   auto build = [&](const JobIO& jio, cudaStream_t st) -> int {  // state update, manipulability, QP record except the collision row
     if (!id) return step ? J(F_FROM_CACHE | F_QPIK | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPIK, jio, st);
-    if (fused) return step ? J(F_DYN | F_STORE | F_QPID | F_STEP, jio, st) : J(F_DYN | F_STORE | F_QPID, jio, st);
+    // (fused: from the state stage 1a has just cached -- the job runs next to the narrow phase, which reads those placements)
+    if (fused) return step ? J(F_DYN | F_FROM_CACHE | F_QPID | F_STEP, jio, st) : J(F_DYN | F_FROM_CACHE | F_QPID, jio, st);
     return step ? J(F_FROM_CACHE | F_QPID | F_STEP, jio, st) : J(F_FROM_CACHE | F_QPID, jio, st);
   };
 
@@ -105,7 +106,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   }
 
   // ---- main pipeline
-  const bool par_build = c->par_build && fused && !id && prio;
+  const bool par_build = c->par_build && fused && prio;
   if (par_build) {
     // the QP build only needs the cached joint placements: it runs NEXT TO the narrow phase on its own stream.  (Round 1 rejected this
     // with the monolithic 255-register collision kernel; with the closed-form stage in a 128-register kernel and the GJK stage waiting
@@ -115,11 +116,15 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
     // two-route manipulability: Cholesky under a conditioning certificate, the rest (~10-15 % of random states) redone by the
     // rank-revealing route in a follow-up launch over their list -- the 6 x 6 column-pivoted QR was 73 % of this kernel
     JobIO bio = io;
-    bio.manip_list = c->manip_list; bio.manip_count = c->manip_count;
-    CU(cudaMemsetAsync(c->manip_count, 0, sizeof(int), c->build_stream));
-    rc = build(bio, c->build_stream); if (rc) return rc;
-    bio.redo = true;
-    rc = build(bio, c->build_stream); if (rc) return rc;
+    if (id) {   // QPID: state update + dynamics + record in one job (inline manipulability fallback), still next to the narrow phase
+      rc = build(bio, c->build_stream); if (rc) return rc;
+    } else {
+      bio.manip_list = c->manip_list; bio.manip_count = c->manip_count;
+      CU(cudaMemsetAsync(c->manip_count, 0, sizeof(int), c->build_stream));
+      rc = build(bio, c->build_stream); if (rc) return rc;
+      bio.redo = true;
+      rc = build(bio, c->build_stream); if (rc) return rc;
+    }
     mark(c, "build", c->build_stream);
     CU(cudaEventRecord(c->ev_mbuild, c->build_stream));
   }
