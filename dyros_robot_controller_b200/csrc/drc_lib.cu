@@ -156,6 +156,7 @@ static int run_qp(drc_ctx* c, int B, bool id, bool step, const double* q, const 
   if (sched) sio.order = c->order;
   if (prio) { sio.order_off = c->slow_count; CU(cudaStreamWaitEvent(s, c->ev_order, 0)); }   // those robots are solved by the priority pipeline
   if (split_dyn) CU(cudaEventRecord(c->ev_solve, s));
+  mark(c, "admm_begin", s);   // admm - admm_begin = the main solver launch in situ
   rc = id ? launch_admm<QpidCfg<NV>, true>(c, sio, s) : launch_admm<QpikCfg<NV>, false>(c, sio, s);
   if (rc) return rc;
   mark(c, "admm", s);

@@ -56,12 +56,12 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   io.qp = c->qp;
   bind_cache(c, io);
   const DrcFrame fr = frame_of(c->model, frame);
-  if (c->timing) cudaEventRecord(c->ev[0], s);
+  if (c->timing) { cudaEventRecord(c->ev[0], s); c->tr_n = 0; mark(c, "start", s); }
   int rc = DRC_OK;
   const bool sched = c->prm.schedule_hint != 0 && B >= 64;
-  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; }
+  if (sched) { rc = launch_schedule(c, B, s); if (rc) return rc; mark(c, "schedule", s); }
   // stage 1: joint placements -> cache (fused calls), self-collision narrow phase; EPA pass on the side stream
-  if (q) { rc = launch_job<NV, false, F_STORE>(c, fr, io, s); if (rc) return rc; }
+  if (q) { rc = launch_job<NV, false, F_STORE>(c, fr, io, s); if (rc) return rc; mark(c, "fk", s); }
   CU(cudaEventRecord(c->ev_store, s));
   // stage 2 NEXT TO the narrow phase on its own stream (both only read the cached state): whole-body kinematics, manipulability and
   // the QP record except the self-collision row.  QPIK: manipulability in two routes as in the manipulator pipeline (Cholesky under
@@ -81,6 +81,7 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
       bio.redo = true;
       rc = launch_job<NV, false, K_IK, W>(c, fr, bio, bs); if (rc) return rc;
     }
+    mark(c, "build", bs);
     CU(cudaEventRecord(c->ev_mbuild, bs));
   }
   CollisionIO cio;
@@ -91,7 +92,7 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   cio.row_n = ACT; cio.row_col0 = d.act_mani_start; cio.src0 = d.mani_start; cio.nsrc = MANI;
   rc = launch_collision<NV, false>(c, cio, s, true);
   if (rc) return rc;
-  if (c->timing) cudaEventRecord(c->ev[1], s);
+  if (c->timing) { cudaEventRecord(c->ev[1], s); mark(c, "collision", s); }
   CU(cudaStreamWaitEvent(s, c->ev_mbuild, 0));
   if (c->timing) cudaEventRecord(c->ev[2], s);
   if (q) CU(cudaEventRecord(c->ev_solve, s));   // "the solver launch may start": the dynamics-only job becomes eligible with it
@@ -104,18 +105,22 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   if (rc) return rc;
   sio.skip = c->epa_flag;
   if (sched) sio.order = c->order;
+  mark(c, "admm_begin", s);   // admm - admm_begin = the main solver launch in situ (next to the EPA pass and the dynamics job)
   rc = id ? launch_admm<MomaIdCfg<ACT>, true>(c, sio, s, mani_mask, c->c_gact) : launch_admm<MomaIkCfg<ACT>, false>(c, sio, s, mani_mask, c->c_gact);
   if (rc) return rc;
+  mark(c, "admm", s);
   if (q) {  // updateState's dynamics -> cache, behind the solver launch: its blocks fill the SMs the convergence tail leaves idle
     // (eligible together with the solver launch, not earlier: its long-lived 255-register blocks would otherwise sit on the SMs
     // while the narrow phase and the QP build -- the critical path -- wait for room)
     CU(cudaStreamWaitEvent(c->dyn_stream, c->ev_solve, 0));
     rc = launch_dyn_job<NV, K_DYN, W>(c, fr, io, c->dyn_stream); if (rc) return rc;
+    mark(c, "dynamics", c->dyn_stream);
     CU(cudaEventRecord(c->ev_dyn, c->dyn_stream));
     CU(cudaStreamWaitEvent(s, c->ev_dyn, 0));
   }
   rc = join_epa(c, s);
-  if (c->timing) cudaEventRecord(c->ev[3], s);
+  mark(c, "epa_robots", s);
+  if (c->timing) { cudaEventRecord(c->ev[3], s); mark(c, "end", s); }
   return rc;
 }
 

@@ -1,0 +1,79 @@
+"""GPU edge cases of the control-cycle path (through the C ABI): ragged batch sizes, batch-size independence of every robot's
+result, non-finite inputs, empty batches.  The reference runs one robot per process (examples/C++/src/fr3_controller.cpp:116-134),
+so "a robot's result is a function of that robot's inputs only" is the property a batched drop-in has to keep bit for bit."""
+import numpy as np
+import pytest
+
+from tests.conftest import LINK, workload
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(ctx, oracle, B, seed):
+    q, qd, q_t, xdot_t = workload(oracle.model, B, seed, stress=True)
+    ctx.update_state(q_t, qd)
+    x_t = ctx.get_frame(LINK, want=("pose",))["pose"]
+    return q, qd, x_t, xdot_t
+
+
+@pytest.mark.parametrize("kind", ["ik", "id"])
+def test_ragged_batches_equal_the_rows_of_a_large_one(gpu_ctx, oracle, kind):
+    """Prefixes of 1 ... 8191 robots (partial warps, partial blocks, below / above the priority-pipeline batch threshold, with and
+    without a schedule from an earlier call) return exactly the rows the 8192-robot call returns."""
+    model, ctx = gpu_ctx
+    B = 8192
+    q, qd, x_t, xdot_t = _inputs(ctx, oracle, B, 21)
+    call = ctx.cycle_qpik_step if kind == "ik" else ctx.cycle_qpid_step
+    full = call(q, qd, x_t, xdot_t, LINK)
+    full = {k: np.array(full[k], copy=True) for k in ("out", "status", "iters")}
+    for n in (1, 2, 3, 4, 31, 33, 95, 129, 1000, 8191):
+        r = call(q[:n], qd[:n], x_t[:n], xdot_t[:n], LINK)
+        assert np.array_equal(r["status"], full["status"][:n]), (kind, n)
+        assert np.array_equal(r["iters"], full["iters"][:n]), (kind, n)
+        assert np.array_equal(r["out"], full["out"][:n]), (kind, n)
+    # a strided subset, in another order
+    idx = np.arange(B - 1, 0, -7)
+    r = call(q[idx], qd[idx], x_t[idx], xdot_t[idx], LINK)
+    assert np.array_equal(r["iters"], full["iters"][idx]) and np.array_equal(r["out"], full["out"][idx])
+
+
+def test_nonfinite_inputs_stay_in_their_robot(gpu_ctx, oracle):
+    """NaN / Inf joint states or targets: the call returns, the affected robots report failure with the reference's fallback (zeros,
+    robot_controller.cpp:283-287 -- OSQP never reports `solved` on non-finite data), every other robot's result is bit-identical."""
+    model, ctx = gpu_ctx
+    B = 4096
+    q, qd, x_t, xdot_t = _inputs(ctx, oracle, B, 22)
+    clean = ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)
+    clean = {k: np.array(clean[k], copy=True) for k in ("out", "status", "iters")}
+    q2, qd2, x2, xd2 = q.copy(), qd.copy(), x_t.copy(), xdot_t.copy()
+    bad = np.array([0, 1, 32, 100, 1025, 2047, 4095])
+    q2[0, 3] = np.nan
+    q2[1, :] = np.inf
+    qd2[32, 0] = np.nan
+    x2[100, 0] = np.nan
+    xd2[1025, 5] = -np.inf
+    q2[2047, 6] = np.nan
+    x2[4095, 11] = np.nan
+    r = ctx.cycle_qpik_step(q2, qd2, x2, xd2, LINK)
+    good = np.ones(B, bool)
+    good[bad] = False
+    assert np.array_equal(r["out"][good], clean["out"][good])
+    assert np.array_equal(r["iters"][good], clean["iters"][good]) and np.array_equal(r["status"][good], clean["status"][good])
+    assert (r["status"][bad] != 1).all(), r["status"][bad]
+    assert np.array_equal(r["out"][bad], np.zeros((bad.size, 7))), r["out"][bad]
+    # and the context is healthy afterwards
+    again = ctx.cycle_qpik_step(q, qd, x_t, xdot_t, LINK)
+    assert np.array_equal(again["out"], clean["out"]) and np.array_equal(again["iters"], clean["iters"])
+
+
+def test_empty_and_oversized_batches_are_rejected(gpu_ctx):
+    from dyros_robot_controller_b200._capi import DrcError
+    model, ctx = gpu_ctx
+    z7, z12, z6 = np.zeros((0, 7)), np.zeros((0, 12)), np.zeros((0, 6))
+    with pytest.raises(DrcError):
+        ctx.update_state(z7, z7)
+    with pytest.raises(DrcError):
+        ctx.cycle_qpik_step(z7, z7, z12, z6, LINK)
+    big = np.zeros((65537, 7))
+    with pytest.raises(DrcError):
+        ctx.update_state(big, big)
