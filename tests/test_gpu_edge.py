@@ -77,3 +77,38 @@ def test_empty_and_oversized_batches_are_rejected(gpu_ctx):
     big = np.zeros((65537, 7))
     with pytest.raises(DrcError):
         ctx.update_state(big, big)
+
+
+@pytest.mark.parametrize("robot", ["husky_fr3", "xls_fr3"])
+@pytest.mark.parametrize("kind", ["ik", "id"])
+def test_whole_body_ragged_batches_and_nonfinite_inputs(robot, kind):
+    """The same two properties on the mobile-manipulator path (two robots per warp / one per warp, EPA pass on a side stream,
+    dynamics job behind the solver): prefixes return the rows of the large call bit for bit; a NaN state fails alone."""
+    import dyros_robot_controller_b200 as drc
+    from tests.conftest import MOMA, moma_workload
+    d = MOMA[robot]
+    model = drc.Model(d["urdf"], d["srdf"]).attach_mobile_base(d["kin"], d["joint_idx"], d["actuator_idx"])
+    ctx = drc.Context(model, 4096, device=0)
+
+    class _M:   # moma_workload reads the joint limits off an oracle-like object
+        q_lo, q_hi, v_lim = model.q_lower, model.q_upper, model.v_limit
+    B = 4096
+    q, qd, q_t, xdot_t = moma_workload(_M, model.wheel_num, B, 41)
+    ctx.moma_update_state(q_t, qd)
+    x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
+    full = ctx.moma_cycle(kind, q, qd, x_t, xdot_t, LINK)
+    full = {k: np.array(full[k], copy=True) for k in ("out", "status", "iters")}
+    for n in (1, 2, 3, 33, 129, 1000, 4095):
+        r = ctx.moma_cycle(kind, q[:n], qd[:n], x_t[:n], xdot_t[:n], LINK)
+        assert np.array_equal(r["status"], full["status"][:n]), (robot, kind, n)
+        assert np.array_equal(r["iters"], full["iters"][:n]), (robot, kind, n)
+        assert np.array_equal(r["out"], full["out"][:n]), (robot, kind, n)
+    q2 = q.copy()
+    bad = np.array([0, 63, 2048, 4095])
+    q2[bad, 3 + model.wheel_num + 2] = np.nan   # an arm joint (a mecanum wheel ANGLE enters neither the kinematics nor the QPIK record)
+    r = ctx.moma_cycle(kind, q2, qd, x_t, xdot_t, LINK)
+    good = np.ones(B, bool)
+    good[bad] = False
+    assert np.array_equal(r["out"][good], full["out"][good]) and np.array_equal(r["iters"][good], full["iters"][good])
+    assert (r["status"][bad] != 1).all()
+    assert np.isfinite(r["out"][bad]).all() if kind == "ik" else True   # QPIK failure = zeros; QPID failure = gravity of a NaN state
