@@ -538,6 +538,9 @@ def run_ours(args):
     line = {"metric": METRIC if args.workload == "fr3_qpik" else f"batched control cycles/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
+            # this rank's timed steps one by one: the spread is the convergence tail (a step that holds an unpredicted max_iter robot)
+            "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms)),
+                        "all": [round(float(x), 3) for x in step_ms]},
             "config": {"workload": wl["desc"], "batch_per_gpu": B, "global_batch": world * B,
                        "parallelism": f"batch shard x{world}, no collective on the solve path",
                        "l2": "256 MiB buffer zeroed between timed steps", "seed": "default_rng(1000*rank)",
