@@ -217,6 +217,42 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
+def latency_b1(ctx, n_cpu: int = 3000, n_gpu: int = 1000):
+    """BASELINE configs[0]: ONE FR3 updateState + QPIKStep control cycle (batch 1), the case the reference itself runs -- latency of
+    the CPU port in reference-faithful mode on one thread (median and p99 after a warm-up) next to the latency of the same
+    cycle through drc_host_cycle_qpik_step on the GPU (host buffers in, host buffers out, synchronous).  Different robot state per call."""
+    from oracle.c_oracle import Oracle
+    urdf, srdf = robot_paths("fr3")
+    o = Oracle(urdf, srdf, threads=1)
+    f = o.frame_id(LINK)
+
+    class M:
+        dof, q_lower, q_upper, v_limit = o.nv, o.model.q_lo, o.model.q_hi, o.model.v_lim
+    n = max(n_cpu, n_gpu)
+    q, qd, q_t, xdot_t = make_workload(M, n, 123)
+    x_t = o.update_state(q_t, qd, f)["pose"]
+    o.set_fresh_workspace(True)
+    o.set_geom_params(gjk_tol=1e-6)
+    for i in range(200):
+        o.cycle(1, q[i:i + 1], qd[i:i + 1], x_t[i:i + 1], xdot_t[i:i + 1], f)
+    tc = np.empty(n_cpu)
+    for i in range(n_cpu):
+        t0 = time.perf_counter()
+        o.cycle(1, q[i:i + 1], qd[i:i + 1], x_t[i:i + 1], xdot_t[i:i + 1], f)
+        tc[i] = time.perf_counter() - t0
+    for i in range(50):
+        ctx.cycle_qpik_step(q[i:i + 1], qd[i:i + 1], x_t[i:i + 1], xdot_t[i:i + 1], LINK)
+    tg = np.empty(n_gpu)
+    for i in range(n_gpu):
+        t0 = time.perf_counter()
+        ctx.cycle_qpik_step(q[i:i + 1], qd[i:i + 1], x_t[i:i + 1], xdot_t[i:i + 1], LINK)
+        tg[i] = time.perf_counter() - t0
+    us = lambda a, p_: float(np.percentile(a, p_) * 1e6)
+    return {"workload": "FR3 updateState+QPIKStep, batch 1 (BASELINE configs[0]); per-call wall time incl. the Python / ctypes call",
+            "cpu_us": {"median": us(tc, 50), "p99": us(tc, 99), "calls": n_cpu, "mode": "oracle port, one thread, reference-faithful"},
+            "gpu_us": {"median": us(tg, 50), "p99": us(tg, 99), "calls": n_gpu, "path": "drc_host_cycle_qpik_step, pageable host buffers"}}
+
+
 def oracle_cycles_per_s(B: int, threads: int, seed: int = 0, passes: int = 1, workload: str = "fr3_qpik", faithful: bool = False):
     """Time the CPU restatement (oracle port) of the workload on `threads` host threads.  faithful: the reference's per-cycle
     behaviour -- the whole workspace (solver data, scratch) heap-allocated and released every control cycle (QP_base.h:143-177,
@@ -565,6 +601,12 @@ def run_ours(args):
             "solved_fraction": float(np.mean(status == 1)), "mean_admm_iters": float(np.mean(iters))}
     if per_rank is not None:
         line["per_rank"] = per_rank
+    if world == 1 and args.workload == "fr3_qpik":
+        try:   # BASELINE configs[0] (batch 1): a latency pair, reported next to the throughput metric, never part of it
+            ctx.enable_timing(False)
+            line["latency_b1"] = latency_b1(ctx)
+        except Exception as e:
+            line["latency_b1"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and args.workload == "fr3_qpik" and not args.no_siblings:
         del ctx, flush
         torch.cuda.empty_cache()

@@ -344,6 +344,27 @@ struct Stage {
     outs.push_back({h, d, cnt * sizeof(int)});
     return d;
   }
+  // The solver launches write every result once, from the lane that owns it, and nothing on the device reads it back.  When the
+  // caller's buffer is page-locked host memory this device can address (cudaHostAlloc / cudaHostRegister under unified addressing),
+  // the fused cycle entry points hand the kernels its device alias: the results cross PCIe while the solve is still running instead
+  // of in a staged copy behind the last kernel.  Pageable buffers take the staged route.
+  template <class T>
+  static T* device_alias(T* h) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<T*>(at.devicePointer);
+  }
+  double* out_direct(double* h, size_t cnt) {
+    if (!h) return nullptr;
+    if (double* d = device_alias(h)) return d;
+    return out(h, cnt);
+  }
+  int* out_i_direct(int* h, size_t cnt) {
+    if (!h) return nullptr;
+    if (int* d = device_alias(h)) return d;
+    return out_i(h, cnt);
+  }
   double* take(size_t cnt) {
     if (used + cnt > c->stage_doubles) { err = DRC_E_NOMEM; return nullptr; }
     double* d = c->stage + used;

@@ -915,16 +915,16 @@ int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double*
   // q, qdot feed stage 1 (FK, self-collision); the targets are only read by the QP-build kernel: upload them behind stage 1
   const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
   st.late_done();
-  double* dout = st.out(qdot_out, Bz * n);
-  int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
+  double* dout = st.out_direct(qdot_out, Bz * n);
+  int *ds = st.out_i_direct(status, Bz), *di = st.out_i_direct(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpik_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
 }
 int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* tau_out, int* status, int* iters) {
   HOST_PRELUDE
   const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
   st.late_done();
-  double* dout = st.out(tau_out, Bz * n);
-  int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
+  double* dout = st.out_direct(tau_out, Bz * n);
+  int *ds = st.out_i_direct(status, Bz), *di = st.out_i_direct(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpid_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
 }
 

@@ -71,6 +71,7 @@ static int moma_qp(drc_ctx* c, int B, bool id, const double* q, const double* qd
   {
     cudaStream_t bs = c->build_stream;
     CU(cudaStreamWaitEvent(bs, c->ev_store, 0));
+    if (c->late_pending) { CU(cudaStreamWaitEvent(bs, c->ev_late, 0)); c->late_pending = false; }   // targets still uploading (host entry points)
     JobIO bio = io;
     if (id) {
       rc = launch_job<NV, false, K_ID, W>(c, fr, bio, bs); if (rc) return rc;
@@ -293,16 +294,19 @@ int drc_host_moma_qpid_step(drc_ctx_t* c, int B, const double* x_target, const d
 }
 int drc_host_moma_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* eta_out, int* status, int* iters) {
   MOMA_HOST_PRELUDE
-  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6);
-  double* dout = st.out(eta_out, Bz * a);
-  int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
+  // q, qdot feed stage 1 (joint placements, narrow phase); the targets are only read by the QP-build job: upload them behind stage 1
+  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
+  st.late_done();
+  double* dout = st.out_direct(eta_out, Bz * a);
+  int *ds = st.out_i_direct(status, Bz), *di = st.out_i_direct(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_moma_cycle_qpik_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
 }
 int drc_host_moma_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* tau_out, double* etadot_out, int* status, int* iters) {
   MOMA_HOST_PRELUDE
-  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6);
-  double *dout = st.out(tau_out, Bz * a), *dout2 = st.out(etadot_out, Bz * a);
-  int *ds = st.out_i(status, Bz), *di = st.out_i(iters, Bz);
+  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in_late(x_target, Bz * 12), *dx = st.in_late(xdot_target, Bz * 6);
+  st.late_done();
+  double *dout = st.out_direct(tau_out, Bz * a), *dout2 = st.out_direct(etadot_out, Bz * a);
+  int *ds = st.out_i_direct(status, Bz), *di = st.out_i_direct(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_moma_cycle_qpid_step(c, B, dq, dqd, dxt, dx, frame, dout, dout2, ds, di, DRC_LAYOUT_AOS, nullptr));
 }
 

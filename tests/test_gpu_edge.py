@@ -112,3 +112,22 @@ def test_whole_body_ragged_batches_and_nonfinite_inputs(robot, kind):
     assert np.array_equal(r["out"][good], full["out"][good]) and np.array_equal(r["iters"][good], full["iters"][good])
     assert (r["status"][bad] != 1).all()
     assert np.isfinite(r["out"][bad]).all() if kind == "ik" else True   # QPIK failure = zeros; QPID failure = gravity of a NaN state
+
+
+def test_page_locked_output_buffers_take_the_direct_route(gpu_ctx, oracle):
+    """Host entry points with page-locked result buffers: the solver launches store straight into them (device alias of the host
+    allocation) instead of a staged D2H copy; same bits as with pageable buffers, including the failure fallback rows."""
+    import torch
+    model, ctx = gpu_ctx
+    B = 8192
+    q, qd, x_t, xdot_t = _inputs(ctx, oracle, B, 23)
+    for call in (ctx.cycle_qpik_step, ctx.cycle_qpid_step):
+        ref = call(q, qd, x_t, xdot_t, LINK)
+        ref = {k: np.array(ref[k], copy=True) for k in ("out", "status", "iters")}
+        p_out = torch.full((B, 7), float("nan"), dtype=torch.float64).pin_memory()
+        p_st = torch.full((B,), -7, dtype=torch.int32).pin_memory()
+        p_it = torch.full((B,), -7, dtype=torch.int32).pin_memory()
+        r = call(q, qd, x_t, xdot_t, LINK, out=p_out.numpy(), status=p_st.numpy(), iters=p_it.numpy())
+        assert np.array_equal(p_out.numpy(), ref["out"]) and np.array_equal(p_st.numpy(), ref["status"])
+        assert np.array_equal(p_it.numpy(), ref["iters"])
+        assert r["out"] is not None
