@@ -131,3 +131,30 @@ def test_page_locked_output_buffers_take_the_direct_route(gpu_ctx, oracle):
         assert np.array_equal(p_out.numpy(), ref["out"]) and np.array_equal(p_st.numpy(), ref["status"])
         assert np.array_equal(p_it.numpy(), ref["iters"])
         assert r["out"] is not None
+
+
+@pytest.mark.parametrize("kind", ["ik", "id"])
+def test_whole_body_page_locked_outputs(kind):
+    """Same as above on the mobile-manipulator host entry points (targets uploaded behind stage 1, results stored directly)."""
+    import torch
+    import dyros_robot_controller_b200 as drc
+    from tests.conftest import MOMA, moma_workload
+    d = MOMA["husky_fr3"]
+    model = drc.Model(d["urdf"], d["srdf"]).attach_mobile_base(d["kin"], d["joint_idx"], d["actuator_idx"])
+    ctx = drc.Context(model, 4096, device=0)
+
+    class _M:
+        q_lo, q_hi, v_lim = model.q_lower, model.q_upper, model.v_limit
+    B, a = 4096, model.actuated_dof
+    q, qd, q_t, xdot_t = moma_workload(_M, model.wheel_num, B, 43)
+    ctx.moma_update_state(q_t, qd)
+    x_t = ctx.moma_get_state(LINK, want=("pose",))["pose"]
+    ref = ctx.moma_cycle(kind, q, qd, x_t, xdot_t, LINK)
+    ref = {k: (None if ref.get(k) is None else np.array(ref[k], copy=True)) for k in ("out", "etadot", "status", "iters")}
+    p_out, p_out2 = (torch.full((B, a), float("nan"), dtype=torch.float64).pin_memory() for _ in range(2))
+    p_st, p_it = (torch.full((B,), -7, dtype=torch.int32).pin_memory() for _ in range(2))
+    ctx.moma_cycle(kind, q, qd, x_t, xdot_t, LINK, out=p_out.numpy(), out2=p_out2.numpy(), status=p_st.numpy(), iters=p_it.numpy())
+    assert np.array_equal(p_out.numpy(), ref["out"]) and np.array_equal(p_st.numpy(), ref["status"])
+    assert np.array_equal(p_it.numpy(), ref["iters"])
+    if kind == "id":
+        assert np.array_equal(p_out2.numpy(), ref["etadot"])
