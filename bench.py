@@ -374,10 +374,8 @@ def run_ours(args):
     def cycle(a_q, a_qd, a_xt, a_xd, o_out, o_st, o_it, o_out2=None):
         if moma:
             ctx.moma_cycle(wl["kind"], a_q, a_qd, a_xt, a_xd, LINK, out=o_out, out2=o_out2, status=o_st, iters=o_it)
-        elif taskspace:   # config 2: updateState + CLIKStep (qdot*) + OSFStep (tau*), no QP
-            ctx.update_state(a_q, a_qd)
-            ctx.clik_step(a_xt, a_xd, link, out=o_out)
-            ctx.osf_step(a_xt, a_xd, link, out=o_out2)
+        elif taskspace:   # config 2: updateState + CLIKStep (qdot*) + OSFStep (tau*), no QP -- one launch
+            ctx.cycle_clik_osf_step(a_q, a_qd, a_xt, a_xd, link, out=o_out, out2=o_out2)
         elif wl["kind"] == "ik":
             ctx.cycle_qpik_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
         else:
@@ -664,9 +662,7 @@ def measure_sibling(name: str, B: int, local: int, peak: float, steps: int = 5, 
         if moma:
             ctx.moma_cycle(wl["kind"], a_q, a_qd, a_xt, a_xd, LINK, out=o_out, out2=o_out2, status=o_st, iters=o_it)
         elif taskspace:
-            ctx.update_state(a_q, a_qd)
-            ctx.clik_step(a_xt, a_xd, link, out=o_out)
-            ctx.osf_step(a_xt, a_xd, link, out=o_out2)
+            ctx.cycle_clik_osf_step(a_q, a_qd, a_xt, a_xd, link, out=o_out, out2=o_out2)
         elif wl["kind"] == "ik":
             ctx.cycle_qpik_step(a_q, a_qd, a_xt, a_xd, LINK, out=o_out, status=o_st, iters=o_it)
         else:

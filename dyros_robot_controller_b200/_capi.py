@@ -45,11 +45,11 @@ SYMBOLS = [
     "drc_batch_update_state", "drc_batch_get_frame", "drc_batch_get_dynamics", "drc_batch_get_manipulability",
     "drc_batch_get_min_distance", "drc_batch_qpik", "drc_batch_qpik_step", "drc_batch_qpid", "drc_batch_qpid_step",
     "drc_batch_clik_step", "drc_batch_osf", "drc_batch_osf_step", "drc_batch_joint_torque_step",
-    "drc_batch_task_space_cubic", "drc_batch_cycle_qpik_step", "drc_batch_cycle_qpid_step",
+    "drc_batch_task_space_cubic", "drc_batch_cycle_qpik_step", "drc_batch_cycle_qpid_step", "drc_batch_cycle_clik_osf_step",
     "drc_host_update_state", "drc_host_get_frame", "drc_host_get_dynamics", "drc_host_get_manipulability",
     "drc_host_get_min_distance", "drc_host_qpik", "drc_host_qpik_step", "drc_host_qpid", "drc_host_qpid_step",
     "drc_host_clik_step", "drc_host_osf", "drc_host_osf_step", "drc_host_joint_torque_step",
-    "drc_host_task_space_cubic", "drc_host_cycle_qpik_step", "drc_host_cycle_qpid_step",
+    "drc_host_task_space_cubic", "drc_host_cycle_qpik_step", "drc_host_cycle_qpid_step", "drc_host_cycle_clik_osf_step",
     "drc_ctx_enable_timing", "drc_ctx_last_timing", "drc_ctx_launch_count", "drc_bench_fp64_peak",
     "drc_ctx_last_trace", "drc_ctx_enable_qp_debug", "drc_host_get_qp_debug",
     "drc_model_attach_mobile_base", "drc_model_moma_info", "drc_model_base_jacobian",

@@ -339,6 +339,9 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
   // desired task-space signal
   DRC_PHASE(PH_BUILD);
   double des[6];
+  // fused CLIKStep + OSFStep (one job, two outputs): the two controllers form different desired signals from the same error
+  constexpr bool CLIK_AND_OSF = (FLAGS & F_CLIK) != 0 && (FLAGS & F_OSF) != 0;
+  double des_osf[6];
   if (FLAGS & (F_QPIK | F_QPID | F_CLIK | F_OSF)) {
     double xd_t[6];
 #pragma unroll
@@ -361,10 +364,11 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
         // MobileManipulator QPIKStep: Kp e + xdot_target as well (mobile_manipulator/robot_controller.cpp:181)
         constexpr bool no_kv = (FLAGS & F_CLIK) != 0 || (MOMA && (FLAGS & F_QPIK) != 0);
         des[r] = prm.Kp_task[r] * xe[r] + (no_kv ? xd_t[r] : prm.Kv_task[r] * (xd_t[r] - xdot[r]));
+        if (CLIK_AND_OSF) des_osf[r] = prm.Kp_task[r] * xe[r] + prm.Kv_task[r] * (xd_t[r] - xdot[r]);   // OSFStep (:238)
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) des[r] = xd_t[r];
+      for (int r = 0; r < 6; ++r) { des[r] = xd_t[r]; if (CLIK_AND_OSF) des_osf[r] = xd_t[r]; }
     }
   }
 
@@ -417,7 +421,7 @@ DRC_HD void robot_job(const DrcModelDev& m, const DrcParams& prm, const DrcFrame
     double y[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      double s = des[r];
+      double s = CLIK_AND_OSF ? des_osf[r] : des[r];
       if (io.aux) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) s -= JMi[r * NV + j] * io.aux[b * io.saux.sb + j * io.saux.sk];

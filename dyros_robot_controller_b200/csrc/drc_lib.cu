@@ -759,6 +759,26 @@ int drc_batch_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double
   QP_ENTRY(true, true, q, qdot, x_target, xdot_target, tau_out, nullptr)
 }
 
+// BASELINE config 2 as ONE job: updateState (state + dynamics -> cache) + CLIKStep (qdot*) + OSFStep (tau*) from the values the job
+// already holds in registers, instead of three launches that each redo the forward kinematics.  No null-space vectors (use the
+// separate entry points for those).
+int drc_batch_cycle_clik_osf_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target,
+                                  int frame, double* qdot_out, double* tau_out, int layout, void* stream) {
+  int rc = check_batch(c, B); if (rc) return rc;
+  rc = check_frame(c, frame); if (rc) return rc;
+  if (!q || !qdot || !x_target || !xdot_target || !qdot_out || !tau_out) return fail(DRC_E_INVALID, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->model->hm.dev.drive_type != kNoBase) return fail(DRC_E_UNSUPPORTED, "CLIK / OSF are manipulator controllers");
+  const int n = c->model->hm.dev.nv;
+  JobIO io; std::memset(&io, 0, sizeof io);
+  io.B = B; io.q = q; io.qd = qdot; io.sq = lay(layout, n, B); io.sqd = io.sq;
+  io.x_target = x_target; io.sxt = lay(layout, 12, B); io.xdot_target = xdot_target; io.sxd = lay(layout, 6, B);
+  io.out = qdot_out; io.out2 = tau_out; io.sout = lay(layout, n, B); io.saux = io.sout; io.saux2 = io.sout;
+  bind_cache(c, io);
+  const DrcFrame fr = frame_of(c->model, frame);
+  DRC_DISPATCH_NV(n, c->model->hm.chain, return (launch_job<NV, CHAIN, F_DYN | F_STORE | F_CLIK | F_OSF | F_STEP>(c, fr, io, pick(c, stream))));
+}
+
 // T control ticks of QPIKCubic / QPIKStep + the integrate step, without a host round trip between ticks
 int drc_batch_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,
                            const double* xdot_target, const double* x_init, const double* xdot_init, double t_start, double t0,
@@ -926,6 +946,13 @@ int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double*
   double* dout = st.out_direct(tau_out, Bz * n);
   int *ds = st.out_i_direct(status, Bz), *di = st.out_i_direct(iters, Bz);
   return st.finish(st.err ? st.err : drc_batch_cycle_qpid_step(c, B, dq, dqd, dxt, dx, frame, dout, ds, di, DRC_LAYOUT_AOS, nullptr));
+}
+
+int drc_host_cycle_clik_osf_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target, const double* xdot_target, int frame, double* qdot_out, double* tau_out) {
+  HOST_PRELUDE
+  const double *dq = st.in(q, Bz * n), *dqd = st.in(qdot, Bz * n), *dxt = st.in(x_target, Bz * 12), *dx = st.in(xdot_target, Bz * 6);
+  double *dout = st.out_direct(qdot_out, Bz * n), *dout2 = st.out_direct(tau_out, Bz * n);
+  return st.finish(st.err ? st.err : drc_batch_cycle_clik_osf_step(c, B, dq, dqd, dxt, dx, frame, dout, dout2, DRC_LAYOUT_AOS, nullptr));
 }
 
 int drc_host_rollout_qpik(drc_ctx_t* c, int B, int T, double dt, double* q, double* qdot, const double* x_target,

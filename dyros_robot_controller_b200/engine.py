@@ -481,6 +481,34 @@ class Context:
         self._B = B
         return dict(out=out, status=status, iters=iters)
 
+    def cycle_clik_osf_step(self, q, qdot, x_target, xdot_target, link, out=None, out2=None):
+        """updateState + CLIKStep (qdot*, `out`) + OSFStep (tau*, `out2`) as ONE launch (BASELINE config 2), no null-space vectors.
+        numpy in -> numpy out (host path); torch CUDA in -> torch out (async).  Leaves the full state cache like update_state."""
+        f = self._frame(link)
+        if _is_torch(q):
+            import torch
+            q, B = self._t_in(q, self.n)
+            qd, _ = self._t_in(qdot, self.n, B)
+            xt, _ = self._t_in(x_target, 12, B)
+            xd, _ = self._t_in(xdot_target, 6, B)
+            out = torch.empty((B, self.n), dtype=torch.float64, device=q.device) if out is None else out
+            out2 = torch.empty((B, self.n), dtype=torch.float64, device=q.device) if out2 is None else out2
+            check(lib().drc_batch_cycle_clik_osf_step(self._h, B, self._tp(q), self._tp(qd), self._tp(xt), self._tp(xd), f,
+                                                      self._tp(out), self._tp(out2), _capi.LAYOUT_AOS, self._stream()),
+                  "drc_batch_cycle_clik_osf_step")
+            self._B = B
+            return dict(qdot=out, tau=out2)
+        q, B = self._np_in(q, self.n)
+        qd, _ = self._np_in(qdot, self.n, B)
+        xt, _ = self._np_in(pose12(x_target), 12, B)
+        xd, _ = self._np_in(xdot_target, 6, B)
+        out = np.zeros((B, self.n)) if out is None else out
+        out2 = np.zeros((B, self.n)) if out2 is None else out2
+        check(lib().drc_host_cycle_clik_osf_step(self._h, B, self._p(q), self._p(qd), self._p(xt), self._p(xd), f, self._p(out),
+                                                 self._p(out2)), "drc_host_cycle_clik_osf_step")
+        self._B = B
+        return dict(qdot=out, tau=out2)
+
     def rollout_qpik(self, q, qdot, x_target, xdot_target, link, ticks, dt, x_init=None, xdot_init=None, t_start=0.0, t0=0.0,
                      duration=0.0):
         """Closed-loop rollout: `ticks` control cycles of updateState + QPIKCubic (duration > 0) / QPIKStep, each followed by

@@ -141,6 +141,10 @@ int drc_batch_osf_step(drc_ctx_t* c, int B, const double* x_target, const double
                        int frame, double* tau_out, int layout, void* stream);
 int drc_batch_joint_torque_step(drc_ctx_t* c, int B, const double* q_target, const double* qdot_target, double* tau_out,
                                 int layout, void* stream);
+/* BASELINE config 2 fused: updateState (src/manipulator/robot_data.cpp:91-124) + CLIKStep (robot_controller.cpp:156-171, no
+ * null-space velocity) + OSFStep (:232-240, no null-space torque) in ONE launch; leaves the same state cache as drc_batch_update_state */
+int drc_batch_cycle_clik_osf_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                  const double* xdot_target, int frame, double* qdot_out, double* tau_out, int layout, void* stream);
 /* DyrosMath::getTaskSpaceCubic (include/math_type_define.h:647-685) for per-robot targets and a common time */
 int drc_batch_task_space_cubic(drc_ctx_t* c, int B, const double* x_target, const double* xdot_target, const double* x_init,
                                const double* xdot_init, double t, double t0, double duration, double* x_des,
@@ -194,6 +198,8 @@ int drc_host_cycle_qpik_step(drc_ctx_t* c, int B, const double* q, const double*
                              const double* xdot_target, int frame, double* qdot_out, int* status, int* iters);
 int drc_host_cycle_qpid_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
                              const double* xdot_target, int frame, double* tau_out, int* status, int* iters);
+int drc_host_cycle_clik_osf_step(drc_ctx_t* c, int B, const double* q, const double* qdot, const double* x_target,
+                                 const double* xdot_target, int frame, double* qdot_out, double* tau_out);
 
 /* ---- mobile base + mobile manipulator (reference src/mobile/robot_data.cpp, src/mobile_manipulator/*.cpp).
  * Attach the base to a compiled URDF model BEFORE creating contexts: replaces the Mobile::RobotData(KinematicParam) and
