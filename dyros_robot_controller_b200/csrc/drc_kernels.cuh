@@ -338,7 +338,7 @@ static __device__ __forceinline__ int sched_bucket_of(int iters) {
 #endif
 constexpr int kAdmmWarps = DRC_ADMM_WARPS;  // one warp per block: a finished warp frees its slot without waiting for block-mates
 #ifndef DRC_ADMM_MINBLOCKS   // lab builds measure other register budgets (blocks per SM; 12 = 168 registers)
-#define DRC_ADMM_MINBLOCKS ((4 * MINB) / kAdmmWarps)
+#define DRC_ADMM_MINBLOCKS (MINB >= 8 ? MINB : (4 * MINB) / kAdmmWarps)   // MINB >= 8: blocks per SM given directly
 #endif
 template <class Cfg, bool ID, int MINB>
 __global__ void __launch_bounds__(kAdmmWarps * 32, DRC_ADMM_MINBLOCKS) k_admm(const __grid_constant__ SolveIO io, const __grid_constant__ QpOptions o) {
