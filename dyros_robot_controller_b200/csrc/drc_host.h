@@ -260,8 +260,7 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
   io.qp_x = c->dbg_x; io.qp_y = c->dbg_y;
   if (c->warm_on && !ID) { io.qp_x = c->ws_x; io.qp_y = c->ws_y; io.warm_x = c->ws_x; io.warm_y = c->ws_y; }
   if (c->roll_q && !io.roll_q) { io.roll_q = c->roll_q; io.roll_qd = c->roll_qd; io.sroll = c->sroll; io.roll_dt = c->roll_dt; io.fail_ticks = c->roll_fail; io.iters_total = c->roll_iters; }
-  // one instantiation per QP shape.  Register budget: 12 warps / SM = 168 registers for the QPIK shapes (measured best of 208 / 168 /
-  // 128); 8 warps / SM = 255 registers for the QPID shapes -- with 4 unit bundles per core lane they spill 1.4 KB under the
+  // one instantiation per QP shape.  Register budget: 12 warps / SM = 168 registers for the whole-body QPIK shapes; 8 warps / SM = 255 registers for the QPID shapes -- with 4 unit bundles per core lane they spill 1.4 KB under the
   // 168-register cap and the spill traffic + a code size beyond the instruction cache made `long_scoreboard` and `no_instruction`
   // the top stalls (ncu, profiles/r02c_ncu_summary_siblings.md): same-box A/B 7.97e6 -> 1.37e7 FR3 QPID cycles/s
   // (profiles/r02c_lab_variants_qpid_registers.txt).  The dynamic shared-memory opt-in is a per-device
@@ -271,7 +270,14 @@ static int launch_admm(drc_ctx* c, SolveIO io, cudaStream_t s, unsigned unit_mas
 #ifndef DRC_ADMM_MINB_ID
 #define DRC_ADMM_MINB_ID 8   // blocks (= warps) per SM of the QPID solver launches
 #endif
-  constexpr int MB = ID ? DRC_ADMM_MINB_ID : 3;
+#ifndef DRC_ADMM_MINB_IK
+#define DRC_ADMM_MINB_IK 8   // manipulator QPIK: ptxas settles at 202 registers without a spill -> 9 warps / SM
+#endif
+  // manipulator QPIK (slack formulation): its step ends with the slowest robots' serial iterations, and the spill-free build
+  // shortens them -- same-box A/B 2.29 -> 2.39e7 cycles/s with the schedule hint (1.60 -> 1.53e7 without it, where the bulk's
+  // occupancy counts; profiles/r02c_lab_variants_qpik_registers.txt).  The whole-body QPIK shapes run at 262 144 ... 1 M robots,
+  // where throughput counts: they keep 12 warps / SM.
+  constexpr int MB = ID ? DRC_ADMM_MINB_ID : (Cfg::SLACK ? DRC_ADMM_MINB_IK : 3);
   CU(cudaFuncSetAttribute(k_admm<Cfg, ID, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_admm<Cfg, ID, MB><<<blocks, kAdmmWarps * 32, smem, s>>>(io, o);
   c->launches++;
